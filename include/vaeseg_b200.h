@@ -1,0 +1,162 @@
+/*
+ * vaeseg_b200 -- C ABI of the B200-native training hot path of yyNoBug/VAE_segmentation.
+ *
+ * The reference has no FFI of its own (it is pure PyTorch): each entry
+ * point below replaces the library kernel that the cited reference line reaches through
+ * torch.nn on the hot path.  Host side (vae_segmentation_b200/*.py) binds these with ctypes.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (PyTorch caching allocator);
+ *    the library allocates no device memory.
+ *  - activations are NDHWC ("channels last"), dtype selected by `dtype`:
+ *      VS_F32  (check mode: fp32 storage, fp32 accumulate)   VS_BF16 (bf16 storage, fp32 accumulate)
+ *    tensors called "planar" are NCDHW fp32 (the nn.Module boundary layout).
+ *  - parameters and parameter gradients are fp32 in PyTorch's own layouts
+ *    (Conv3d [Cout,Cin,kD,kH,kW], ConvTranspose3d [Cin,Cout,2,2,2], Linear [out,in]).
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), performs no
+ *    host synchronisation and is CUDA-graph capturable.
+ *  - return value: 0 on success, negative vs_status otherwise; vs_last_error_string()
+ *    describes the last failure on the calling thread.  There is no CPU fallback.
+ */
+#ifndef VAESEG_B200_H
+#define VAESEG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum { VS_OK = 0, VS_ERR_SHAPE = -1, VS_ERR_UNSUPPORTED = -2, VS_ERR_ALIGN = -3, VS_ERR_CUDA = -4 } vs_status;
+typedef enum { VS_F32 = 0, VS_BF16 = 1 } vs_dtype;
+
+const char* vs_last_error_string(void);
+int vs_version(void);
+/* 1 when the library was built with the tcgen05/TMA (sm_100a) conv kernels */
+int vs_has_tcgen05(void);
+
+/* ---- weight repacking (derived caches of the fp32 master weights) ------------------- */
+/* Conv3d 3x3x3 weight [Cout,Cin,27] -> wf[27][Cin][Cout] (fprop) and, when wd != NULL,
+ * wd[27 (flipped)][Cout][Cin] (dgrad operand).  joint_model.py:40,43,46,106,224,366 */
+int vs_pack_conv3_weight(const float* w, float* wf, float* wd, int cin, int cout, void* stream);
+
+/* ---- 3x3x3 convolution, padding 1 (Conv3d at joint_model.py:40-46,106,224,366) ------- */
+/* x: NDHWC `in_dtype` (or planar fp32 when in_planar=1, used by the in_blocks whose input is
+ * the module's NCDHW fp32 tensor); wpk: fp32 [27][Cin][Cout]; bias fp32 [Cout] or NULL;
+ * y: NDHWC `out_dtype` (or planar fp32 when out_planar=1); stats: fp32 [N][Cout][2]
+ * (sum, sum of squares of the fp32 accumulators; zeroed by the call) or NULL.            */
+int vs_conv3x3x3_fprop(int in_dtype, int out_dtype, int in_planar, int out_planar,
+                       const void* x, const float* wpk, const float* bias, void* y, float* stats,
+                       int n, int d, int h, int w, int cin, int cout, void* stream);
+/* dgrad is the same contraction with the flipped/transposed pack (wd of vs_pack_conv3_weight):
+ * dx = conv3(dy, wd), Cin/Cout swapped.  Provided as its own symbol for the binding's clarity. */
+int vs_conv3x3x3_dgrad(int in_dtype, int out_dtype, int out_planar,
+                       const void* dy, const float* wdpk, void* dx,
+                       int n, int d, int h, int w, int cin, int cout, void* stream);
+/* dw[Cout,Cin,27] (+)= sum_v dy[v,co] * x[v+tap,ci]; db[Cout] (+)= sum_v dy (db may be NULL).
+ * x may be planar fp32 (in_planar=1).  accumulate=0 overwrites.  workspace: fp32
+ * vs_conv3_wgrad_workspace_bytes() bytes (partial sums).                                 */
+size_t vs_conv3_wgrad_workspace_bytes(int n, int d, int h, int w, int cin, int cout);
+int vs_conv3x3x3_wgrad(int dtype, int in_planar, const void* x, const void* dy, float* dw, float* db,
+                       void* workspace, size_t ws_bytes, int accumulate,
+                       int n, int d, int h, int w, int cin, int cout, void* stream);
+
+/* ---- 2x2x2 stride-2 convolution and transposed convolution (joint_model.py:118,130) --- */
+/* Both layers are one of two contractions over a weight viewed as wt[A][B][8]:
+ *   gather : coarse[o, a] = bias[a] + sum_{k,b} wt[a][b][k] * fine[2o+k, b]
+ *   scatter: fine[2o+k, b] = bias[b] + sum_a    wt[a][b][k] * coarse[o, a]
+ * Conv3d(k2,s2)       : fprop = gather (A=Cout,B=Cin), dgrad = scatter.
+ * ConvTranspose3d(k2) : fprop = scatter (A=Cin,B=Cout), dgrad = gather.
+ * (dc,hc,wc) are the COARSE spatial dims; the fine tensor is (2dc,2hc,2wc).            */
+int vs_k2s2_gather(int dtype, const void* fine, const float* wt, const float* bias, void* coarse,
+                   int n, int dc, int hc, int wc, int a, int b, void* stream);
+int vs_k2s2_scatter(int dtype, const void* coarse, const float* wt, const float* bias, void* fine,
+                    int n, int dc, int hc, int wc, int a, int b, void* stream);
+/* dwt[A][B][8] (+)= sum_o coarse[o,a]*fine[2o+k,b]; optional bias grads over either side. */
+int vs_k2s2_wgrad(int dtype, const void* coarse, const void* fine, float* dwt,
+                  float* dbias_coarse, float* dbias_fine, int accumulate,
+                  int n, int dc, int hc, int wc, int a, int b, void* stream);
+
+/* ---- InstanceNorm3d(affine=False, eps 1e-5) + ReLU (joint_model.py:9-15,38,104) ------- */
+/* a = relu((y-mean)*rstd) [+ skip]; mean/rstd derived from stats[N][C][2] over `s` voxels.  */
+int vs_inorm_relu_apply(int dtype, const void* y, const float* stats, const void* skip, void* a,
+                        int n, long long s, int c, void* stream);
+/* sums[N][C][2] = (sum g*mask, sum g*mask*xhat) with mask = [y > mean]; zeroed by the call. */
+int vs_inorm_relu_bwd_reduce(int dtype, const void* g, const void* y, const float* stats, float* sums,
+                             int n, long long s, int c, void* stream);
+/* dy = rstd * (g*mask - sums0/s - xhat * sums1/s)                                         */
+int vs_inorm_relu_bwd_apply(int dtype, const void* g, const void* y, const float* stats, const float* sums,
+                            void* dy, int n, long long s, int c, void* stream);
+/* dst += src (gradient fan-in at the additive skips, joint_model.py:381,383)               */
+int vs_add_inplace(int dtype, void* dst, const void* src, long long count, void* stream);
+
+/* ---- softmax over n_class=2 (joint_model.py:225,367) ---------------------------------- */
+/* logits: NDHWC fp32 [N][S][2]; probs: planar fp32 [N][2][S]                               */
+int vs_softmax2_fwd(const float* logits, float* probs, int n, long long s, void* stream);
+/* dlogits (NDHWC `dtype`) from planar dprobs and saved planar probs                        */
+int vs_softmax2_bwd(int dtype, const float* dprobs, const float* probs, void* dlogits,
+                    int n, long long s, void* stream);
+
+/* ---- Linear layers + reparameterisation of the VAE (joint_model.py:216-218,241-250) --- */
+/* x: NDHWC `dtype` [B][S3][C] read in the reference's NCDHW flatten order i = c*S3 + v.
+ * mean = Wm x + bm; std = relu(Ws x + bs); lat = mean + z*std*scale (use_z) or mean.       */
+int vs_fc_encode_fwd(int dtype, const void* x, const float* wm, const float* bm, const float* ws,
+                     const float* bs, const float* z, float scale, int use_z,
+                     float* mean, float* std, float* lat, int batch, int s3, int c, int dim, void* stream);
+/* h = W2 lat + b2 written NDHWC `dtype` [B][S3][C]                                         */
+int vs_fc_decode_fwd(int dtype, const float* lat, const float* w2, const float* b2, void* h,
+                     int batch, int s3, int c, int dim, void* stream);
+/* dlat[B][dim] = dh W2 ; dw2/db2 (+)= when non-NULL                                        */
+int vs_fc_decode_bwd(int dtype, const void* dh, const float* lat, const float* w2, float* dlat,
+                     float* dw2, float* db2, int accumulate, int batch, int s3, int c, int dim, void* stream);
+/* gm = dlat + gmean_ext ; gs = (dlat*z*scale*use_z + gstd_ext) * [std>0]   (ext may be NULL)
+ * dx = gm Wm + gs Ws (NDHWC `dtype`); dwm/dbm/dws/dbs (+)= when non-NULL.
+ * gbuf: fp32 scratch [2][B][dim].                                                          */
+int vs_fc_encode_bwd(int dtype, const void* x, const float* wm, const float* ws, const float* z,
+                     float scale, int use_z, const float* std, const float* dlat,
+                     const float* gmean_ext, const float* gstd_ext, float* gbuf, void* dx,
+                     float* dwm, float* dbm, float* dws, float* dbs, int accumulate,
+                     int batch, int s3, int c, int dim, void* stream);
+
+/* ---- losses (utils/evaluation.py:6-18,42-80; main_source.py:150-182) ------------------ */
+typedef enum { VS_TGT_TENSOR = 0, VS_TGT_BINARIZE = 1, VS_TGT_CONFIDENT = 2, VS_TGT_LABEL = 3,
+               VS_TGT_ARGMAX = 4 } vs_target_mode;
+/* sums[N][C][3] = (sum s*t', sum s', sum t') over voxels, with t' = f_mode(t):
+ *   TENSOR t, BINARIZE [t>=.5], CONFIDENT (t>.8 ->1, t<.2 ->0), LABEL onehot of label[N][1][S]
+ *   (fp32 class index), ARGMAX: both s and t replaced by onehot(argmax) (binary=True).
+ * src, tgt planar fp32 [N][C][S].  zeroed by the call.                                     */
+int vs_dice_sums(const float* src, const float* tgt, int mode, float* sums,
+                 int n, int c, long long s, void* stream);
+/* gsrc = gper[n,c]*(2 t' D - 2I)/D^2, gtgt = gper[n,c]*(2 s D - 2I)/D^2, D = S+T+eps;
+ * gsrc/gtgt may be NULL; accumulate adds into them.                                        */
+int vs_dice_bwd(const float* src, const float* tgt, int mode, const float* sums, const float* gper,
+                float eps, float* gsrc, float* gtgt, int accumulate,
+                int n, int c, long long s, void* stream);
+/* out[0] = mean_b 0.5*(sum std^2 + sum mean^2 - 2 sum log(std+1e-5))                       */
+int vs_kl_fwd(const float* mean, const float* std, float* out, int batch, int dim, void* stream);
+int vs_kl_bwd(const float* mean, const float* std, const float* gout, float* gmean, float* gstd,
+              int batch, int dim, void* stream);
+/* elementwise thresholding: mode BINARIZE or CONFIDENT                                     */
+int vs_binarize(const float* a, float* out, int mode, long long count, void* stream);
+/* label[N][1][S] (fp32 class index) -> planar one-hot [N][C][S] (main_target.py:520-522)   */
+int vs_one_hot(const float* label, float* out, int n, int c, long long s, void* stream);
+
+/* ---- optimiser / teacher update on flat fp32 arenas (main_target.py:347-352,512-516) --- */
+/* SGD(momentum, dampening 0, no wd, no nesterov): first!=0 initialises buf=g.  gscale scales g. */
+int vs_sgd_step(float* p, const float* g, float* buf, long long count, float lr, float momentum,
+                int first, float gscale, void* stream);
+int vs_adam_step(float* p, const float* g, float* m, float* v, long long count, float lr, float beta1,
+                 float beta2, float eps, int step, float gscale, void* stream);
+/* teacher = alpha*teacher + (1-alpha)*student                                              */
+int vs_ema_update(float* teacher, const float* student, long long count, float alpha, void* stream);
+/* device-side loss composition for the target-domain step incl. dynamic lambda (type 8,
+ * main_target.py:550-560) without a host sync: terms = (recon_loss, dsc_loss_fake, klloss);
+ * writes final loss and the two scalar weights (d final/d recon, d final/d fake, d final/d kl). */
+int vs_compose_target_loss(const float* terms, float lambda_vae, int loss_type, int use_kl,
+                           float* final_loss, float* weights, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VAESEG_B200_H */

@@ -1,0 +1,60 @@
+"""CPU-side checks of the drop-in module surface: state_dict layout, initialisation stream,
+layer programs (no kernels run here)."""
+import torch
+
+from oracle import ref_torch as R
+from vae_segmentation_b200 import engine, joint_model
+
+
+def test_segmentation_state_dict_matches_reference_layout_and_init():
+    torch.manual_seed(3)
+    seg = joint_model.Segmentation(1, 2, norm_type=1)
+    torch.manual_seed(3)
+    sd = R.init_seg_state()
+    msd = seg.state_dict()
+    assert list(msd.keys()) == list(sd.keys()) and len(msd) == 68
+    assert all(torch.equal(msd[k], sd[k]) for k in sd)
+    assert sum(p.numel() for p in seg.parameters()) == 2276018
+    seg.load_state_dict(sd, strict=True)
+
+
+def test_vae_state_dict_matches_reference_layout_and_init():
+    torch.manual_seed(4)
+    vae = joint_model.VAE(2, 2, norm_type=1, dim=128)
+    torch.manual_seed(4)
+    sd = R.init_vae_state(2, 128, 128)
+    msd = vae.state_dict()
+    assert list(msd.keys()) == list(sd.keys()) and len(msd) == 90
+    assert all(torch.equal(msd[k], sd[k]) for k in sd)
+    assert sum(p.numel() for p in vae.parameters()) == 15434378
+    assert msd["fc_mean.weight"].shape == (128, 16384)
+    assert joint_model.VAE(2, 2, norm_type=1, dim=128, patch=96).fc2.weight.shape == (6912, 128)
+
+
+def test_joint_wrapper_attribute_names():
+    j = joint_model.Joint([joint_model.Segmentation(1, 2, norm_type=1), joint_model.VAE(2, 2, norm_type=1, dim=128)])
+    assert len(j.state_dict()) == 158
+    assert all(k.startswith(("Seg.", "Vae.")) for k in j.state_dict())
+    names = [n for n, _ in j.Vae.named_parameters()]
+    assert any(n.startswith("fc_mean") for n in names) and any(n.startswith("down5") for n in names)
+    assert hasattr(j.Seg, "up5") and hasattr(j.Seg, "out_block")
+
+
+def test_layer_programs():
+    seg = joint_model.Segmentation(1, 2, norm_type=1)
+    layers, params = seg._prog()
+    kinds = [l.kind for l in layers]
+    assert kinds.count(engine.C3IN) == 25 and kinds.count(engine.K2DOWN) == 4
+    assert kinds.count(engine.K2UP) == 4 and kinds[-1] == engine.HEAD
+    assert [l.save_as for l in layers if l.save_as] == ["x2", "x3"]
+    assert [l.skip_from for l in layers if l.skip_from] == ["x3", "x2"]
+    for l in layers:
+        w = params[l.wi]
+        if l.kind in (engine.C3IN, engine.HEAD):
+            assert tuple(w.shape) == (l.cout, l.cin, 3, 3, 3)
+        else:
+            assert tuple(w.shape) == (l.cin, l.cout, 2, 2, 2) and l.cin == l.cout
+    vae = joint_model.VAE(2, 2, norm_type=1, dim=128, patch=64)
+    (enc, dec, fc), vparams = vae._prog()
+    assert len(enc) == 1 + 5 * 4 and len(dec) == 5 * 4 + 1
+    assert tuple(vparams[fc[0]].shape) == (128, 2048)

@@ -1,0 +1,144 @@
+"""Pins the CPU oracle (oracle/ref_torch.py): against the golden fixtures generated from the
+REAL reference (tests/golden/, oracle/make_golden.py) and, when /root/reference is present
+(authoring container), against the real reference modules executed live."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import make_golden as MG
+from oracle import ref_torch as R
+from oracle import reference_shim
+
+
+def _summary(grads):
+    return MG.grad_summary(grads)
+
+
+def _close(a, b, rtol, atol):
+    np.testing.assert_allclose(np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64), rtol=rtol, atol=atol)
+
+
+def test_losses_match_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "losses.npz"))
+    a, t = torch.from_numpy(g["a"]), torch.from_numpy(g["t"])
+    mean, std = torch.from_numpy(g["mean"]), torch.from_numpy(g["std"])
+    _close(R.avg_dsc(a, t), g["dsc_full"], 1e-6, 0)
+    _close(R.avg_dsc(a, t, botindex=1, topindex=2), g["dsc_fg"], 1e-6, 0)
+    _close(R.avg_dsc(a, t, botindex=1, topindex=2, return_mean=False), g["dsc_fg_vec"], 1e-6, 0)
+    _close(R.avg_dsc(a, t, binary=True, botindex=1, topindex=2), g["dsc_binary"], 1e-6, 0)
+    _close(R.kl_loss(mean, std), g["kl"], 1e-6, 0)
+    _close(R.dice(a, t), g["dice"], 1e-6, 0)
+    assert np.array_equal(R.binarize(a).numpy(), g["binarize"])
+    assert np.array_equal(R.confident_binarize(a).numpy(), g["confident"])
+
+
+def test_seg_train_step_matches_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "seg_p32.npz"))
+    seg_sd, _, img, label = MG.case_inputs(MG.SEG_CASE, seg=True)
+    loss, grads, pred = R.seg_train_step(seg_sd, img, label, eps=0.000001)
+    _close(loss, g["loss"], 1e-5, 0)
+    _close(MG.sample(pred), g["probs_sample"], 1e-4, 1e-6)
+    _close(pred.sum((2, 3, 4)), g["probs_sum"], 1e-5, 0)
+    assert list(grads.keys()) == list(g["grad_names"])
+    _close(_summary(grads), g["grad_summary"], 2e-3, 2e-6)
+
+
+@pytest.mark.timeout(600)
+def test_vae_train_step_matches_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "vae_p128.npz"))
+    _, vae_sd, _, label = MG.case_inputs(MG.VAE_CASE, vae=True)
+    torch.manual_seed(MG.VAE_CASE["seed"] + 1000)
+    loss, dsc, kl, grads, recon = R.vae_train_step(vae_sd, label, scale=0.35, eps=0.000001)
+    _close(loss, g["loss"], 1e-5, 0)
+    _close(kl, g["kl"], 1e-5, 0)
+    _close(dsc, g["dsc"], 1e-5, 0)
+    _close(MG.sample(recon, 5), g["recon_sample"], 1e-4, 1e-6)
+    _close(_summary(grads), g["grad_summary"], 5e-3, 5e-6)
+
+
+@pytest.mark.timeout(600)
+def test_joint_step_matches_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "joint_p128.npz"))
+    seg_sd, vae_sd, img, label = MG.case_inputs(MG.JOINT_CASE, vae=True, seg=True)
+    out, grads = R.joint_target_step(seg_sd, vae_sd, seg_sd, img, label, lambda_vae=1.0, loss_type=0)
+    for k in ("final", "recon_loss", "dsc_loss", "dsc_loss_fake", "klloss"):
+        _close(out[k], g[k], 2e-5, 0)
+    _close(MG.sample(out["pred"], 5), g["pred_sample"], 1e-4, 1e-6)
+    _close(MG.sample(out["recon"], 5), g["recon_sample"], 1e-4, 1e-6)
+    _close(_summary(grads), g["grad_summary"], 5e-3, 5e-6)
+
+
+def test_dynamic_lambda_composition():
+    # main_target.py:550-560
+    one = torch.tensor
+    for recon, lam, want in ((0.10, 1.0, 0.6 * 0.10 + 0.5), (0.20, 1.0, 0.20 + 0.5 / 1.2),
+                             (0.25, 1.0, 0.25 + 0.5 / 2.0), (0.40, 0.2, 0.6 * 0.40 + 0.5)):
+        got = R.compose_target_loss(one(recon), one(0.5), one(3.0), lambda_vae=lam, loss_type=8)
+        assert abs(float(got) - want) < 1e-6
+    got = R.compose_target_loss(one(0.2), one(0.5), one(3.0), lambda_vae=2.0, loss_type=0, kl=True)
+    assert abs(float(got) - (2.0 * 0.2 + 0.5 + 0.00002 * 2.0 * 3.0)) < 1e-6
+
+
+def test_sgd_and_ema_match_torch():
+    torch.manual_seed(0)
+    p = {"a": torch.randn(5), "b": torch.randn(3, 2)}
+    params = [torch.nn.Parameter(v.clone()) for v in p.values()]
+    opt = torch.optim.SGD(params, lr=1e-2, momentum=0.9)
+    sd, bufs = dict(p), None
+    for _ in range(3):
+        grads = {k: torch.randn_like(v) for k, v in sd.items()}
+        for q, g in zip(params, grads.values()):
+            q.grad = g.clone()
+        opt.step()
+        sd, bufs = R.sgd_step(sd, grads, bufs, lr=1e-2, momentum=0.9)
+    for q, v in zip(params, sd.values()):
+        assert torch.allclose(q.detach(), v, atol=1e-7)
+    e = R.ema_update({"a": torch.ones(2)}, {"a": torch.zeros(2)}, alpha=0.995)
+    assert torch.allclose(e["a"], torch.full((2,), 0.995))
+
+
+needs_ref = pytest.mark.skipif(not reference_shim.available(), reason="reference tree not present")
+
+
+@needs_ref
+def test_oracle_equals_real_reference_seg_and_init():
+    jm, ev = reference_shim.load()
+    torch.manual_seed(7)
+    seg = jm.Segmentation(1, 2, norm_type=1)
+    torch.manual_seed(7)
+    sd = R.init_seg_state()
+    ref_sd = seg.state_dict()
+    assert list(ref_sd.keys()) == list(sd.keys())
+    assert all(torch.equal(ref_sd[k], sd[k]) for k in sd)
+    x = torch.randn(1, 1, 32, 32, 32).clamp(-1, 1)
+    with torch.no_grad():
+        ref = seg({"i": x}, "i", "o")["o"]
+        mine = R.seg_forward(sd, x)
+    assert torch.equal(ref, mine)
+
+
+@needs_ref
+@pytest.mark.timeout(600)
+def test_oracle_equals_real_reference_vae_and_losses():
+    jm, ev = reference_shim.load()
+    torch.manual_seed(8)
+    vae = jm.VAE(2, 2, norm_type=1, dim=128)
+    torch.manual_seed(8)
+    sd = R.init_vae_state(2, 128, 128)
+    assert all(torch.equal(v, sd[k]) for k, v in vae.state_dict().items())
+    x = R.one_hot((torch.rand(1, 1, 128, 128, 128) > 0.9).float())
+    with torch.no_grad():
+        torch.manual_seed(9)
+        ref, rm, rs = vae(x, if_random=True, scale=0.35)
+        torch.manual_seed(9)
+        mine, mm, ms = R.vae_forward(sd, x, if_random=True, scale=0.35)
+    assert torch.equal(ref, mine) and torch.equal(rm, mm) and torch.equal(rs, ms)
+    d = {"a": ref, "b": x, "mean": rm, "std": rs}
+    assert torch.equal(ev.avg_dsc(d, "a", "b", botindex=1, topindex=2), R.avg_dsc(ref, x, botindex=1, topindex=2))
+    assert torch.equal(ev.KLloss(d), R.kl_loss(rm, rs))
+    # generalised flat dim: P=64 runs through the restatement (the real VAE cannot)
+    sd64 = R.init_vae_state(2, 128, 64)
+    out, _, _ = R.vae_forward(sd64, R.one_hot((torch.rand(1, 1, 64, 64, 64) > 0.9).float()))
+    assert out.shape == (1, 2, 64, 64, 64)

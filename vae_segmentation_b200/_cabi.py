@@ -1,0 +1,85 @@
+"""ctypes binding of libvaeseg_b200.so (declared in include/vaeseg_b200.h).
+
+The shared library is built in-tree by csrc/build.sh (see __graft_entry__.build).  There is
+no fallback: if the library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_longlong, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libvaeseg_b200.so")
+
+VS_F32, VS_BF16 = 0, 1
+TGT_TENSOR, TGT_BINARIZE, TGT_CONFIDENT, TGT_LABEL, TGT_ARGMAX = 0, 1, 2, 3, 4
+
+_P, _I, _L, _F, _Z = c_void_p, c_int, c_longlong, c_float, c_size_t
+
+# name -> argtypes (restype is int unless listed in _RESTYPES)
+_SIGNATURES = {
+    "vs_last_error_string": [],
+    "vs_version": [],
+    "vs_has_tcgen05": [],
+    "vs_pack_conv3_weight": [_P, _P, _P, _I, _I, _P],
+    "vs_conv3x3x3_fprop": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "vs_conv3x3x3_dgrad": [_I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "vs_conv3_wgrad_workspace_bytes": [_I, _I, _I, _I, _I, _I],
+    "vs_conv3x3x3_wgrad": [_I, _I, _P, _P, _P, _P, _P, _Z, _I, _I, _I, _I, _I, _I, _I, _P],
+    "vs_k2s2_gather": [_I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "vs_k2s2_scatter": [_I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "vs_k2s2_wgrad": [_I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "vs_inorm_relu_apply": [_I, _P, _P, _P, _P, _I, _L, _I, _P],
+    "vs_inorm_relu_bwd_reduce": [_I, _P, _P, _P, _P, _I, _L, _I, _P],
+    "vs_inorm_relu_bwd_apply": [_I, _P, _P, _P, _P, _P, _I, _L, _I, _P],
+    "vs_add_inplace": [_I, _P, _P, _L, _P],
+    "vs_softmax2_fwd": [_P, _P, _I, _L, _P],
+    "vs_softmax2_bwd": [_I, _P, _P, _P, _I, _L, _P],
+    "vs_fc_encode_fwd": [_I, _P, _P, _P, _P, _P, _P, _F, _I, _P, _P, _P, _I, _I, _I, _I, _P],
+    "vs_fc_decode_fwd": [_I, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "vs_fc_decode_bwd": [_I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "vs_fc_encode_bwd": [_I, _P, _P, _P, _P, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "vs_dice_sums": [_P, _P, _I, _P, _I, _I, _L, _P],
+    "vs_dice_bwd": [_P, _P, _I, _P, _P, _F, _P, _P, _I, _I, _I, _L, _P],
+    "vs_kl_fwd": [_P, _P, _P, _I, _I, _P],
+    "vs_kl_bwd": [_P, _P, _P, _P, _P, _I, _I, _P],
+    "vs_binarize": [_P, _P, _I, _L, _P],
+    "vs_one_hot": [_P, _P, _I, _I, _L, _P],
+    "vs_sgd_step": [_P, _P, _P, _L, _F, _F, _I, _F, _P],
+    "vs_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _P],
+    "vs_ema_update": [_P, _P, _L, _F, _P],
+    "vs_compose_target_loss": [_P, _F, _I, _I, _P, _P, _P],
+}
+_RESTYPES = {"vs_last_error_string": c_char_p, "vs_conv3_wgrad_workspace_bytes": c_size_t}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def lib():
+    """Loads the shared library once; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                "vaeseg_b200: %s is missing -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or vae_segmentation_b200/csrc/build.sh); there is no CPU fallback" % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.argtypes = argtypes
+            fn.restype = _RESTYPES.get(name, c_int)
+        _lib = handle
+    return _lib
+
+
+def last_error():
+    msg = lib().vs_last_error_string()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def call(name, *args):
+    """Calls an int-returning entry point; a negative status raises RuntimeError."""
+    rc = getattr(lib(), name)(*args)
+    if rc != 0:
+        raise RuntimeError("vaeseg_b200.%s failed (status %d): %s" % (name, rc, last_error()))

@@ -1,0 +1,393 @@
+// 3x3x3 convolution (padding 1) on CUDA cores: fp32-accumulate direct kernels.
+//
+// Role: (a) the fp32 "check mode" path (1e-4 parity bar needs fp32 operands);
+//       (b) the layers the tensor-core path does not take (Cin in {1,2}, Cout = 2);
+//       (c) the wgrad contraction.
+// Replaces cuDNN fprop / dgrad / wgrad reached from joint_model.py:40,43,46,106,224,366.
+//
+// Layout: activations NDHWC (T = float | bf16), or planar fp32 at the module boundary.
+// Tile: 4x8x8 output voxels per CTA, 128 threads, halo 6x10x10 staged in shared memory as
+// fp32 channel-quads so one LDS.128 feeds four input channels.
+#include "vs_common.cuh"
+
+namespace {
+
+constexpr int TD = 4, TH = 8, TW = 8;
+constexpr int HD = TD + 2, HH = TH + 2, HW = TW + 2;
+constexpr int HV = HD * HH * HW;          // 600 halo voxels
+constexpr int CIB = 8;                    // input channels per shared-memory stage
+constexpr int NT = 128;
+
+struct ConvDims { int n, d, h, w, cin, cout, tiles_d, tiles_h, tiles_w; };
+
+__device__ __forceinline__ void decode_tile(int tile, const ConvDims& p, int& n, int& d0, int& h0, int& w0) {
+    int tw = tile % p.tiles_w; tile /= p.tiles_w;
+    int th = tile % p.tiles_h; tile /= p.tiles_h;
+    int td = tile % p.tiles_d; n = tile / p.tiles_d;
+    d0 = td * TD; h0 = th * TH; w0 = tw * TW;
+}
+
+// Stage the halo of `cib` channels starting at c0 into xs[plane][voxel] (fp32, zero padded).
+template <typename TI, bool IN_PLANAR>
+__device__ __forceinline__ void load_halo(float4 (*xs)[HV], const TI* __restrict__ x, const ConvDims& p,
+                                          int n, int d0, int h0, int w0, int c0, int cib) {
+    const long long S = (long long)p.d * p.h * p.w;
+    for (int i = threadIdx.x; i < HV; i += NT) {
+        int hw = i % HW, hh = (i / HW) % HH, hd = i / (HW * HH);
+        int gd = d0 + hd - 1, gh = h0 + hh - 1, gw = w0 + hw - 1;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (gd >= 0 && gd < p.d && gh >= 0 && gh < p.h && gw >= 0 && gw < p.w) {
+            long long vox = ((long long)gd * p.h + gh) * p.w + gw;
+            if (IN_PLANAR) {
+                const float* xp = reinterpret_cast<const float*>(x);
+                for (int c = 0; c < cib; ++c) v[c] = xp[((long long)n * p.cin + c0 + c) * S + vox];
+            } else {
+                const TI* px = x + ((long long)n * S + vox) * p.cin + c0;
+                if (cib == 8 && (p.cin & 7) == 0) Store<TI>::ld8(px, v);
+                else for (int c = 0; c < cib; ++c) v[c] = Store<TI>::ld(px + c);
+            }
+        }
+        xs[0][i] = make_float4(v[0], v[1], v[2], v[3]);
+        xs[1][i] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+}
+
+// y = conv3(x, wpk) (+bias), optional per-(n,c) sum / sum-of-squares of the fp32 accumulators.
+template <typename TI, typename TO, int COB, bool IN_PLANAR, bool OUT_PLANAR>
+__global__ void __launch_bounds__(NT) conv3_direct_kernel(const TI* __restrict__ x, const float* __restrict__ wpk,
+                                                          const float* __restrict__ bias, TO* __restrict__ y,
+                                                          float* __restrict__ stats, ConvDims p) {
+    __shared__ float4 xs[2][HV];
+    __shared__ float4 ws[27][CIB][COB / 4];
+    __shared__ float sred[COB][2];
+
+    int n, d0, h0, w0;
+    decode_tile(blockIdx.x, p, n, d0, h0, w0);
+    const int co0 = blockIdx.y * COB;
+    const int t = threadIdx.x;
+    const int tw = t & 7, th = (t >> 3) & 7, tdp = t >> 6;
+
+    float acc0[COB], acc1[COB];
+#pragma unroll
+    for (int j = 0; j < COB; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
+
+    for (int c0 = 0; c0 < p.cin; c0 += CIB) {
+        const int cib = min(CIB, p.cin - c0);
+        __syncthreads();
+        load_halo<TI, IN_PLANAR>(xs, x, p, n, d0, h0, w0, c0, cib);
+        for (int i = t; i < 27 * CIB * (COB / 4); i += NT) {
+            int j = i % (COB / 4), cc = (i / (COB / 4)) % CIB, tap = i / ((COB / 4) * CIB);
+            float wv[4] = {0.f, 0.f, 0.f, 0.f};
+            if (cc < cib) {
+                const float* pw = wpk + ((long long)tap * p.cin + c0 + cc) * p.cout + co0 + j * 4;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if (co0 + j * 4 + q < p.cout) wv[q] = pw[q];
+            }
+            ws[tap][cc][j] = make_float4(wv[0], wv[1], wv[2], wv[3]);
+        }
+        __syncthreads();
+        const int nplane = cib > 4 ? 2 : 1;
+#pragma unroll 1
+        for (int kd = 0; kd < 3; ++kd) {
+#pragma unroll 1
+            for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const int tap = (kd * 3 + kh) * 3 + kw;
+                    const int i0 = ((tdp + kd) * HH + th + kh) * HW + tw + kw;
+                    const int i1 = i0 + 2 * HH * HW;
+                    for (int pl = 0; pl < nplane; ++pl) {
+                        const float4 a0 = xs[pl][i0], a1 = xs[pl][i1];
+                        const float a0v[4] = {a0.x, a0.y, a0.z, a0.w};
+                        const float a1v[4] = {a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc) {
+#pragma unroll
+                            for (int j = 0; j < COB / 4; ++j) {
+                                const float4 wv = ws[tap][pl * 4 + cc][j];
+                                acc0[4 * j + 0] = fmaf(a0v[cc], wv.x, acc0[4 * j + 0]);
+                                acc0[4 * j + 1] = fmaf(a0v[cc], wv.y, acc0[4 * j + 1]);
+                                acc0[4 * j + 2] = fmaf(a0v[cc], wv.z, acc0[4 * j + 2]);
+                                acc0[4 * j + 3] = fmaf(a0v[cc], wv.w, acc0[4 * j + 3]);
+                                acc1[4 * j + 0] = fmaf(a1v[cc], wv.x, acc1[4 * j + 0]);
+                                acc1[4 * j + 1] = fmaf(a1v[cc], wv.y, acc1[4 * j + 1]);
+                                acc1[4 * j + 2] = fmaf(a1v[cc], wv.z, acc1[4 * j + 2]);
+                                acc1[4 * j + 3] = fmaf(a1v[cc], wv.w, acc1[4 * j + 3]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- epilogue ----
+    const int gh = h0 + th, gw = w0 + tw;
+    const int gd0 = d0 + tdp, gd1 = d0 + tdp + 2;
+    const bool v0 = gd0 < p.d && gh < p.h && gw < p.w;
+    const bool v1 = gd1 < p.d && gh < p.h && gw < p.w;
+    if (bias != nullptr) {
+#pragma unroll
+        for (int j = 0; j < COB; ++j) {
+            float b = (co0 + j < p.cout) ? bias[co0 + j] : 0.f;
+            acc0[j] += b; acc1[j] += b;
+        }
+    }
+    if (stats != nullptr) {
+        if (t < COB * 2) sred[t >> 1][t & 1] = 0.f;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < COB; ++j) {
+            float a = v0 ? acc0[j] : 0.f, b = v1 ? acc1[j] : 0.f;
+            float s = warp_sum(a + b);
+            float q = warp_sum(a * a + b * b);
+            if ((t & 31) == 0) { atomicAdd(&sred[j][0], s); atomicAdd(&sred[j][1], q); }
+        }
+        __syncthreads();
+        if (t < COB * 2 && co0 + (t >> 1) < p.cout)
+            atomicAdd(&stats[((long long)n * p.cout + co0 + (t >> 1)) * 2 + (t & 1)], sred[t >> 1][t & 1]);
+    }
+    const long long S = (long long)p.d * p.h * p.w;
+#pragma unroll
+    for (int sel = 0; sel < 2; ++sel) {
+        const bool valid = sel ? v1 : v0;
+        if (!valid) continue;
+        const float* acc = sel ? acc1 : acc0;
+        const long long vox = ((long long)(sel ? gd1 : gd0) * p.h + gh) * p.w + gw;
+        if (OUT_PLANAR) {
+            float* yp = reinterpret_cast<float*>(y);
+#pragma unroll
+            for (int j = 0; j < COB; ++j)
+                if (co0 + j < p.cout) yp[((long long)n * p.cout + co0 + j) * S + vox] = acc[j];
+        } else {
+            TO* py = y + ((long long)n * S + vox) * p.cout + co0;
+            if constexpr (COB % 8 == 0) {
+#pragma unroll
+                for (int j8 = 0; j8 < COB / 8; ++j8) {
+                    float v[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) v[q] = acc[j8 * 8 + q];
+                    Store<TO>::st8(py + j8 * 8, v);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < COB; ++j) if (co0 + j < p.cout) Store<TO>::st(py + j, acc[j]);
+            }
+        }
+    }
+}
+
+// ---- wgrad: dw[co][ci][tap] += sum_v dy[v,co] * x[v+tap,ci] ------------------------------
+// Thread = one (ci,co) pair of the CTA's chunk, 27 tap accumulators in registers, sliding
+// three-wide register window along w.  CTAs are persistent over voxel tiles so the final
+// atomics are O(grid), not O(tiles).
+template <typename T, int WCIB, int WCOB, bool IN_PLANAR>
+__global__ void __launch_bounds__(NT) conv3_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy,
+                                                         float* __restrict__ dw, float* __restrict__ db,
+                                                         ConvDims p, int total_tiles) {
+    constexpr int PAIRS = WCIB * WCOB;
+    constexpr int G = NT / PAIRS;             // row groups
+    static_assert(NT % PAIRS == 0, "pairs must divide the block");
+    __shared__ float xs[HV][WCIB];
+    __shared__ float dys[TD * TH * TW][WCOB];
+
+    const int t = threadIdx.x;
+    const int pair = t % PAIRS, grp = t / PAIRS;
+    const int ci_l = pair / WCOB, co_l = pair % WCOB;
+    const int c0 = blockIdx.y * WCIB, co0 = blockIdx.z * WCOB;
+    const long long S = (long long)p.d * p.h * p.w;
+
+    float acc[27];
+#pragma unroll
+    for (int i = 0; i < 27; ++i) acc[i] = 0.f;
+    float gsum = 0.f;
+
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int n, d0, h0, w0;
+        decode_tile(tile, p, n, d0, h0, w0);
+        __syncthreads();
+        for (int i = t; i < HV * WCIB; i += NT) {
+            int c = i % WCIB, hv = i / WCIB;
+            int hw = hv % HW, hh = (hv / HW) % HH, hd = hv / (HW * HH);
+            int gd = d0 + hd - 1, gh = h0 + hh - 1, gw = w0 + hw - 1;
+            float v = 0.f;
+            if (c0 + c < p.cin && gd >= 0 && gd < p.d && gh >= 0 && gh < p.h && gw >= 0 && gw < p.w) {
+                long long vox = ((long long)gd * p.h + gh) * p.w + gw;
+                if (IN_PLANAR) v = reinterpret_cast<const float*>(x)[((long long)n * p.cin + c0 + c) * S + vox];
+                else v = Store<T>::ld(x + ((long long)n * S + vox) * p.cin + c0 + c);
+            }
+            xs[hv][c] = v;
+        }
+        for (int i = t; i < TD * TH * TW * WCOB; i += NT) {
+            int c = i % WCOB, v = i / WCOB;
+            int lw = v % TW, lh = (v / TW) % TH, ld = v / (TW * TH);
+            int gd = d0 + ld, gh = h0 + lh, gw = w0 + lw;
+            float g = 0.f;
+            if (co0 + c < p.cout && gd < p.d && gh < p.h && gw < p.w)
+                g = Store<T>::ld(dy + ((long long)n * S + ((long long)gd * p.h + gh) * p.w + gw) * p.cout + co0 + c);
+            dys[v][c] = g;
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int row = grp; row < TD * TH; row += G) {
+            const int ld = row / TH, lh = row % TH;
+            float xw[9][3];
+#pragma unroll
+            for (int r = 0; r < 9; ++r) {
+                const int base = ((ld + r / 3) * HH + lh + r % 3) * HW;
+                xw[r][0] = xs[base][ci_l];
+                xw[r][1] = xs[base + 1][ci_l];
+            }
+#pragma unroll
+            for (int lw = 0; lw < TW; ++lw) {
+                const float g = dys[row * TW + lw][co_l];
+                gsum += g;
+#pragma unroll
+                for (int r = 0; r < 9; ++r) {
+                    const int base = ((ld + r / 3) * HH + lh + r % 3) * HW;
+                    xw[r][2] = xs[base + lw + 2][ci_l];
+                    acc[r * 3 + 0] = fmaf(g, xw[r][0], acc[r * 3 + 0]);
+                    acc[r * 3 + 1] = fmaf(g, xw[r][1], acc[r * 3 + 1]);
+                    acc[r * 3 + 2] = fmaf(g, xw[r][2], acc[r * 3 + 2]);
+                    xw[r][0] = xw[r][1];
+                    xw[r][1] = xw[r][2];
+                }
+            }
+        }
+    }
+    const int ci = c0 + ci_l, co = co0 + co_l;
+    if (ci < p.cin && co < p.cout) {
+        float* pd = dw + ((long long)co * p.cin + ci) * 27;
+#pragma unroll
+        for (int i = 0; i < 27; ++i) atomicAdd(pd + i, acc[i]);
+        if (db != nullptr && ci == 0) atomicAdd(db + co, gsum);
+    }
+}
+
+// w[Cout][Cin][27] -> wf[27][Cin][Cout], wd[26-tap][Cout][Cin]
+__global__ void pack_conv3_weight_kernel(const float* __restrict__ w, float* __restrict__ wf, float* __restrict__ wd,
+                                         int cin, int cout) {
+    const int total = cout * cin * 27;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int tap = i % 27, ci = (i / 27) % cin, co = i / (27 * cin);
+        float v = w[i];
+        wf[((long long)tap * cin + ci) * cout + co] = v;
+        if (wd != nullptr) wd[((long long)(26 - tap) * cout + co) * cin + ci] = v;
+    }
+}
+
+ConvDims make_dims(int n, int d, int h, int w, int cin, int cout) {
+    ConvDims p;
+    p.n = n; p.d = d; p.h = h; p.w = w; p.cin = cin; p.cout = cout;
+    p.tiles_d = (d + TD - 1) / TD; p.tiles_h = (h + TH - 1) / TH; p.tiles_w = (w + TW - 1) / TW;
+    return p;
+}
+
+template <typename TI, typename TO, bool IN_PLANAR, bool OUT_PLANAR>
+int launch_conv3(const void* x, const float* wpk, const float* bias, void* y, float* stats, const ConvDims& p,
+                 cudaStream_t st) {
+    const long long tiles = (long long)p.n * p.tiles_d * p.tiles_h * p.tiles_w;
+    VS_REQUIRE(tiles < 2147483647LL, VS_ERR_SHAPE, "conv3: too many tiles");
+    const int cob = p.cout >= 16 ? 16 : (p.cout >= 8 ? 8 : 4);
+    dim3 grid((unsigned)tiles, (p.cout + cob - 1) / cob);
+    if (cob == 16)
+        conv3_direct_kernel<TI, TO, 16, IN_PLANAR, OUT_PLANAR><<<grid, NT, 0, st>>>((const TI*)x, wpk, bias, (TO*)y, stats, p);
+    else if (cob == 8)
+        conv3_direct_kernel<TI, TO, 8, IN_PLANAR, OUT_PLANAR><<<grid, NT, 0, st>>>((const TI*)x, wpk, bias, (TO*)y, stats, p);
+    else
+        conv3_direct_kernel<TI, TO, 4, IN_PLANAR, OUT_PLANAR><<<grid, NT, 0, st>>>((const TI*)x, wpk, bias, (TO*)y, stats, p);
+    VS_CHECK_LAUNCH("conv3_direct_kernel");
+    return VS_OK;
+}
+
+int conv3_common(int in_dtype, int out_dtype, int in_planar, int out_planar, const void* x, const float* wpk,
+                 const float* bias, void* y, float* stats, int n, int d, int h, int w, int cin, int cout, void* stream) {
+    VS_REQUIRE(n > 0 && d > 0 && h > 0 && w > 0 && cin > 0 && cout > 0, VS_ERR_SHAPE, "conv3: bad shape");
+    VS_REQUIRE(x && wpk && y, VS_ERR_SHAPE, "conv3: null pointer");
+    VS_REQUIRE(vs_aligned16(x) && vs_aligned16(y) && vs_aligned16(wpk), VS_ERR_ALIGN, "conv3: pointers must be 16B aligned");
+    if (!out_planar) VS_REQUIRE(cout % 8 == 0 || cout == 2, VS_ERR_UNSUPPORTED, "conv3: NDHWC output needs Cout %% 8 == 0 or Cout == 2 (got %d)", cout);
+    if (in_planar) VS_REQUIRE(in_dtype == VS_F32, VS_ERR_UNSUPPORTED, "conv3: planar input is fp32 only");
+    if (out_planar) VS_REQUIRE(out_dtype == VS_F32, VS_ERR_UNSUPPORTED, "conv3: planar output is fp32 only");
+    cudaStream_t st = (cudaStream_t)stream;
+    ConvDims p = make_dims(n, d, h, w, cin, cout);
+    if (stats) VS_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * n * cout, st), "conv3 stats memset");
+    if (in_planar) {
+        VS_REQUIRE(!out_planar, VS_ERR_UNSUPPORTED, "conv3: planar->planar unsupported");
+        if (out_dtype == VS_F32) return launch_conv3<float, float, true, false>(x, wpk, bias, y, stats, p, st);
+        return launch_conv3<float, bf16, true, false>(x, wpk, bias, y, stats, p, st);
+    }
+    if (out_planar) {
+        if (in_dtype == VS_F32) return launch_conv3<float, float, false, true>(x, wpk, bias, y, stats, p, st);
+        return launch_conv3<bf16, float, false, true>(x, wpk, bias, y, stats, p, st);
+    }
+    if (in_dtype == VS_F32 && out_dtype == VS_F32) return launch_conv3<float, float, false, false>(x, wpk, bias, y, stats, p, st);
+    if (in_dtype == VS_BF16 && out_dtype == VS_BF16) return launch_conv3<bf16, bf16, false, false>(x, wpk, bias, y, stats, p, st);
+    if (in_dtype == VS_BF16 && out_dtype == VS_F32) return launch_conv3<bf16, float, false, false>(x, wpk, bias, y, stats, p, st);
+    VS_FAIL(VS_ERR_UNSUPPORTED, "conv3: dtype combination in=%d out=%d unsupported", in_dtype, out_dtype);
+}
+
+template <typename T, bool IN_PLANAR>
+int launch_wgrad(const void* x, const void* dy, float* dw, float* db, const ConvDims& p, cudaStream_t st) {
+    const long long tiles = (long long)p.n * p.tiles_d * p.tiles_h * p.tiles_w;
+    const int sms = vs_sm_count();
+    if (p.cin >= 8 && p.cout >= 16) {
+        dim3 grid(1, (p.cin + 7) / 8, (p.cout + 15) / 16);
+        long long slots = (long long)sms * 6 / ((long long)grid.y * grid.z);
+        grid.x = (unsigned)max(1LL, min(tiles, slots));
+        conv3_wgrad_kernel<T, 8, 16, IN_PLANAR><<<grid, NT, 0, st>>>((const T*)x, (const T*)dy, dw, db, p, (int)tiles);
+    } else if (p.cin >= 8 && p.cout >= 8) {
+        dim3 grid(1, (p.cin + 7) / 8, (p.cout + 7) / 8);
+        long long slots = (long long)sms * 6 / ((long long)grid.y * grid.z);
+        grid.x = (unsigned)max(1LL, min(tiles, slots));
+        conv3_wgrad_kernel<T, 8, 8, IN_PLANAR><<<grid, NT, 0, st>>>((const T*)x, (const T*)dy, dw, db, p, (int)tiles);
+    } else if (p.cin >= 8) {                       // out_block: Cout = 2
+        dim3 grid(1, (p.cin + 7) / 8, (p.cout + 1) / 2);
+        grid.x = (unsigned)max(1LL, min(tiles, (long long)sms * 6));
+        conv3_wgrad_kernel<T, 8, 2, IN_PLANAR><<<grid, NT, 0, st>>>((const T*)x, (const T*)dy, dw, db, p, (int)tiles);
+    } else {                                       // in_blocks: Cin in {1,2}
+        dim3 grid(1, (p.cin + 1) / 2, (p.cout + 7) / 8);
+        grid.x = (unsigned)max(1LL, min(tiles, (long long)sms * 6));
+        conv3_wgrad_kernel<T, 2, 8, IN_PLANAR><<<grid, NT, 0, st>>>((const T*)x, (const T*)dy, dw, db, p, (int)tiles);
+    }
+    VS_CHECK_LAUNCH("conv3_wgrad_kernel");
+    return VS_OK;
+}
+
+}  // namespace
+
+extern "C" int vs_pack_conv3_weight(const float* w, float* wf, float* wd, int cin, int cout, void* stream) {
+    VS_REQUIRE(w && wf && cin > 0 && cout > 0, VS_ERR_SHAPE, "pack_conv3_weight: bad arguments");
+    const int total = cin * cout * 27;
+    pack_conv3_weight_kernel<<<min(1024, (total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, wf, wd, cin, cout);
+    VS_CHECK_LAUNCH("pack_conv3_weight_kernel");
+    return VS_OK;
+}
+
+extern "C" int vs_conv3x3x3_fprop_direct(int in_dtype, int out_dtype, int in_planar, int out_planar, const void* x,
+                                         const float* wpk, const float* bias, void* y, float* stats, int n, int d,
+                                         int h, int w, int cin, int cout, void* stream) {
+    return conv3_common(in_dtype, out_dtype, in_planar, out_planar, x, wpk, bias, y, stats, n, d, h, w, cin, cout, stream);
+}
+
+extern "C" size_t vs_conv3_wgrad_workspace_bytes(int, int, int, int, int, int) { return 0; }
+
+extern "C" int vs_conv3x3x3_wgrad(int dtype, int in_planar, const void* x, const void* dy, float* dw, float* db,
+                                  void* workspace, size_t ws_bytes, int accumulate, int n, int d, int h, int w,
+                                  int cin, int cout, void* stream) {
+    (void)workspace; (void)ws_bytes;
+    VS_REQUIRE(n > 0 && d > 0 && h > 0 && w > 0 && cin > 0 && cout > 0, VS_ERR_SHAPE, "conv3 wgrad: bad shape");
+    VS_REQUIRE(x && dy && dw, VS_ERR_SHAPE, "conv3 wgrad: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    ConvDims p = make_dims(n, d, h, w, cin, cout);
+    if (!accumulate) {
+        VS_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * 27 * cin * cout, st), "wgrad memset");
+        if (db) VS_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * cout, st), "wgrad memset db");
+    }
+    if (in_planar) {
+        if (dtype == VS_F32) return launch_wgrad<float, true>(x, dy, dw, db, p, st);
+        return launch_wgrad<bf16, true>(x, dy, dw, db, p, st);
+    }
+    if (dtype == VS_F32) return launch_wgrad<float, false>(x, dy, dw, db, p, st);
+    if (dtype == VS_BF16) return launch_wgrad<bf16, false>(x, dy, dw, db, p, st);
+    VS_FAIL(VS_ERR_UNSUPPORTED, "conv3 wgrad: unknown dtype %d", dtype);
+}

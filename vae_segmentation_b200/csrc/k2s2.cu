@@ -1,0 +1,296 @@
+// 2x2x2 stride-2 convolution / transposed convolution as non-overlapping patch contractions.
+// Replaces cuDNN for Conv3d(C,C,2,stride=2) (joint_model.py:130) and
+// ConvTranspose3d(C,C,2,stride=2) (joint_model.py:118): fprop, dgrad and wgrad of both are the
+// three kernels below (see include/vaeseg_b200.h for the gather/scatter algebra).
+// These layers are HBM-bound (AI 7-114 flop/B): fp32-accumulate CUDA-core
+// kernels with 16-byte channel vectors; weights staged in shared memory.
+#include "vs_common.cuh"
+
+namespace {
+
+struct K2Dims { int n, dc, hc, wc, a, b; };
+
+__device__ __forceinline__ void decode_coarse(long long o, const K2Dims& p, int& n, int& od, int& oh, int& ow) {
+    ow = (int)(o % p.wc); o /= p.wc;
+    oh = (int)(o % p.hc); o /= p.hc;
+    od = (int)(o % p.dc); n = (int)(o / p.dc);
+}
+__device__ __forceinline__ long long fine_index(const K2Dims& p, int n, int od, int oh, int ow, int k) {
+    const int fd = 2 * od + (k >> 2), fh = 2 * oh + ((k >> 1) & 1), fw = 2 * ow + (k & 1);
+    return (((long long)n * (2 * p.dc) + fd) * (2 * p.hc) + fh) * (2 * p.wc) + fw;
+}
+
+// coarse[o,a] = bias[a] + sum_{k,b} wt[a][b][k] * fine[2o+k, b]
+template <typename T, int AOB>
+__global__ void __launch_bounds__(128) k2s2_gather_kernel(const T* __restrict__ fine, const float* __restrict__ wt,
+                                                          const float* __restrict__ bias, T* __restrict__ coarse,
+                                                          K2Dims p, long long total) {
+    __shared__ float4 ws[8][8][AOB / 4];      // [k][bb][a/4]
+    const int t = threadIdx.x;
+    const long long o = (long long)blockIdx.x * 128 + t;
+    const bool valid = o < total;
+    const int a0 = blockIdx.y * AOB;
+    int n = 0, od = 0, oh = 0, ow = 0;
+    if (valid) decode_coarse(o, p, n, od, oh, ow);
+    float acc[AOB];
+#pragma unroll
+    for (int j = 0; j < AOB; ++j) acc[j] = 0.f;
+    for (int b0 = 0; b0 < p.b; b0 += 8) {
+        __syncthreads();
+        for (int i = t; i < 8 * 8 * AOB; i += 128) {
+            int k = i % 8, bb = (i / 8) % 8, aa = i / 64;
+            reinterpret_cast<float*>(&ws[k][bb][0])[aa] = wt[((long long)(a0 + aa) * p.b + b0 + bb) * 8 + k];
+        }
+        __syncthreads();
+        if (valid) {
+#pragma unroll 2
+            for (int k = 0; k < 8; ++k) {
+                float xv[8];
+                Store<T>::ld8(fine + fine_index(p, n, od, oh, ow, k) * p.b + b0, xv);
+#pragma unroll
+                for (int bb = 0; bb < 8; ++bb) {
+#pragma unroll
+                    for (int j = 0; j < AOB / 4; ++j) {
+                        const float4 wv = ws[k][bb][j];
+                        acc[4 * j + 0] = fmaf(xv[bb], wv.x, acc[4 * j + 0]);
+                        acc[4 * j + 1] = fmaf(xv[bb], wv.y, acc[4 * j + 1]);
+                        acc[4 * j + 2] = fmaf(xv[bb], wv.z, acc[4 * j + 2]);
+                        acc[4 * j + 3] = fmaf(xv[bb], wv.w, acc[4 * j + 3]);
+                    }
+                }
+            }
+        }
+    }
+    if (valid) {
+#pragma unroll
+        for (int j8 = 0; j8 < AOB / 8; ++j8) {
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = acc[j8 * 8 + q] + (bias ? bias[a0 + j8 * 8 + q] : 0.f);
+            Store<T>::st8(coarse + o * p.a + a0 + j8 * 8, v);
+        }
+    }
+}
+
+// fine[2o+k, b] = bias[b] + sum_a wt[a][b][k] * coarse[o, a]
+// thread = (two coarse voxels, one k); BOB output channels.
+template <typename T, int BOB>
+__global__ void __launch_bounds__(256) k2s2_scatter_kernel(const T* __restrict__ coarse, const float* __restrict__ wt,
+                                                           const float* __restrict__ bias, T* __restrict__ fine,
+                                                           K2Dims p, long long total) {
+    __shared__ float4 ws[8][BOB / 4][8];      // [aa][b/4][k]
+    const int t = threadIdx.x;
+    const int k = t & 7;
+    const long long o0 = (long long)blockIdx.x * 64 + (t >> 3);
+    const long long o1 = o0 + 32;
+    const bool v0 = o0 < total, v1 = o1 < total;
+    const int b0 = blockIdx.y * BOB;
+    float acc0[BOB], acc1[BOB];
+#pragma unroll
+    for (int j = 0; j < BOB; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
+    for (int a0 = 0; a0 < p.a; a0 += 8) {
+        __syncthreads();
+        for (int i = t; i < 8 * BOB * 8; i += 256) {
+            int kk = i % 8, bb = (i / 8) % BOB, aa = i / (8 * BOB);
+            reinterpret_cast<float*>(&ws[aa][bb / 4][kk])[bb % 4] = wt[((long long)(a0 + aa) * p.b + b0 + bb) * 8 + kk];
+        }
+        __syncthreads();
+        float x0[8], x1[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { x0[q] = 0.f; x1[q] = 0.f; }
+        if (v0) Store<T>::ld8(coarse + o0 * p.a + a0, x0);
+        if (v1) Store<T>::ld8(coarse + o1 * p.a + a0, x1);
+#pragma unroll
+        for (int aa = 0; aa < 8; ++aa) {
+#pragma unroll
+            for (int j = 0; j < BOB / 4; ++j) {
+                const float4 wv = ws[aa][j][k];
+                acc0[4 * j + 0] = fmaf(x0[aa], wv.x, acc0[4 * j + 0]);
+                acc0[4 * j + 1] = fmaf(x0[aa], wv.y, acc0[4 * j + 1]);
+                acc0[4 * j + 2] = fmaf(x0[aa], wv.z, acc0[4 * j + 2]);
+                acc0[4 * j + 3] = fmaf(x0[aa], wv.w, acc0[4 * j + 3]);
+                acc1[4 * j + 0] = fmaf(x1[aa], wv.x, acc1[4 * j + 0]);
+                acc1[4 * j + 1] = fmaf(x1[aa], wv.y, acc1[4 * j + 1]);
+                acc1[4 * j + 2] = fmaf(x1[aa], wv.z, acc1[4 * j + 2]);
+                acc1[4 * j + 3] = fmaf(x1[aa], wv.w, acc1[4 * j + 3]);
+            }
+        }
+    }
+#pragma unroll
+    for (int sel = 0; sel < 2; ++sel) {
+        if (!(sel ? v1 : v0)) continue;
+        const float* acc = sel ? acc1 : acc0;
+        int n, od, oh, ow;
+        decode_coarse(sel ? o1 : o0, p, n, od, oh, ow);
+        T* pf = fine + fine_index(p, n, od, oh, ow, k) * p.b + b0;
+#pragma unroll
+        for (int j8 = 0; j8 < BOB / 8; ++j8) {
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = acc[j8 * 8 + q] + (bias ? bias[b0 + j8 * 8 + q] : 0.f);
+            Store<T>::st8(pf + j8 * 8, v);
+        }
+    }
+}
+
+// dwt[a][b][k] += sum_o coarse[o,a] * fine[2o+k,b]; CTA = 8 a x BCH b pairs, persistent over
+// blocks of 32 coarse voxels staged in shared memory.
+template <typename T, int BCH>
+__global__ void __launch_bounds__(8 * BCH) k2s2_wgrad_kernel(const T* __restrict__ coarse, const T* __restrict__ fine,
+                                                             float* __restrict__ dwt, K2Dims p, long long total) {
+    constexpr int NTH = 8 * BCH;
+    constexpr int VB = 32;
+    __shared__ float cs[VB][8];
+    __shared__ float fs[VB][8][BCH];
+    const int t = threadIdx.x;
+    const int a_l = t / BCH, b_l = t % BCH;
+    const int a0 = blockIdx.y * 8, b0 = blockIdx.z * BCH;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (long long base = (long long)blockIdx.x * VB; base < total; base += (long long)gridDim.x * VB) {
+        __syncthreads();
+        for (int i = t; i < VB * 8; i += NTH) {
+            int aa = i % 8, v = i / 8;
+            long long o = base + v;
+            cs[v][aa] = o < total ? Store<T>::ld(coarse + o * p.a + a0 + aa) : 0.f;
+        }
+        for (int i = t; i < VB * 8 * BCH; i += NTH) {
+            int bb = i % BCH, k = (i / BCH) % 8, v = i / (BCH * 8);
+            long long o = base + v;
+            float f = 0.f;
+            if (o < total) {
+                int n, od, oh, ow;
+                decode_coarse(o, p, n, od, oh, ow);
+                f = Store<T>::ld(fine + fine_index(p, n, od, oh, ow, k) * p.b + b0 + bb);
+            }
+            fs[v][k][bb] = f;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int v = 0; v < VB; ++v) {
+            const float c = cs[v][a_l];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] = fmaf(c, fs[v][k][b_l], acc[k]);
+        }
+    }
+    float* pd = dwt + ((long long)(a0 + a_l) * p.b + b0 + b_l) * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(pd + k, acc[k]);
+}
+
+// out[c] += sum_rows t[row][c]   (C % 8 == 0)
+template <typename T>
+__global__ void __launch_bounds__(256) channel_sum_kernel(const T* __restrict__ x, float* __restrict__ out,
+                                                          long long rows, int c) {
+    __shared__ float red[256][8];
+    const int groups = c / 8;                 // <= 32
+    const int t = threadIdx.x;
+    const int lanes = 256 / groups;
+    const int g = t % groups, lane = t / groups;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (lane < lanes) {
+        for (long long r = (long long)blockIdx.x * lanes + lane; r < rows; r += (long long)gridDim.x * lanes) {
+            float v[8];
+            Store<T>::ld8(x + r * c + g * 8, v);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] += v[q];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) red[t][q] = (lane < lanes) ? acc[q] : 0.f;
+    __syncthreads();
+    if (t < c) {
+        const int gg = t / 8, q = t % 8;
+        float s = 0.f;
+        for (int l = 0; l < lanes; ++l) s += red[l * groups + gg][q];
+        atomicAdd(out + t, s);
+    }
+}
+
+template <typename T>
+int channel_sum(const T* x, float* out, long long rows, int c, cudaStream_t st) {
+    VS_REQUIRE(c % 8 == 0 && c <= 256, VS_ERR_UNSUPPORTED, "channel_sum: C must be a multiple of 8 <= 256 (got %d)", c);
+    const int lanes = 256 / (c / 8);
+    int blocks = (int)min((long long)vs_sm_count() * 4, (rows + lanes - 1) / lanes);
+    channel_sum_kernel<T><<<max(blocks, 1), 256, 0, st>>>(x, out, rows, c);
+    VS_CHECK_LAUNCH("channel_sum_kernel");
+    return VS_OK;
+}
+
+int check_k2(const void* p0, const void* p1, const void* p2, int n, int dc, int hc, int wc, int a, int b, const char* who) {
+    VS_REQUIRE(n > 0 && dc > 0 && hc > 0 && wc > 0, VS_ERR_SHAPE, "%s: bad shape", who);
+    VS_REQUIRE(a % 8 == 0 && b % 8 == 0 && a >= 8 && b >= 8, VS_ERR_UNSUPPORTED, "%s: channels must be multiples of 8 (A=%d B=%d)", who, a, b);
+    VS_REQUIRE(p0 && p1 && p2, VS_ERR_SHAPE, "%s: null pointer", who);
+    VS_REQUIRE(vs_aligned16(p0) && vs_aligned16(p1) && vs_aligned16(p2), VS_ERR_ALIGN, "%s: pointers must be 16B aligned", who);
+    return VS_OK;
+}
+
+}  // namespace
+
+extern "C" int vs_k2s2_gather(int dtype, const void* fine, const float* wt, const float* bias, void* coarse,
+                              int n, int dc, int hc, int wc, int a, int b, void* stream) {
+    int rc = check_k2(fine, wt, coarse, n, dc, hc, wc, a, b, "k2s2_gather");
+    if (rc) return rc;
+    K2Dims p = {n, dc, hc, wc, a, b};
+    const long long total = (long long)n * dc * hc * wc;
+    cudaStream_t st = (cudaStream_t)stream;
+    VS_DISPATCH_DTYPE(dtype, T, {
+        if (a % 16 == 0) {
+            dim3 grid(vs_ceil_div(total, 128), a / 16);
+            k2s2_gather_kernel<T, 16><<<grid, 128, 0, st>>>((const T*)fine, wt, bias, (T*)coarse, p, total);
+        } else {
+            dim3 grid(vs_ceil_div(total, 128), a / 8);
+            k2s2_gather_kernel<T, 8><<<grid, 128, 0, st>>>((const T*)fine, wt, bias, (T*)coarse, p, total);
+        }
+    });
+    VS_CHECK_LAUNCH("k2s2_gather_kernel");
+    return VS_OK;
+}
+
+extern "C" int vs_k2s2_scatter(int dtype, const void* coarse, const float* wt, const float* bias, void* fine,
+                               int n, int dc, int hc, int wc, int a, int b, void* stream) {
+    int rc = check_k2(coarse, wt, fine, n, dc, hc, wc, a, b, "k2s2_scatter");
+    if (rc) return rc;
+    K2Dims p = {n, dc, hc, wc, a, b};
+    const long long total = (long long)n * dc * hc * wc;
+    cudaStream_t st = (cudaStream_t)stream;
+    VS_DISPATCH_DTYPE(dtype, T, {
+        if (b % 16 == 0) {
+            dim3 grid(vs_ceil_div(total, 64), b / 16);
+            k2s2_scatter_kernel<T, 16><<<grid, 256, 0, st>>>((const T*)coarse, wt, bias, (T*)fine, p, total);
+        } else {
+            dim3 grid(vs_ceil_div(total, 64), b / 8);
+            k2s2_scatter_kernel<T, 8><<<grid, 256, 0, st>>>((const T*)coarse, wt, bias, (T*)fine, p, total);
+        }
+    });
+    VS_CHECK_LAUNCH("k2s2_scatter_kernel");
+    return VS_OK;
+}
+
+extern "C" int vs_k2s2_wgrad(int dtype, const void* coarse, const void* fine, float* dwt, float* dbias_coarse,
+                             float* dbias_fine, int accumulate, int n, int dc, int hc, int wc, int a, int b,
+                             void* stream) {
+    int rc = check_k2(coarse, fine, dwt, n, dc, hc, wc, a, b, "k2s2_wgrad");
+    if (rc) return rc;
+    K2Dims p = {n, dc, hc, wc, a, b};
+    const long long total = (long long)n * dc * hc * wc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!accumulate) {
+        VS_CUDA(cudaMemsetAsync(dwt, 0, sizeof(float) * 8 * a * b, st), "k2s2 wgrad memset");
+        if (dbias_coarse) VS_CUDA(cudaMemsetAsync(dbias_coarse, 0, sizeof(float) * a, st), "k2s2 wgrad memset");
+        if (dbias_fine) VS_CUDA(cudaMemsetAsync(dbias_fine, 0, sizeof(float) * b, st), "k2s2 wgrad memset");
+    }
+    VS_DISPATCH_DTYPE(dtype, T, {
+        const int bch = (b % 16 == 0) ? 16 : 8;
+        dim3 grid(1, a / 8, b / bch);
+        long long slots = max(1LL, (long long)vs_sm_count() * 8 / ((long long)grid.y * grid.z));
+        grid.x = (unsigned)max(1LL, min(slots, (total + 31) / 32));
+        if (bch == 16) k2s2_wgrad_kernel<T, 16><<<grid, 128, 0, st>>>((const T*)coarse, (const T*)fine, dwt, p, total);
+        else k2s2_wgrad_kernel<T, 8><<<grid, 64, 0, st>>>((const T*)coarse, (const T*)fine, dwt, p, total);
+        VS_CHECK_LAUNCH("k2s2_wgrad_kernel");
+        if (dbias_coarse) { rc = channel_sum<T>((const T*)coarse, dbias_coarse, total, a, st); if (rc) return rc; }
+        if (dbias_fine) { rc = channel_sum<T>((const T*)fine, dbias_fine, total * 8, b, st); if (rc) return rc; }
+    });
+    return VS_OK;
+}

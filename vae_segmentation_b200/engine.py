@@ -1,0 +1,330 @@
+"""Layer-program executor behind the drop-in modules.
+
+A network (or a single block) is described as a flat list of `Layer`s; `program_forward`
+launches the C-ABI kernels layer by layer and records a tape, `program_backward` replays the
+tape in reverse with hand-written dgrad / wgrad / norm-backward kernels.  torch.autograd only
+sees one node per network (`ProgramFn`, `VAEFn`), so the backward schedule, buffer reuse and
+gradient accumulation are ours.
+
+Internal activation layout is NDHWC in the compute dtype (bf16, or fp32 in check mode); the
+nn.Module boundary stays NCDHW fp32 ("planar"): first layers read planar input directly and
+the softmax head writes planar probabilities, so no layout-conversion kernels run.
+
+Reference semantics implemented here: joint_model.py:35-52,101-136 (blocks), :369-390
+(Segmentation.forward incl. the two additive skips), :227-272 (VAE.forward).
+"""
+import torch
+
+from . import ops
+
+C3IN, K2DOWN, K2UP, HEAD = "c3in", "k2down", "k2up", "head"
+
+
+class Layer(object):
+    __slots__ = ("kind", "name", "cin", "cout", "wi", "bi", "save_as", "skip_from", "in_planar")
+
+    def __init__(self, kind, name, cin, cout, wi, bi, save_as=None, skip_from=None, in_planar=False):
+        self.kind, self.name, self.cin, self.cout = kind, name, cin, cout
+        self.wi, self.bi = wi, bi
+        self.save_as, self.skip_from, self.in_planar = save_as, skip_from, in_planar
+
+
+class PackCache(object):
+    """Derived caches of the fp32 master weights ([27][Cin][Cout] fprop / dgrad packs).
+    Keyed by storage pointer + tensor version + an explicit epoch that the fused optimiser
+    bumps (its raw-pointer updates do not touch torch's version counters)."""
+
+    def __init__(self):
+        self.epoch = 0
+        self._store = {}
+
+    def invalidate(self):
+        self.epoch += 1
+        self._store.clear()
+
+    def conv3(self, w):
+        key = (w.data_ptr(), w._version, self.epoch)
+        hit = self._store.get(w.data_ptr())
+        if hit is not None and hit[0] == key:
+            return hit[1], hit[2]
+        wf, wd = ops.pack_conv3_weight(w.detach(), want_dgrad=True)
+        self._store[w.data_ptr()] = (key, wf, wd)
+        return wf, wd
+
+
+def _grad_target(p_ref, need):
+    """Where a parameter gradient goes: into an existing .grad (accumulate in place, return
+    None to autograd) or into a fresh tensor returned to autograd."""
+    if not need:
+        return None, False
+    g = p_ref.grad if p_ref is not None else None
+    if g is not None and g.is_cuda and g.dtype == torch.float32 and g.is_contiguous():
+        return g, True
+    return None, False
+
+
+def _pair_targets(param_refs, need, wi, bi, wshape, bshape, device):
+    """Resolves where the (weight, bias) gradients of one layer go.  Returns (dw, db, acc):
+    buffers handed to the kernel (db None when the bias needs no gradient) and whether the
+    kernel accumulates into them (existing .grad) or overwrites fresh tensors."""
+    tw, aw = _grad_target(param_refs[wi], need[wi])
+    tb, ab = _grad_target(param_refs[bi], need[bi])
+    if need[wi] and need[bi] and aw != ab:
+        raise RuntimeError("weight and bias of one layer must both have (or both lack) a .grad buffer")
+    acc = aw if need[wi] else ab
+    if tw is None:                       # fresh gradient, or scratch when only the bias trains
+        tw = torch.empty(wshape, device=device, dtype=torch.float32)
+    if need[bi] and tb is None:
+        tb = torch.empty(bshape, device=device, dtype=torch.float32)
+    return tw, tb, acc
+
+
+def _hand_back(grads, need, wi, bi, tw, tb, acc):
+    grads[wi] = tw if (need[wi] and not acc) else None
+    grads[bi] = tb if (need[bi] and not acc) else None
+
+
+def program_forward(layers, tensors, x, dims, dtype, cache, record=True):
+    """x: NDHWC `dtype` tensor (planar fp32 when layers[0].in_planar).  dims=(N,D,H,W) of x.
+    Returns (out, out_dims, tape)."""
+    n, d, h, w = dims
+    tape = []
+    slots = {}
+    cur = x
+    for L in layers:
+        if L.kind == C3IN:
+            wf, wd = cache.conv3(tensors[L.wi])
+            # the conv bias is a no-op ahead of InstanceNorm(affine=False): skipped
+            y, stats = ops.conv3_fprop(cur, wf, None, (n, d, h, w), L.cin, L.cout, dtype, in_planar=L.in_planar)
+            skip = slots[L.skip_from] if L.skip_from is not None else None
+            a = ops.inorm_relu_apply(y, stats, skip)
+            if record:
+                tape.append((L, cur, y, stats, (n, d, h, w), wd))
+            cur = a
+        elif L.kind == K2DOWN:
+            d, h, w = d // 2, h // 2, w // 2
+            out = ops.k2s2_gather(cur, tensors[L.wi].detach(), tensors[L.bi].detach(), (n, d, h, w), L.cout, L.cin)
+            if record:
+                tape.append((L, cur, None, None, (n, d, h, w), None))
+            cur = out
+        elif L.kind == K2UP:
+            out = ops.k2s2_scatter(cur, tensors[L.wi].detach(), tensors[L.bi].detach(), (n, d, h, w), L.cin, L.cout)
+            if record:
+                tape.append((L, cur, None, None, (n, d, h, w), None))
+            d, h, w = d * 2, h * 2, w * 2
+            cur = out
+        elif L.kind == HEAD:
+            wf, wd = cache.conv3(tensors[L.wi])
+            logits, _ = ops.conv3_fprop(cur, wf, tensors[L.bi].detach(), (n, d, h, w), L.cin, L.cout, torch.float32,
+                                        in_planar=L.in_planar, want_stats=False)
+            probs = ops.softmax2_fwd(logits, (n, d, h, w))
+            if record:
+                tape.append((L, cur, probs, None, (n, d, h, w), wd))
+            cur = probs
+        else:
+            raise RuntimeError("unknown layer kind %r" % (L.kind,))
+        if L.save_as is not None:
+            slots[L.save_as] = cur
+    return cur, (n, d, h, w), tape
+
+
+def program_backward(tape, g, dtype, need, grads, param_refs, need_input_grad):
+    """Replays `tape` in reverse.  need[i]: whether tensor i wants a gradient; grads[i] receives
+    the tensor handed back to autograd (None when accumulated in place into .grad).
+    Returns the gradient w.r.t. the program input (or None)."""
+    pending = {}                     # slot name -> gradient arriving through an additive skip
+    for idx in range(len(tape) - 1, -1, -1):
+        L, x_in, y, stats, dims, wd, wt = tape[idx]
+        first = idx == 0
+        want_dx = (not first) or need_input_grad
+        if L.save_as is not None and L.save_as in pending:
+            g = ops.add_inplace(g, pending.pop(L.save_as))
+        if L.kind == C3IN:
+            if L.skip_from is not None:
+                pending[L.skip_from] = g
+            dy = ops.inorm_relu_bwd(g, y, stats)
+            if need[L.wi]:
+                tgt, acc = _grad_target(param_refs[L.wi], True)
+                dw, _ = ops.conv3_wgrad(x_in, dy, dims, L.cin, L.cout, dw=tgt, in_planar=L.in_planar, accumulate=acc)
+                grads[L.wi] = None if acc else dw
+            if need[L.bi]:
+                # exactly zero: the bias cancels in InstanceNorm
+                tgt, acc = _grad_target(param_refs[L.bi], True)
+                grads[L.bi] = None if acc else torch.zeros(L.cout, device=dy.device, dtype=torch.float32)
+            g = ops.conv3_dgrad(dy, wd, dims, L.cin, L.cout, dtype, out_planar=L.in_planar) if want_dx else None
+        elif L.kind == K2DOWN:
+            # dims are the coarse (output) dims; g is the coarse gradient
+            if need[L.wi] or need[L.bi]:
+                tw, tb, acc = _pair_targets(param_refs, need, L.wi, L.bi, (L.cout, L.cin, 2, 2, 2), (L.cout,), g.device)
+                ops.k2s2_wgrad(g, x_in, dims, L.cout, L.cin, dwt=tw, dbias_coarse=tb, accumulate=acc)
+                _hand_back(grads, need, L.wi, L.bi, tw, tb, acc)
+            g = ops.k2s2_scatter(g, wt, None, dims, L.cout, L.cin) if want_dx else None
+        elif L.kind == K2UP:
+            # dims are the coarse (input) dims; g is the fine gradient
+            if need[L.wi] or need[L.bi]:
+                tw, tb, acc = _pair_targets(param_refs, need, L.wi, L.bi, (L.cin, L.cout, 2, 2, 2), (L.cout,), g.device)
+                ops.k2s2_wgrad(x_in, g, dims, L.cin, L.cout, dwt=tw, dbias_fine=tb, accumulate=acc)
+                _hand_back(grads, need, L.wi, L.bi, tw, tb, acc)
+            g = ops.k2s2_gather(g, wt, None, dims, L.cin, L.cout) if want_dx else None
+        elif L.kind == HEAD:
+            probs = y
+            dlogits = ops.softmax2_bwd(g, probs, dims, dtype)
+            if need[L.wi] or need[L.bi]:
+                tw, tb, acc = _pair_targets(param_refs, need, L.wi, L.bi, (L.cout, L.cin, 3, 3, 3), (L.cout,), g.device)
+                ops.conv3_wgrad(x_in, dlogits, dims, L.cin, L.cout, dw=tw, db=tb, in_planar=L.in_planar, accumulate=acc)
+                _hand_back(grads, need, L.wi, L.bi, tw, tb, acc)
+            g = ops.conv3_dgrad(dlogits, wd, dims, L.cin, L.cout, dtype, out_planar=L.in_planar) if want_dx else None
+    return g
+
+
+def _record_weights(tape, tensors):
+    """Appends the (detached) k2s2 weight to the tape entries that need it in backward."""
+    out = []
+    for entry in tape:
+        L = entry[0]
+        wt = tensors[L.wi].detach() if L.kind in (K2DOWN, K2UP) else None
+        out.append(entry + (wt,))
+    return out
+
+
+class ProgramFn(torch.autograd.Function):
+    """One autograd node for a whole conv program (Segmentation, or a single block)."""
+
+    @staticmethod
+    def forward(ctx, spec, x, *tensors):
+        layers, dtype, cache, param_refs = spec
+        planar = layers[0].in_planar
+        if planar:
+            n, d, h, w = x.shape[0], x.shape[2], x.shape[3], x.shape[4]
+        else:
+            n, d, h, w = x.shape[0], x.shape[1], x.shape[2], x.shape[3]
+        record = any(ctx.needs_input_grad)
+        out, _, tape = program_forward(layers, tensors, x.contiguous(), (n, d, h, w), dtype, cache, record=record)
+        ctx.tape = _record_weights(tape, tensors) if record else None
+        ctx.dtype = dtype
+        ctx.param_refs = param_refs
+        ctx.ntensors = len(tensors)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        need = list(ctx.needs_input_grad[2:])
+        grads = [None] * ctx.ntensors
+        gx = program_backward(ctx.tape, g.contiguous(), ctx.dtype, need, grads, ctx.param_refs,
+                              ctx.needs_input_grad[1])
+        ctx.tape = None
+        return (None, gx) + tuple(grads)
+
+
+class VAEFn(torch.autograd.Function):
+    """Shape VAE as one autograd node: encoder program -> fc_mean/fc_std/reparam -> fc2 ->
+    decoder program -> softmax head.  Returns (recon, mean, std).  joint_model.py:227-272."""
+
+    @staticmethod
+    def forward(ctx, spec, x, z, scale, use_z, *tensors):
+        enc, dec, fc, dtype, cache, param_refs, dim = spec
+        n, d, h, w = x.shape[0], x.shape[2], x.shape[3], x.shape[4]
+        record = any(ctx.needs_input_grad)
+        ctx.set_materialize_grads(False)
+        hcur, (n, d2, h2, w2), tape_e = program_forward(enc, tensors, x.contiguous(), (n, d, h, w), dtype, cache, record)
+        c = enc[-1].cout
+        s3 = d2 * h2 * w2
+        wm, bm, ws, bs, w2_, b2_ = [tensors[i].detach() for i in fc]
+        if wm.shape[1] != s3 * c:
+            raise RuntimeError("VAE: fc_mean expects flat dim %d but the encoder produced %d (patch size vs. "
+                               "constructor `patch` mismatch)" % (wm.shape[1], s3 * c))
+        mean, std, lat = ops.fc_encode_fwd(hcur, wm, bm, ws, bs, z, scale, use_z, n, s3, c, dim)
+        hdec = ops.fc_decode_fwd(lat, w2_, b2_, n, s3, c, dim, dtype, d2)
+        recon, _, tape_d = program_forward(dec, tensors, hdec, (n, d2, h2, w2), dtype, cache, record)
+        if record:
+            ctx.tape_e = _record_weights(tape_e, tensors)
+            ctx.tape_d = _record_weights(tape_d, tensors)
+            ctx.fc_saved = (hcur, z, scale, use_z, std, lat, (n, s3, c, dim), [tensors[i].detach() for i in fc])
+        ctx.spec_small = (fc, dtype, param_refs)
+        ctx.ntensors = len(tensors)
+        return recon, mean, std
+
+    @staticmethod
+    def backward(ctx, g_recon, g_mean, g_std):
+        fc, dtype, param_refs = ctx.spec_small
+        need = list(ctx.needs_input_grad[5:])
+        grads = [None] * ctx.ntensors
+        hcur, z, scale, use_z, std, lat, (n, s3, c, dim), fcw = ctx.fc_saved
+        wm, bm, ws, bs, w2_, b2_ = fcw
+        i_wm, i_bm, i_ws, i_bs, i_w2, i_b2 = fc
+        dlat = None
+        if g_recon is not None:
+            dh = program_backward(ctx.tape_d, g_recon.contiguous(), dtype, need, grads, param_refs, True)
+            if need[i_w2] or need[i_b2]:
+                tw, tb, acc = _pair_targets(param_refs, need, i_w2, i_b2, tuple(w2_.shape), tuple(b2_.shape), dh.device)
+                dlat = ops.fc_decode_bwd(dh, lat, w2_, n, s3, c, dim, dw2=tw, db2=tb, accumulate=acc)
+                _hand_back(grads, need, i_w2, i_b2, tw, tb, acc)
+            else:
+                dlat = ops.fc_decode_bwd(dh, lat, w2_, n, s3, c, dim)
+        enc_params = any(need[i] for i in (i_wm, i_bm, i_ws, i_bs))
+        # anything upstream of the latent?
+        upstream = ctx.needs_input_grad[1] or enc_params or any(need[e[0].wi] for e in ctx.tape_e)
+        gx = None
+        if upstream and (dlat is not None or g_mean is not None or g_std is not None):
+            tgts = {}
+            acc_flags = set()
+            for i, like in ((i_wm, wm), (i_bm, bm), (i_ws, ws), (i_bs, bs)):
+                t, a = _grad_target(param_refs[i], need[i])
+                if need[i] and t is None:
+                    t = torch.empty_like(like)
+                    a = False
+                tgts[i] = t
+                if need[i]:
+                    acc_flags.add(a)
+            if enc_params and (len(acc_flags) != 1 or not all(need[i] for i in (i_wm, i_bm, i_ws, i_bs))):
+                raise RuntimeError("fc_mean / fc_std parameters must share requires_grad and .grad allocation state")
+            acc = acc_flags.pop() if acc_flags else False
+            dhe = ops.fc_encode_bwd(hcur, wm, ws, z, scale, use_z, std, dlat,
+                                    g_mean.contiguous() if g_mean is not None else None,
+                                    g_std.contiguous() if g_std is not None else None,
+                                    n, s3, c, dim, want_dx=True, dwm=tgts[i_wm], dbm=tgts[i_bm], dws=tgts[i_ws],
+                                    dbs=tgts[i_bs], accumulate=acc)
+            for i in (i_wm, i_bm, i_ws, i_bs):
+                grads[i] = None if (acc or not need[i]) else tgts[i]
+            gx = program_backward(ctx.tape_e, dhe, dtype, need, grads, param_refs, ctx.needs_input_grad[1])
+        ctx.tape_e = ctx.tape_d = ctx.fc_saved = None
+        return (None, gx, None, None, None) + tuple(grads)
+
+
+class DecodeFn(torch.autograd.Function):
+    """VAE decoder only (mid_input=True, joint_model.py:251-271): latent -> recon."""
+
+    @staticmethod
+    def forward(ctx, spec, lat, *tensors):
+        dec, fc, dtype, cache, param_refs, dim, side = spec
+        w2_, b2_ = tensors[fc[4]].detach(), tensors[fc[5]].detach()
+        n = lat.shape[0]
+        c = dec[0].cin
+        s3 = side ** 3
+        record = any(ctx.needs_input_grad)
+        lat = lat.contiguous().float()
+        hdec = ops.fc_decode_fwd(lat, w2_, b2_, n, s3, c, dim, dtype, side)
+        recon, _, tape = program_forward(dec, tensors, hdec, (n, side, side, side), dtype, cache, record)
+        if record:
+            ctx.tape = _record_weights(tape, tensors)
+            ctx.saved = (lat, w2_, b2_, (n, s3, c, dim))
+        ctx.small = (fc, dtype, param_refs)
+        ctx.ntensors = len(tensors)
+        return recon
+
+    @staticmethod
+    def backward(ctx, g):
+        fc, dtype, param_refs = ctx.small
+        need = list(ctx.needs_input_grad[2:])
+        grads = [None] * ctx.ntensors
+        lat, w2_, b2_, (n, s3, c, dim) = ctx.saved
+        dh = program_backward(ctx.tape, g.contiguous(), dtype, need, grads, param_refs, True)
+        i_w2, i_b2 = fc[4], fc[5]
+        if need[i_w2] or need[i_b2]:
+            tw, tb, acc = _pair_targets(param_refs, need, i_w2, i_b2, tuple(w2_.shape), tuple(b2_.shape), dh.device)
+            dlat = ops.fc_decode_bwd(dh, lat, w2_, n, s3, c, dim, dw2=tw, db2=tb, accumulate=acc)
+            _hand_back(grads, need, i_w2, i_b2, tw, tb, acc)
+        else:
+            dlat = ops.fc_decode_bwd(dh, lat, w2_, n, s3, c, dim)
+        ctx.tape = ctx.saved = None
+        return (None, dlat if ctx.needs_input_grad[1] else None) + tuple(grads)

@@ -1,0 +1,266 @@
+"""Tensor-level wrappers over the C ABI (one function per entry point of include/vaeseg_b200.h).
+
+PyTorch supplies device memory and the current CUDA stream; every op launches hand-written
+kernels from libvaeseg_b200.so.  CPU tensors are rejected: there is no fallback path.
+"""
+import torch
+
+from . import _cabi
+from ._cabi import VS_BF16, VS_F32
+
+_DT = {torch.float32: VS_F32, torch.bfloat16: VS_BF16}
+
+
+def _dt(t):
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise RuntimeError("vaeseg_b200: unsupported activation dtype %s" % t.dtype)
+
+
+def _p(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("vaeseg_b200: tensor is on %s; the hot path runs on CUDA only (no CPU fallback)" % t.device)
+    if not t.is_contiguous():
+        raise RuntimeError("vaeseg_b200: tensor must be contiguous")
+    return t.data_ptr()
+
+
+def _f32(t, what):
+    if t is not None and t.dtype != torch.float32:
+        raise RuntimeError("vaeseg_b200: %s must be float32, got %s" % (what, t.dtype))
+    return t
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def has_tcgen05():
+    return bool(_cabi.lib().vs_has_tcgen05())
+
+
+# ---- 3x3x3 convolution ---------------------------------------------------------------
+def pack_conv3_weight(w, want_dgrad=True):
+    """[Cout,Cin,3,3,3] fp32 -> (wf [27,Cin,Cout], wd [27,Cout,Cin] or None)."""
+    cout, cin = w.shape[0], w.shape[1]
+    _f32(w, "weight")
+    wf = torch.empty(27, cin, cout, device=w.device, dtype=torch.float32)
+    wd = torch.empty(27, cout, cin, device=w.device, dtype=torch.float32) if want_dgrad else None
+    _cabi.call("vs_pack_conv3_weight", _p(w), _p(wf), _p(wd), cin, cout, _stream())
+    return wf, wd
+
+
+def conv3_fprop(x, wf, bias, dims, cin, cout, out_dtype, in_planar=False, out_planar=False, want_stats=True):
+    """dims = (N, D, H, W).  Returns (y, stats)."""
+    n, d, h, w = dims
+    dev = x.device
+    if out_planar:
+        y = torch.empty(n, cout, d, h, w, device=dev, dtype=torch.float32)
+    else:
+        y = torch.empty(n, d, h, w, cout, device=dev, dtype=out_dtype)
+    stats = torch.empty(n, cout, 2, device=dev, dtype=torch.float32) if want_stats else None
+    _cabi.call("vs_conv3x3x3_fprop", _dt(x), _dt(y), int(in_planar), int(out_planar), _p(x), _p(_f32(wf, "wf")),
+               _p(_f32(bias, "bias")), _p(y), _p(stats), n, d, h, w, cin, cout, _stream())
+    return y, stats
+
+
+def conv3_dgrad(dy, wd, dims, cin, cout, out_dtype, out_planar=False):
+    """dy: [N,D,H,W,Cout] -> dx [N,D,H,W,Cin] (or planar fp32 [N,Cin,D,H,W])."""
+    n, d, h, w = dims
+    if out_planar:
+        dx = torch.empty(n, cin, d, h, w, device=dy.device, dtype=torch.float32)
+    else:
+        dx = torch.empty(n, d, h, w, cin, device=dy.device, dtype=out_dtype)
+    _cabi.call("vs_conv3x3x3_dgrad", _dt(dy), _dt(dx), int(out_planar), _p(dy), _p(_f32(wd, "wd")), _p(dx),
+               n, d, h, w, cin, cout, _stream())
+    return dx
+
+
+def conv3_wgrad(x, dy, dims, cin, cout, dw=None, db=None, in_planar=False, accumulate=False):
+    """dw [Cout,Cin,3,3,3] fp32 (+)= ; db [Cout] optional.  Returns (dw, db)."""
+    n, d, h, w = dims
+    if dw is None:
+        dw = torch.empty(cout, cin, 3, 3, 3, device=dy.device, dtype=torch.float32)
+        accumulate = False
+    _cabi.call("vs_conv3x3x3_wgrad", _dt(dy), int(in_planar), _p(x), _p(dy), _p(_f32(dw, "dw")), _p(_f32(db, "db")),
+               None, 0, int(accumulate), n, d, h, w, cin, cout, _stream())
+    return dw, db
+
+
+# ---- k2s2 ------------------------------------------------------------------------------
+def k2s2_gather(fine, wt, bias, cdims, a, b):
+    """fine [N,2dc,2hc,2wc,B] -> coarse [N,dc,hc,wc,A]; cdims = (N,dc,hc,wc)."""
+    n, dc, hc, wc = cdims
+    coarse = torch.empty(n, dc, hc, wc, a, device=fine.device, dtype=fine.dtype)
+    _cabi.call("vs_k2s2_gather", _dt(fine), _p(fine), _p(_f32(wt, "wt")), _p(_f32(bias, "bias")), _p(coarse),
+               n, dc, hc, wc, a, b, _stream())
+    return coarse
+
+
+def k2s2_scatter(coarse, wt, bias, cdims, a, b):
+    n, dc, hc, wc = cdims
+    fine = torch.empty(n, 2 * dc, 2 * hc, 2 * wc, b, device=coarse.device, dtype=coarse.dtype)
+    _cabi.call("vs_k2s2_scatter", _dt(coarse), _p(coarse), _p(_f32(wt, "wt")), _p(_f32(bias, "bias")), _p(fine),
+               n, dc, hc, wc, a, b, _stream())
+    return fine
+
+
+def k2s2_wgrad(coarse, fine, cdims, a, b, dwt=None, dbias_coarse=None, dbias_fine=None, accumulate=False):
+    n, dc, hc, wc = cdims
+    if dwt is None:
+        dwt = torch.empty(a, b, 2, 2, 2, device=coarse.device, dtype=torch.float32)
+        accumulate = False
+    _cabi.call("vs_k2s2_wgrad", _dt(coarse), _p(coarse), _p(fine), _p(_f32(dwt, "dwt")), _p(_f32(dbias_coarse, "db")),
+               _p(_f32(dbias_fine, "db")), int(accumulate), n, dc, hc, wc, a, b, _stream())
+    return dwt
+
+
+# ---- InstanceNorm + ReLU -------------------------------------------------------------
+def inorm_relu_apply(y, stats, skip=None):
+    n, c = y.shape[0], y.shape[-1]
+    s = y.numel() // (n * c)
+    a = torch.empty_like(y)
+    _cabi.call("vs_inorm_relu_apply", _dt(y), _p(y), _p(stats), _p(skip), _p(a), n, s, c, _stream())
+    return a
+
+
+def inorm_relu_bwd(g, y, stats):
+    """Returns dy (gradient w.r.t. the raw conv output)."""
+    n, c = y.shape[0], y.shape[-1]
+    s = y.numel() // (n * c)
+    sums = torch.empty(n, c, 2, device=y.device, dtype=torch.float32)
+    _cabi.call("vs_inorm_relu_bwd_reduce", _dt(y), _p(g), _p(y), _p(stats), _p(sums), n, s, c, _stream())
+    dy = torch.empty_like(y)
+    _cabi.call("vs_inorm_relu_bwd_apply", _dt(y), _p(g), _p(y), _p(stats), _p(sums), _p(dy), n, s, c, _stream())
+    return dy
+
+
+def add_inplace(dst, src):
+    assert dst.dtype == src.dtype and dst.numel() == src.numel()
+    _cabi.call("vs_add_inplace", _dt(dst), _p(dst), _p(src), dst.numel(), _stream())
+    return dst
+
+
+# ---- softmax over two classes --------------------------------------------------------
+def softmax2_fwd(logits, dims):
+    n, d, h, w = dims
+    probs = torch.empty(n, 2, d, h, w, device=logits.device, dtype=torch.float32)
+    _cabi.call("vs_softmax2_fwd", _p(_f32(logits, "logits")), _p(probs), n, d * h * w, _stream())
+    return probs
+
+
+def softmax2_bwd(dprobs, probs, dims, out_dtype):
+    n, d, h, w = dims
+    dlogits = torch.empty(n, d, h, w, 2, device=probs.device, dtype=out_dtype)
+    _cabi.call("vs_softmax2_bwd", _dt(dlogits), _p(_f32(dprobs, "dprobs")), _p(_f32(probs, "probs")), _p(dlogits),
+               n, d * h * w, _stream())
+    return dlogits
+
+
+# ---- VAE linear layers -----------------------------------------------------------------
+def fc_encode_fwd(x, wm, bm, ws, bs, z, scale, use_z, batch, s3, c, dim):
+    dev = x.device
+    mean = torch.empty(batch, dim, device=dev, dtype=torch.float32)
+    std = torch.empty_like(mean)
+    lat = torch.empty_like(mean)
+    _cabi.call("vs_fc_encode_fwd", _dt(x), _p(x), _p(wm), _p(bm), _p(ws), _p(bs), _p(z), float(scale), int(use_z),
+               _p(mean), _p(std), _p(lat), batch, s3, c, dim, _stream())
+    return mean, std, lat
+
+
+def fc_decode_fwd(lat, w2, b2, batch, s3, c, dim, out_dtype, side):
+    h = torch.empty(batch, side, side, side, c, device=lat.device, dtype=out_dtype)
+    _cabi.call("vs_fc_decode_fwd", _dt(h), _p(_f32(lat, "lat")), _p(w2), _p(b2), _p(h), batch, s3, c, dim, _stream())
+    return h
+
+
+def fc_decode_bwd(dh, lat, w2, batch, s3, c, dim, dw2=None, db2=None, accumulate=False):
+    dlat = torch.empty(batch, dim, device=dh.device, dtype=torch.float32)
+    _cabi.call("vs_fc_decode_bwd", _dt(dh), _p(dh), _p(lat), _p(w2), _p(dlat), _p(dw2), _p(db2), int(accumulate),
+               batch, s3, c, dim, _stream())
+    return dlat
+
+
+def fc_encode_bwd(x, wm, ws, z, scale, use_z, std, dlat, gmean_ext, gstd_ext, batch, s3, c, dim, want_dx=True,
+                  dwm=None, dbm=None, dws=None, dbs=None, accumulate=False):
+    dev = std.device
+    gbuf = torch.empty(2, batch, dim, device=dev, dtype=torch.float32)
+    dx = torch.empty_like(x) if want_dx else None
+    _cabi.call("vs_fc_encode_bwd", _dt(x), _p(x), _p(wm), _p(ws), _p(z), float(scale), int(use_z), _p(std), _p(dlat),
+               _p(gmean_ext), _p(gstd_ext), _p(gbuf), _p(dx), _p(dwm), _p(dbm), _p(dws), _p(dbs), int(accumulate),
+               batch, s3, c, dim, _stream())
+    return dx
+
+
+# ---- losses ----------------------------------------------------------------------------
+def dice_sums(src, tgt, mode):
+    n, c = src.shape[0], src.shape[1]
+    s = src.numel() // (n * c)
+    sums = torch.empty(n, c, 3, device=src.device, dtype=torch.float32)
+    _cabi.call("vs_dice_sums", _p(_f32(src, "src")), _p(_f32(tgt, "tgt")), int(mode), _p(sums), n, c, s, _stream())
+    return sums
+
+
+def dice_bwd(src, tgt, mode, sums, gper, eps, want_src=True, want_tgt=False, gsrc=None, gtgt=None, accumulate=False):
+    n, c = src.shape[0], src.shape[1]
+    s = src.numel() // (n * c)
+    if want_src and gsrc is None:
+        gsrc = torch.empty_like(src)
+    if want_tgt and gtgt is None:
+        gtgt = torch.empty_like(src)
+    _cabi.call("vs_dice_bwd", _p(src), _p(tgt), int(mode), _p(sums), _p(_f32(gper, "gper")), float(eps), _p(gsrc),
+               _p(gtgt), int(accumulate), n, c, s, _stream())
+    return gsrc, gtgt
+
+
+def kl_fwd(mean, std):
+    out = torch.empty(1, device=mean.device, dtype=torch.float32)
+    _cabi.call("vs_kl_fwd", _p(_f32(mean, "mean")), _p(_f32(std, "std")), _p(out), mean.shape[0], mean.shape[1], _stream())
+    return out
+
+
+def kl_bwd(mean, std, gout):
+    gm, gs = torch.empty_like(mean), torch.empty_like(std)
+    _cabi.call("vs_kl_bwd", _p(mean), _p(std), _p(_f32(gout, "gout")), _p(gm), _p(gs), mean.shape[0], mean.shape[1], _stream())
+    return gm, gs
+
+
+def binarize(a, mode):
+    out = torch.empty_like(a)
+    _cabi.call("vs_binarize", _p(_f32(a, "a")), _p(out), int(mode), a.numel(), _stream())
+    return out
+
+
+def one_hot(label, n_class):
+    n = label.shape[0]
+    s = label.numel() // n
+    out = torch.empty(n, n_class, *label.shape[2:], device=label.device, dtype=torch.float32)
+    _cabi.call("vs_one_hot", _p(_f32(label, "label")), _p(out), n, n_class, s, _stream())
+    return out
+
+
+# ---- optimiser -------------------------------------------------------------------------
+def sgd_step(p, g, buf, lr, momentum, first, gscale=1.0):
+    _cabi.call("vs_sgd_step", _p(_f32(p, "p")), _p(_f32(g, "g")), _p(buf), p.numel(), float(lr), float(momentum),
+               int(first), float(gscale), _stream())
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, gscale=1.0):
+    _cabi.call("vs_adam_step", _p(_f32(p, "p")), _p(_f32(g, "g")), _p(m), _p(v), p.numel(), float(lr), float(beta1),
+               float(beta2), float(eps), int(step), float(gscale), _stream())
+
+
+def ema_update(teacher, student, alpha):
+    _cabi.call("vs_ema_update", _p(_f32(teacher, "teacher")), _p(_f32(student, "student")), teacher.numel(),
+               float(alpha), _stream())
+
+
+def compose_target_loss(terms, lambda_vae, loss_type, use_kl):
+    final = torch.empty(1, device=terms.device, dtype=torch.float32)
+    weights = torch.empty(3, device=terms.device, dtype=torch.float32)
+    _cabi.call("vs_compose_target_loss", _p(_f32(terms, "terms")), float(lambda_vae), int(loss_type), int(use_kl),
+               _p(final), _p(weights), _stream())
+    return final, weights
