@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""Headline benchmark: joint teacher-student train step (seg + frozen-VAE recon + pseudo loss)
+at 96^3 patches -- BASELINE.json config[2] ("C3" in SURVEY.md section 8), volumes/sec.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (one process per GPU)
+  python bench.py --impl reference --steps K --warmup W    reference arm: the CPU oracle port of
+                                                           the reference's PyTorch path, host cores
+
+One JSON line on stdout (rank 0).  `value` times the step with inputs resident in HBM; `e2e`
+times the same step fed from pinned HOST buffers with the loss read back every step.  The
+roofline object is for the kernel signature that takes the largest share of the step, timed
+with CUDA events around its launches inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+PATCH = 96
+PER_GPU_BATCH = 2
+METRIC = "joint train-step volumes/sec at 96^3 patch"
+UNIT = "volumes/s"
+RIDGE = 249.0          # flop/byte, measured peaks
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        p = json.load(open(path))
+        return {"hbm": p["hbm_gbs"], "tensor_burst": p["bf16_tflops"],
+                "tensor": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor": 1400.0, "source": "fallback"}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference's PyTorch CPU path
+# ---------------------------------------------------------------------------------------------
+def cpu_joint_steps(steps, warmup, batch, patch=PATCH, seed=0):
+    """Times `steps` reference-faithful joint steps (main_target.py:520-592,734-736 semantics)
+    on the host cores with all threads.  Returns seconds per step."""
+    from oracle import ref_torch as R
+    from vae_segmentation_b200.synthetic import synth_image, synth_label
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(seed)
+    seg_sd = R.init_seg_state()
+    vae_sd = R.init_vae_state(2, 128, patch)
+    teacher_sd = seg_sd
+    img, label = synth_image(batch, patch), synth_label(batch, patch)
+    bufs = None
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        _, grads = R.joint_target_step(seg_sd, vae_sd, teacher_sd, img, label, lambda_vae=1.0, loss_type=0)
+        seg_sd, bufs = R.sgd_step(seg_sd, grads, bufs, lr=1e-2, momentum=0.9)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return sum(times) / len(times)
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    batch = 1            # bounded sample: one 96^3 volume per step (the CPU step is seconds long)
+    sec = cpu_joint_steps(args.steps, args.warmup, batch)
+    value = batch / sec
+    cores = torch.get_num_threads()
+    sample = "%d steps x %d volume(s) of the 96^3 joint step (oracle port, torch CPU fp32)" % (args.steps, batch)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "joint teacher-student step, 96^3, lambda_vae=1, loss type 0 (BASELINE.json config[2])",
+                       "patch": PATCH, "per_step_batch": batch},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.tmp.flush()
+        rows = [r.strip().split(",") for r in open(self.tmp.name).read().splitlines() if r.strip()]
+        os.unlink(self.tmp.name)
+        mhz, reasons, mx = [], set(), None
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in rows:
+            try:
+                if int(r[0]) != self.gpu_index:
+                    continue
+                mhz.append(float(r[1]))
+                mx = float(r[2])
+                for nm, v in zip(names, r[5:9]):
+                    if v.strip().lower() == "active":
+                        reasons.add(nm)
+            except (ValueError, IndexError):
+                continue
+        if mhz:
+            mhz.sort()
+            out = {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(mhz)}
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+# per-kernel accounting
+# ---------------------------------------------------------------------------------------------
+def kernel_cost(name, key):
+    """ALGORITHMIC (flops, bytes) of one launch, from its shape signature."""
+    size = {0: 4, 1: 2}
+    if name == "vs_conv3x3x3_fprop":
+        idt, odt, _, _, n, d, h, w, cin, cout = key
+        vox = n * d * h * w
+        return 2.0 * 27 * cin * cout * vox, vox * (cin * size[idt] + cout * size[odt])
+    if name == "vs_conv3x3x3_dgrad":
+        idt, odt, _, n, d, h, w, cin, cout = key
+        vox = n * d * h * w
+        return 2.0 * 27 * cin * cout * vox, vox * (cout * size[idt] + cin * size[odt])
+    if name == "vs_conv3x3x3_wgrad":
+        dt, _, _, _, n, d, h, w, cin, cout = key
+        vox = n * d * h * w
+        return 2.0 * 27 * cin * cout * vox, vox * (cin + cout) * size[dt]
+    if name in ("vs_k2s2_gather", "vs_k2s2_scatter", "vs_k2s2_wgrad"):
+        dt = key[0]
+        n, dc, hc, wc, a, b = key[-6:]
+        vox = n * dc * hc * wc
+        return 2.0 * 8 * a * b * vox, vox * (a + 8 * b) * size[dt]
+    if name == "vs_inorm_relu_apply":
+        dt, n, s, c = key
+        return 0.0, 2.0 * n * s * c * size[dt]
+    if name in ("vs_inorm_relu_bwd_reduce",):
+        dt, n, s, c = key
+        return 0.0, 2.0 * n * s * c * size[dt]
+    if name == "vs_inorm_relu_bwd_apply":
+        dt, n, s, c = key
+        return 0.0, 3.0 * n * s * c * size[dt]
+    return 0.0, 0.0
+
+
+class KernelTimer(object):
+    """_cabi profiler hook: CUDA events (on the launching stream) around selected calls."""
+
+    def __init__(self, only=None):
+        self.only = only
+        self.events = {}
+
+    def __call__(self, name, key, launch):
+        sig = (name, key)
+        if self.only is not None and sig != self.only:
+            return launch()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = launch()
+        e1.record()
+        self.events.setdefault(sig, []).append((e0, e1))
+        return rc
+
+    def totals(self):
+        torch.cuda.synchronize()
+        return {sig: (sum(a.elapsed_time(b) for a, b in evs), len(evs)) for sig, evs in self.events.items()}
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--patch", type=int, default=PATCH)
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH)
+    ap.add_argument("--loss-type", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-table", action="store_true", help="also print the per-kernel time table to stderr")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    from vae_segmentation_b200 import _cabi
+    from vae_segmentation_b200 import joint_model as jm
+    from vae_segmentation_b200 import train_step as ts
+    from vae_segmentation_b200.synthetic import synth_image, synth_label
+
+    P, B = args.patch, args.batch
+    torch.manual_seed(0)                     # identical replicas on every rank
+    mk = lambda: jm.Joint([jm.Segmentation(1, 2, norm_type=1), jm.VAE(2, 2, norm_type=1, dim=128, patch=P)])
+    student, teacher = mk(), mk()
+    teacher.load_state_dict(student.state_dict())          # teacher = copy of student (main_target.py:428)
+    student.to(dev).set_precision(args.precision)
+    teacher.to(dev).set_precision(args.precision)
+    trainer = ts.JointTrainer(student, teacher, lr=1e-2, momentum=0.9, lambda_vae=1.0, loss_type=args.loss_type)
+
+    torch.manual_seed(1000 + rank)           # per-rank shard of the global batch
+    img_h = synth_image(B, P).pin_memory()
+    lab_h = synth_label(B, P).pin_memory()
+    img_d, lab_d = img_h.to(dev), lab_h.to(dev)
+    h2d = img_h.numel() * 4 + lab_h.numel() * 4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    def step_resident():
+        return trainer.step(img_d, lab_d)
+
+    loss_host = torch.empty(1).pin_memory()
+
+    def step_e2e():
+        img_d.copy_(img_h, non_blocking=True)
+        lab_d.copy_(lab_h, non_blocking=True)
+        mon = trainer.step(img_d, lab_d)
+        loss_host.copy_(mon["final_loss"].reshape(1), non_blocking=False)      # device->host read of the loss
+
+    # ---- warm-up + kernel table (picks the dominant kernel signature) -----------------------
+    for _ in range(max(args.warmup, 3) - 1):
+        step_resident()
+    table = KernelTimer()
+    _cabi.set_profiler(table)
+    step_resident()
+    _cabi.set_profiler(None)
+    totals = table.totals()
+    dominant = max(totals.items(), key=lambda kv: kv[1][0])[0]
+    step_ms_profiled = sum(v[0] for v in totals.values())
+    if args.kernel_table and rank == 0:
+        by_name = {}
+        for (nm, key), (ms, cnt) in totals.items():
+            a = by_name.setdefault(nm, [0.0, 0])
+            a[0] += ms
+            a[1] += cnt
+        for nm, (ms, cnt) in sorted(by_name.items(), key=lambda kv: -kv[1][0]):
+            print("%-28s %4d launches %9.3f ms" % (nm, cnt, ms), file=sys.stderr)
+        for (nm, key), (ms, cnt) in sorted(totals.items(), key=lambda kv: -kv[1][0])[:25]:
+            fl, by = kernel_cost(nm, key)
+            print("  %-24s %-44s x%d %8.3f ms  %7.1f TF/s %7.1f GB/s" % (
+                nm, key, cnt, ms, fl * cnt / ms / 1e9 if ms else 0, by * cnt / ms / 1e6 if ms else 0), file=sys.stderr)
+
+    # ---- timed: resident inputs, with CUDA events around the dominant kernel only -----------
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    only = KernelTimer(only=dominant)
+    _cabi.set_profiler(only)
+    calls0 = _cabi.N_CALLS
+    ms_total = timed(step_resident, args.steps)
+    launches = _cabi.N_CALLS - calls0
+    _cabi.set_profiler(None)
+    dom_ms, dom_cnt = only.totals()[dominant]
+    # ---- timed: end to end from pinned host buffers -----------------------------------------
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    clock_info = clocks.stop()
+
+    global_batch = B * world
+    value = global_batch * args.steps / (ms_total / 1e3)
+    e2e_value = global_batch * args.steps / (ms_e2e / 1e3)
+
+    peaks = measured_peaks()
+    fl, by = kernel_cost(*dominant)
+    dur_s = dom_ms / dom_cnt / 1e3
+    if by > 0 and fl / by >= RIDGE:
+        roof = {"bound": "tensor", "achieved": fl / dur_s / 1e12, "peak": peaks["tensor"], "unit": "TFLOP/s"}
+    else:
+        roof = {"bound": "hbm", "achieved": by / dur_s / 1e9, "peak": peaks["hbm"], "unit": "GB/s"}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    roof["traffic"] = None
+    roof["kernel"] = "%s%s" % dominant
+    roof["launches_timed"] = dom_cnt
+    roof["avg_us"] = dur_s * 1e6
+    roof["share_of_step"] = totals[dominant][0] / step_ms_profiled
+    roof["peak_source"] = peaks["source"] + (" sustained" if roof["bound"] == "tensor" else "")
+    tr_path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(tr_path):
+        roof["traffic"] = json.load(open(tr_path)).get(roof["kernel"])
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+            "data": "synthetic",
+            "config": {"workload": "joint teacher-student step (student Seg+frozen VAE fwd, teacher Joint fwd, recon + "
+                                   "pseudo Dice, bwd through VAE into Seg, SGD m=.9), BASELINE.json config[2]",
+                       "patch": P, "per_gpu_batch": B, "global_batch": global_batch, "lambda_vae": 1.0,
+                       "loss_type": args.loss_type, "parallelism": "dp%d" % world,
+                       "l2": "per-step working set (>1 GB activations) exceeds the 126 MB L2; no explicit flush"},
+            "clocks": clock_info,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "roofline": roof}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sec = cpu_joint_steps(2, 1, 1, patch=P)
+        line["cpu_baseline"] = {"value": 1.0 / sec, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": "2 timed steps (1 warm-up) of the same joint step at batch 1, %d^3, oracle "
+                                          "port of the reference's torch CPU fp32 path" % P}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -44,11 +44,16 @@ int vs_pack_conv3_weight(const float* w, float* wf, float* wd, int cin, int cout
 /* ---- 3x3x3 convolution, padding 1 (Conv3d at joint_model.py:40-46,106,224,366) ------- */
 /* x: NDHWC `in_dtype` (or planar fp32 when in_planar=1, used by the in_blocks whose input is
  * the module's NCDHW fp32 tensor); wpk: fp32 [27][Cin][Cout]; bias fp32 [Cout] or NULL;
- * y: NDHWC `out_dtype` (or planar fp32 when out_planar=1); stats: fp32 [N][Cout][2]
- * (sum, sum of squares of the fp32 accumulators; zeroed by the call) or NULL.            */
+ * y: NDHWC `out_dtype` (or planar fp32 when out_planar=1); stats: fp64 [N][Cout][2]
+ * (sum, sum of squares of the fp32 accumulators, accumulated in double because
+ * E[x^2]-E[x]^2 cancels in fp32; zeroed by the call) or NULL.            */
+/* shift: fp32 scratch [N][Cout] or NULL.  When given, the call first evaluates the convolution
+ * at voxel (1,1,1) of every (n, co) and subtracts that constant from the whole output channel
+ * before statistics and storage: InstanceNorm is invariant to a per-(n,c) shift, and storing
+ * deviations keeps bf16 precision on channels with |mean| >> sigma (VAE layers on masks).     */
 int vs_conv3x3x3_fprop(int in_dtype, int out_dtype, int in_planar, int out_planar,
-                       const void* x, const float* wpk, const float* bias, void* y, float* stats,
-                       int n, int d, int h, int w, int cin, int cout, void* stream);
+                       const void* x, const float* wpk, const float* bias, void* y, double* stats,
+                       float* shift, int n, int d, int h, int w, int cin, int cout, void* stream);
 /* dgrad is the same contraction with the flipped/transposed pack (wd of vs_pack_conv3_weight):
  * dx = conv3(dy, wd), Cin/Cout swapped.  Provided as its own symbol for the binding's clarity. */
 int vs_conv3x3x3_dgrad(int in_dtype, int out_dtype, int out_planar,
@@ -79,14 +84,14 @@ int vs_k2s2_wgrad(int dtype, const void* coarse, const void* fine, float* dwt,
                   int n, int dc, int hc, int wc, int a, int b, void* stream);
 
 /* ---- InstanceNorm3d(affine=False, eps 1e-5) + ReLU (joint_model.py:9-15,38,104) ------- */
-/* a = relu((y-mean)*rstd) [+ skip]; mean/rstd derived from stats[N][C][2] over `s` voxels.  */
-int vs_inorm_relu_apply(int dtype, const void* y, const float* stats, const void* skip, void* a,
+/* a = relu((y-mean)*rstd) [+ skip]; mean/rstd derived from the fp64 stats[N][C][2] over `s` voxels.  */
+int vs_inorm_relu_apply(int dtype, const void* y, const double* stats, const void* skip, void* a,
                         int n, long long s, int c, void* stream);
-/* sums[N][C][2] = (sum g*mask, sum g*mask*xhat) with mask = [y > mean]; zeroed by the call. */
-int vs_inorm_relu_bwd_reduce(int dtype, const void* g, const void* y, const float* stats, float* sums,
+/* sums[N][C][2] (fp64) = (sum g*mask, sum g*mask*xhat) with mask = [y > mean]; zeroed by the call. */
+int vs_inorm_relu_bwd_reduce(int dtype, const void* g, const void* y, const double* stats, double* sums,
                              int n, long long s, int c, void* stream);
 /* dy = rstd * (g*mask - sums0/s - xhat * sums1/s)                                         */
-int vs_inorm_relu_bwd_apply(int dtype, const void* g, const void* y, const float* stats, const float* sums,
+int vs_inorm_relu_bwd_apply(int dtype, const void* g, const void* y, const double* stats, const double* sums,
                             void* dy, int n, long long s, int c, void* stream);
 /* dst += src (gradient fan-in at the additive skips, joint_model.py:381,383)               */
 int vs_add_inplace(int dtype, void* dst, const void* src, long long count, void* stream);

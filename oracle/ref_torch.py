@@ -179,7 +179,7 @@ def vae_forward(sd, x, if_random=False, scale=1, mid_input=False, z=None):
         return vae_decode(sd, x)
     mean, std = vae_encode(sd, x)
     if z is None:
-        z = torch.randn(mean.size(0), mean.size(1))
+        z = torch.randn(mean.size(0), mean.size(1)).to(mean.dtype)
     lat = mean + z * std * scale if if_random else mean
     return vae_decode(sd, lat), mean, std
 
@@ -219,7 +219,7 @@ def confident_binarize(a, hi=0.8, lo=0.2):
 def one_hot(label, n_class=2):
     # main_target.py:520-522 / main_source.py:390-392: zeros.scatter_(1, label.long(), 1)
     lab = label.long()
-    out = torch.zeros(lab.size(0), n_class, *lab.shape[2:])
+    out = torch.zeros(lab.size(0), n_class, *lab.shape[2:], dtype=label.dtype if label.is_floating_point() else torch.float32)
     return out.scatter_(1, lab, 1)
 
 
@@ -280,8 +280,8 @@ def compose_target_loss(recon_loss, dsc_loss_fake, klloss, lambda_vae=1.0, loss_
 # ----------------------------------------------------------------------------------
 # train steps
 # ----------------------------------------------------------------------------------
-def _leafify(sd, requires_grad=True):
-    return OrderedDict((k, v.detach().clone().requires_grad_(requires_grad)) for k, v in sd.items())
+def _leafify(sd, requires_grad=True, dtype=None):
+    return OrderedDict((k, v.detach().clone().to(dtype or v.dtype).requires_grad_(requires_grad)) for k, v in sd.items())
 
 
 def sgd_step(sd, grads, bufs, lr=1e-2, momentum=0.9):
@@ -303,19 +303,25 @@ def ema_update(teacher_sd, student_sd, alpha=0.995):
     return OrderedDict((k, alpha * teacher_sd[k] + (1 - alpha) * student_sd[k]) for k in student_sd)
 
 
-def seg_train_step(seg_sd, img, label, eps=0.0001):
-    """main_source.py:415-437: loss = 1 - avg_dsc(pred, onehot)[fg]; returns loss, grads, pred."""
-    sd = _leafify(seg_sd)
+def seg_train_step(seg_sd, img, label, eps=0.0001, dtype=None):
+    """main_source.py:415-437: loss = 1 - avg_dsc(pred, onehot)[fg]; returns loss, grads, pred.
+    dtype=torch.float64 gives the high-precision "truth" used to calibrate fp32 noise."""
+    sd = _leafify(seg_sd, dtype=dtype)
+    if dtype is not None:
+        img, label = img.to(dtype), label.to(dtype)
     pred = seg_forward(sd, img)
     loss = 1 - avg_dsc(pred, one_hot(label), botindex=1, topindex=2, eps=eps)
     loss.backward()
     return loss.detach(), OrderedDict((k, v.grad) for k, v in sd.items()), pred.detach()
 
 
-def vae_train_step(vae_sd, label, scale=0.35, z=None, eps=0.0001):
+def vae_train_step(vae_sd, label, scale=0.35, z=None, eps=0.0001, dtype=None):
     """main_source.py:389-406: recon = VAE(onehot, if_random=True, scale=.35);
     loss = 1 - avg_dsc(recon, onehot)[fg] + 2e-5 * KL."""
-    sd = _leafify(vae_sd)
+    sd = _leafify(vae_sd, dtype=dtype)
+    if dtype is not None:
+        label = label.to(dtype)
+        z = z.to(dtype) if z is not None else None
     oh = one_hot(label)
     recon, mean, std = vae_forward(sd, oh, if_random=True, scale=scale, z=z)
     kl = kl_loss(mean, std)
@@ -327,13 +333,15 @@ def vae_train_step(vae_sd, label, scale=0.35, z=None, eps=0.0001):
 
 
 def joint_target_step(student_seg_sd, vae_sd, teacher_seg_sd, img, label, lambda_vae=1.0,
-                      loss_type=0, kl=False, confident=False, only_pseudo=False):
+                      loss_type=0, kl=False, confident=False, only_pseudo=False, dtype=None):
     """main_target.py:520-592,734-736: student Joint fwd (dropout=True), teacher Joint
     fwd (sets mean/std, F8), pseudo = binarize(teacher pred), recon / pseudo Dice,
     backward through the frozen VAE into Seg (F9)."""
-    sd = _leafify(student_seg_sd)
-    vsd = _leafify(vae_sd, requires_grad=False)
-    tsd = _leafify(teacher_seg_sd, requires_grad=False)
+    sd = _leafify(student_seg_sd, dtype=dtype)
+    vsd = _leafify(vae_sd, requires_grad=False, dtype=dtype)
+    tsd = _leafify(teacher_seg_sd, requires_grad=False, dtype=dtype)
+    if dtype is not None:
+        img, label = img.to(dtype), label.to(dtype)
     pred, recon, _, _ = joint_forward(sd, vsd, img, dropout=True)
     with torch.no_grad():
         t_pred, _, t_mean, t_std = joint_forward(tsd, vsd, img, dropout=False)

@@ -21,7 +21,7 @@ _SIGNATURES = {
     "vs_version": [],
     "vs_has_tcgen05": [],
     "vs_pack_conv3_weight": [_P, _P, _P, _I, _I, _P],
-    "vs_conv3x3x3_fprop": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "vs_conv3x3x3_fprop": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "vs_conv3x3x3_dgrad": [_I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "vs_conv3_wgrad_workspace_bytes": [_I, _I, _I, _I, _I, _I],
     "vs_conv3x3x3_wgrad": [_I, _I, _P, _P, _P, _P, _P, _Z, _I, _I, _I, _I, _I, _I, _I, _P],
@@ -78,8 +78,28 @@ def last_error():
     return msg.decode("utf-8", "replace") if msg else ""
 
 
+N_CALLS = 0            # C-ABI calls made so far (each launches >= 1 kernel); bench.py reports the delta
+_profiler = None       # optional callable(name, key, launch) installed by bench.py / tools
+
+
+def call_key(name, args):
+    """Shape signature of a call: its non-pointer arguments."""
+    return tuple(a for a, t in zip(args, _SIGNATURES[name]) if t is not _P)
+
+
+def set_profiler(fn):
+    global _profiler
+    _profiler = fn
+
+
 def call(name, *args):
     """Calls an int-returning entry point; a negative status raises RuntimeError."""
-    rc = getattr(lib(), name)(*args)
+    global N_CALLS
+    N_CALLS += 1
+    fn = getattr(lib(), name)
+    if _profiler is not None:
+        rc = _profiler(name, call_key(name, args), lambda: fn(*args))
+    else:
+        rc = fn(*args)
     if rc != 0:
         raise RuntimeError("vaeseg_b200.%s failed (status %d): %s" % (name, rc, last_error()))

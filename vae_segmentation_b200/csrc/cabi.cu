@@ -26,8 +26,8 @@ int vs_sm_count() {
 }
 
 extern "C" int vs_conv3x3x3_fprop_direct(int in_dtype, int out_dtype, int in_planar, int out_planar, const void* x,
-                                         const float* wpk, const float* bias, void* y, float* stats, int n, int d,
-                                         int h, int w, int cin, int cout, void* stream);
+                                         const float* wpk, const float* bias, void* y, double* stats, float* shift,
+                                         int n, int d, int h, int w, int cin, int cout, void* stream);
 
 extern "C" const char* vs_last_error_string(void) { return g_err; }
 extern "C" int vs_version(void) { return 100; }
@@ -40,15 +40,15 @@ extern "C" int vs_has_tcgen05(void) {
 }
 
 extern "C" int vs_conv3x3x3_fprop(int in_dtype, int out_dtype, int in_planar, int out_planar, const void* x,
-                                  const float* wpk, const float* bias, void* y, float* stats, int n, int d, int h,
-                                  int w, int cin, int cout, void* stream) {
-    return vs_conv3x3x3_fprop_direct(in_dtype, out_dtype, in_planar, out_planar, x, wpk, bias, y, stats, n, d, h, w,
-                                     cin, cout, stream);
+                                  const float* wpk, const float* bias, void* y, double* stats, float* shift, int n,
+                                  int d, int h, int w, int cin, int cout, void* stream) {
+    return vs_conv3x3x3_fprop_direct(in_dtype, out_dtype, in_planar, out_planar, x, wpk, bias, y, stats, shift, n, d, h,
+                                     w, cin, cout, stream);
 }
 
 extern "C" int vs_conv3x3x3_dgrad(int in_dtype, int out_dtype, int out_planar, const void* dy, const float* wdpk,
                                   void* dx, int n, int d, int h, int w, int cin, int cout, void* stream) {
     // dx[.., cin] = conv3(dy[.., cout], wd[27][cout][cin]): the fprop contraction with channels swapped
-    return vs_conv3x3x3_fprop_direct(in_dtype, out_dtype, 0, out_planar, dy, wdpk, nullptr, dx, nullptr, n, d, h, w,
+    return vs_conv3x3x3_fprop_direct(in_dtype, out_dtype, 0, out_planar, dy, wdpk, nullptr, dx, nullptr, nullptr, n, d, h, w,
                                      cout, cin, stream);
 }

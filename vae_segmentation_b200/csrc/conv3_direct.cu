@@ -56,10 +56,11 @@ __device__ __forceinline__ void load_halo(float4 (*xs)[HV], const TI* __restrict
 template <typename TI, typename TO, int COB, bool IN_PLANAR, bool OUT_PLANAR>
 __global__ void __launch_bounds__(NT) conv3_direct_kernel(const TI* __restrict__ x, const float* __restrict__ wpk,
                                                           const float* __restrict__ bias, TO* __restrict__ y,
-                                                          float* __restrict__ stats, ConvDims p) {
+                                                          double* __restrict__ stats,
+                                                          const float* __restrict__ shift, ConvDims p) {
     __shared__ float4 xs[2][HV];
     __shared__ float4 ws[27][CIB][COB / 4];
-    __shared__ float sred[COB][2];
+    __shared__ double sred[COB][2];
 
     int n, d0, h0, w0;
     decode_tile(blockIdx.x, p, n, d0, h0, w0);
@@ -133,14 +134,21 @@ __global__ void __launch_bounds__(NT) conv3_direct_kernel(const TI* __restrict__
             acc0[j] += b; acc1[j] += b;
         }
     }
+    if (shift != nullptr) {
+#pragma unroll
+        for (int j = 0; j < COB; ++j) {
+            float k = (co0 + j < p.cout) ? shift[(long long)n * p.cout + co0 + j] : 0.f;
+            acc0[j] -= k; acc1[j] -= k;
+        }
+    }
     if (stats != nullptr) {
-        if (t < COB * 2) sred[t >> 1][t & 1] = 0.f;
+        if (t < COB * 2) sred[t >> 1][t & 1] = 0.0;
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < COB; ++j) {
-            float a = v0 ? acc0[j] : 0.f, b = v1 ? acc1[j] : 0.f;
-            float s = warp_sum(a + b);
-            float q = warp_sum(a * a + b * b);
+            const double a = v0 ? (double)acc0[j] : 0.0, b = v1 ? (double)acc1[j] : 0.0;
+            const double s = warp_sum(a + b);
+            const double q = warp_sum(a * a + b * b);
             if ((t & 31) == 0) { atomicAdd(&sred[j][0], s); atomicAdd(&sred[j][1], q); }
         }
         __syncthreads();
@@ -174,6 +182,38 @@ __global__ void __launch_bounds__(NT) conv3_direct_kernel(const TI* __restrict__
                 for (int j = 0; j < COB; ++j) if (co0 + j < p.cout) Store<TO>::st(py + j, acc[j]);
             }
         }
+    }
+}
+
+// shift[n][co] = conv3(x, w) at voxel (1,1,1): lanes <-> 32 consecutive output channels
+// (coalesced weight reads), the 8 warps split the 27*Cin terms.
+template <typename TI, bool IN_PLANAR>
+__global__ void __launch_bounds__(256) conv3_shift_kernel(const TI* __restrict__ x, const float* __restrict__ wpk,
+                                                          float* __restrict__ shift, ConvDims p) {
+    __shared__ float red[8][32];
+    const int n = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int co = blockIdx.x * 32 + lane;
+    const long long S = (long long)p.d * p.h * p.w;
+    const int terms = 27 * p.cin;
+    float acc = 0.f;
+    for (int i = warp; i < terms; i += 8) {
+        const int tap = i / p.cin, ci = i - tap * p.cin;
+        const int gd = tap / 9, gh = (tap / 3) % 3, gw = tap % 3;       // voxel (1,1,1) + tap - 1
+        float xv = 0.f;
+        if (gd < p.d && gh < p.h && gw < p.w) {
+            const long long vox = ((long long)gd * p.h + gh) * p.w + gw;
+            if (IN_PLANAR) xv = reinterpret_cast<const float*>(x)[((long long)n * p.cin + ci) * S + vox];
+            else xv = Store<TI>::ld(x + ((long long)n * S + vox) * p.cin + ci);
+        }
+        if (co < p.cout) acc = fmaf(xv, wpk[(long long)i * p.cout + co], acc);
+    }
+    red[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && co < p.cout) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += red[k][lane];
+        shift[(long long)n * p.cout + co] = s;
     }
 }
 
@@ -284,24 +324,30 @@ ConvDims make_dims(int n, int d, int h, int w, int cin, int cout) {
 }
 
 template <typename TI, typename TO, bool IN_PLANAR, bool OUT_PLANAR>
-int launch_conv3(const void* x, const float* wpk, const float* bias, void* y, float* stats, const ConvDims& p,
-                 cudaStream_t st) {
+int launch_conv3(const void* x, const float* wpk, const float* bias, void* y, double* stats, float* shift,
+                 const ConvDims& p, cudaStream_t st) {
+    if (shift != nullptr) {
+        dim3 sgrid((p.cout + 31) / 32, p.n);
+        conv3_shift_kernel<TI, IN_PLANAR><<<sgrid, 256, 0, st>>>((const TI*)x, wpk, shift, p);
+        VS_CHECK_LAUNCH("conv3_shift_kernel");
+    }
     const long long tiles = (long long)p.n * p.tiles_d * p.tiles_h * p.tiles_w;
     VS_REQUIRE(tiles < 2147483647LL, VS_ERR_SHAPE, "conv3: too many tiles");
     const int cob = p.cout >= 16 ? 16 : (p.cout >= 8 ? 8 : 4);
     dim3 grid((unsigned)tiles, (p.cout + cob - 1) / cob);
     if (cob == 16)
-        conv3_direct_kernel<TI, TO, 16, IN_PLANAR, OUT_PLANAR><<<grid, NT, 0, st>>>((const TI*)x, wpk, bias, (TO*)y, stats, p);
+        conv3_direct_kernel<TI, TO, 16, IN_PLANAR, OUT_PLANAR><<<grid, NT, 0, st>>>((const TI*)x, wpk, bias, (TO*)y, stats, shift, p);
     else if (cob == 8)
-        conv3_direct_kernel<TI, TO, 8, IN_PLANAR, OUT_PLANAR><<<grid, NT, 0, st>>>((const TI*)x, wpk, bias, (TO*)y, stats, p);
+        conv3_direct_kernel<TI, TO, 8, IN_PLANAR, OUT_PLANAR><<<grid, NT, 0, st>>>((const TI*)x, wpk, bias, (TO*)y, stats, shift, p);
     else
-        conv3_direct_kernel<TI, TO, 4, IN_PLANAR, OUT_PLANAR><<<grid, NT, 0, st>>>((const TI*)x, wpk, bias, (TO*)y, stats, p);
+        conv3_direct_kernel<TI, TO, 4, IN_PLANAR, OUT_PLANAR><<<grid, NT, 0, st>>>((const TI*)x, wpk, bias, (TO*)y, stats, shift, p);
     VS_CHECK_LAUNCH("conv3_direct_kernel");
     return VS_OK;
 }
 
 int conv3_common(int in_dtype, int out_dtype, int in_planar, int out_planar, const void* x, const float* wpk,
-                 const float* bias, void* y, float* stats, int n, int d, int h, int w, int cin, int cout, void* stream) {
+                 const float* bias, void* y, double* stats, float* shift, int n, int d, int h, int w, int cin, int cout,
+                 void* stream) {
     VS_REQUIRE(n > 0 && d > 0 && h > 0 && w > 0 && cin > 0 && cout > 0, VS_ERR_SHAPE, "conv3: bad shape");
     VS_REQUIRE(x && wpk && y, VS_ERR_SHAPE, "conv3: null pointer");
     VS_REQUIRE(vs_aligned16(x) && vs_aligned16(y) && vs_aligned16(wpk), VS_ERR_ALIGN, "conv3: pointers must be 16B aligned");
@@ -310,19 +356,19 @@ int conv3_common(int in_dtype, int out_dtype, int in_planar, int out_planar, con
     if (out_planar) VS_REQUIRE(out_dtype == VS_F32, VS_ERR_UNSUPPORTED, "conv3: planar output is fp32 only");
     cudaStream_t st = (cudaStream_t)stream;
     ConvDims p = make_dims(n, d, h, w, cin, cout);
-    if (stats) VS_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * n * cout, st), "conv3 stats memset");
+    if (stats) VS_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * n * cout, st), "conv3 stats memset");
     if (in_planar) {
         VS_REQUIRE(!out_planar, VS_ERR_UNSUPPORTED, "conv3: planar->planar unsupported");
-        if (out_dtype == VS_F32) return launch_conv3<float, float, true, false>(x, wpk, bias, y, stats, p, st);
-        return launch_conv3<float, bf16, true, false>(x, wpk, bias, y, stats, p, st);
+        if (out_dtype == VS_F32) return launch_conv3<float, float, true, false>(x, wpk, bias, y, stats, shift, p, st);
+        return launch_conv3<float, bf16, true, false>(x, wpk, bias, y, stats, shift, p, st);
     }
     if (out_planar) {
-        if (in_dtype == VS_F32) return launch_conv3<float, float, false, true>(x, wpk, bias, y, stats, p, st);
-        return launch_conv3<bf16, float, false, true>(x, wpk, bias, y, stats, p, st);
+        if (in_dtype == VS_F32) return launch_conv3<float, float, false, true>(x, wpk, bias, y, stats, shift, p, st);
+        return launch_conv3<bf16, float, false, true>(x, wpk, bias, y, stats, shift, p, st);
     }
-    if (in_dtype == VS_F32 && out_dtype == VS_F32) return launch_conv3<float, float, false, false>(x, wpk, bias, y, stats, p, st);
-    if (in_dtype == VS_BF16 && out_dtype == VS_BF16) return launch_conv3<bf16, bf16, false, false>(x, wpk, bias, y, stats, p, st);
-    if (in_dtype == VS_BF16 && out_dtype == VS_F32) return launch_conv3<bf16, float, false, false>(x, wpk, bias, y, stats, p, st);
+    if (in_dtype == VS_F32 && out_dtype == VS_F32) return launch_conv3<float, float, false, false>(x, wpk, bias, y, stats, shift, p, st);
+    if (in_dtype == VS_BF16 && out_dtype == VS_BF16) return launch_conv3<bf16, bf16, false, false>(x, wpk, bias, y, stats, shift, p, st);
+    if (in_dtype == VS_BF16 && out_dtype == VS_F32) return launch_conv3<bf16, float, false, false>(x, wpk, bias, y, stats, shift, p, st);
     VS_FAIL(VS_ERR_UNSUPPORTED, "conv3: dtype combination in=%d out=%d unsupported", in_dtype, out_dtype);
 }
 
@@ -364,9 +410,10 @@ extern "C" int vs_pack_conv3_weight(const float* w, float* wf, float* wd, int ci
 }
 
 extern "C" int vs_conv3x3x3_fprop_direct(int in_dtype, int out_dtype, int in_planar, int out_planar, const void* x,
-                                         const float* wpk, const float* bias, void* y, float* stats, int n, int d,
-                                         int h, int w, int cin, int cout, void* stream) {
-    return conv3_common(in_dtype, out_dtype, in_planar, out_planar, x, wpk, bias, y, stats, n, d, h, w, cin, cout, stream);
+                                         const float* wpk, const float* bias, void* y, double* stats, float* shift,
+                                         int n, int d, int h, int w, int cin, int cout, void* stream) {
+    return conv3_common(in_dtype, out_dtype, in_planar, out_planar, x, wpk, bias, y, stats, shift, n, d, h, w, cin, cout,
+                        stream);
 }
 
 extern "C" size_t vs_conv3_wgrad_workspace_bytes(int, int, int, int, int, int) { return 0; }

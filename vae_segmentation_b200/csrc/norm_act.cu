@@ -10,12 +10,12 @@ namespace {
 constexpr int NT = 256;
 
 template <typename T>
-__global__ void __launch_bounds__(NT) inorm_relu_apply_kernel(const T* __restrict__ y, const float* __restrict__ stats,
+__global__ void __launch_bounds__(NT) inorm_relu_apply_kernel(const T* __restrict__ y, const double* __restrict__ stats,
                                                               const T* __restrict__ skip, T* __restrict__ a,
                                                               long long s, int c) {
     __shared__ float sm[256], sr[256];
     const int n = blockIdx.y, t = threadIdx.x;
-    const float inv_s = 1.f / (float)s;
+    const double inv_s = 1.0 / (double)s;
     for (int ch = t; ch < c; ch += NT) in_mean_rstd(stats + ((long long)n * c + ch) * 2, inv_s, sm[ch], sr[ch]);
     __syncthreads();
     const int groups = c / 8;
@@ -40,20 +40,22 @@ __global__ void __launch_bounds__(NT) inorm_relu_apply_kernel(const T* __restric
 // sums[n][c] = (sum g*mask, sum g*mask*xhat)
 template <typename T>
 __global__ void __launch_bounds__(NT) inorm_relu_bwd_reduce_kernel(const T* __restrict__ g, const T* __restrict__ y,
-                                                                   const float* __restrict__ stats,
-                                                                   float* __restrict__ sums, long long s, int c) {
+                                                                   const double* __restrict__ stats,
+                                                                   double* __restrict__ sums, long long s, int c) {
     __shared__ float sm[256], sr[256];
-    __shared__ float red[NT][17];
+    __shared__ double red[NT][17];
     const int n = blockIdx.y, t = threadIdx.x;
-    const float inv_s = 1.f / (float)s;
+    const double inv_s = 1.0 / (double)s;
     for (int ch = t; ch < c; ch += NT) in_mean_rstd(stats + ((long long)n * c + ch) * 2, inv_s, sm[ch], sr[ch]);
     __syncthreads();
     const int groups = c / 8, lanes = NT / groups;
     const int cg = (t % groups) * 8, lane = t / groups;
     const long long base = (long long)n * s * c;
-    float a0[8], a1[8];
+    // fp64 accumulation: dy = rstd*(g - mean(g) - xhat*mean(g*xhat)) cancels heavily when g is
+    // nearly constant, and ATen's CPU path (the oracle) also accumulates these sums in double
+    double a0[8], a1[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) { a0[q] = 0.f; a1[q] = 0.f; }
+    for (int q = 0; q < 8; ++q) { a0[q] = 0.0; a1[q] = 0.0; }
     for (long long v = (long long)blockIdx.x * lanes + lane; v < s; v += (long long)gridDim.x * lanes) {
         float gv[8], yv[8];
         Store<T>::ld8(g + base + v * c + cg, gv);
@@ -62,8 +64,8 @@ __global__ void __launch_bounds__(NT) inorm_relu_bwd_reduce_kernel(const T* __re
         for (int q = 0; q < 8; ++q) {
             const float xh = (yv[q] - sm[cg + q]) * sr[cg + q];
             const float gm = xh > 0.f ? gv[q] : 0.f;
-            a0[q] += gm;
-            a1[q] = fmaf(gm, xh, a1[q]);
+            a0[q] += (double)gm;
+            a1[q] += (double)gm * (double)xh;
         }
     }
 #pragma unroll
@@ -72,7 +74,7 @@ __global__ void __launch_bounds__(NT) inorm_relu_bwd_reduce_kernel(const T* __re
     for (int o = t; o < c * 2; o += NT) {
         const int ch = o >> 1, which = o & 1;
         const int gg = ch / 8, q = ch % 8;
-        float sacc = 0.f;
+        double sacc = 0.0;
         for (int l = 0; l < lanes; ++l) sacc += red[l * groups + gg][which * 8 + q];
         atomicAdd(sums + ((long long)n * c + ch) * 2 + which, sacc);
     }
@@ -80,16 +82,16 @@ __global__ void __launch_bounds__(NT) inorm_relu_bwd_reduce_kernel(const T* __re
 
 template <typename T>
 __global__ void __launch_bounds__(NT) inorm_relu_bwd_apply_kernel(const T* __restrict__ g, const T* __restrict__ y,
-                                                                  const float* __restrict__ stats,
-                                                                  const float* __restrict__ sums, T* __restrict__ dy,
+                                                                  const double* __restrict__ stats,
+                                                                  const double* __restrict__ sums, T* __restrict__ dy,
                                                                   long long s, int c) {
     __shared__ float sm[256], sr[256], m0[256], m1[256];
     const int n = blockIdx.y, t = threadIdx.x;
-    const float inv_s = 1.f / (float)s;
+    const double inv_s = 1.0 / (double)s;
     for (int ch = t; ch < c; ch += NT) {
         in_mean_rstd(stats + ((long long)n * c + ch) * 2, inv_s, sm[ch], sr[ch]);
-        m0[ch] = sums[((long long)n * c + ch) * 2] * inv_s;
-        m1[ch] = sums[((long long)n * c + ch) * 2 + 1] * inv_s;
+        m0[ch] = (float)(sums[((long long)n * c + ch) * 2] * inv_s);
+        m1[ch] = (float)(sums[((long long)n * c + ch) * 2 + 1] * inv_s);
     }
     __syncthreads();
     const int groups = c / 8;
@@ -167,7 +169,7 @@ int check_norm(const void* a, const void* b, int n, long long s, int c, const ch
 
 }  // namespace
 
-extern "C" int vs_inorm_relu_apply(int dtype, const void* y, const float* stats, const void* skip, void* a,
+extern "C" int vs_inorm_relu_apply(int dtype, const void* y, const double* stats, const void* skip, void* a,
                                    int n, long long s, int c, void* stream) {
     int rc = check_norm(y, a, n, s, c, "inorm_relu_apply");
     if (rc) return rc;
@@ -178,12 +180,12 @@ extern "C" int vs_inorm_relu_apply(int dtype, const void* y, const float* stats,
     return VS_OK;
 }
 
-extern "C" int vs_inorm_relu_bwd_reduce(int dtype, const void* g, const void* y, const float* stats, float* sums,
+extern "C" int vs_inorm_relu_bwd_reduce(int dtype, const void* g, const void* y, const double* stats, double* sums,
                                         int n, long long s, int c, void* stream) {
     int rc = check_norm(g, y, n, s, c, "inorm_relu_bwd_reduce");
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    VS_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * n * c, st), "inorm bwd memset");
+    VS_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * n * c, st), "inorm bwd memset");
     const int lanes = NT / (c / 8);
     long long blocks = (s + (long long)lanes * 8 - 1) / ((long long)lanes * 8);
     dim3 grid((unsigned)max(1LL, min(blocks, (long long)vs_sm_count() * 4)), n);
@@ -193,7 +195,7 @@ extern "C" int vs_inorm_relu_bwd_reduce(int dtype, const void* g, const void* y,
     return VS_OK;
 }
 
-extern "C" int vs_inorm_relu_bwd_apply(int dtype, const void* g, const void* y, const float* stats, const float* sums,
+extern "C" int vs_inorm_relu_bwd_apply(int dtype, const void* g, const void* y, const double* stats, const double* sums,
                                        void* dy, int n, long long s, int c, void* stream) {
     int rc = check_norm(g, dy, n, s, c, "inorm_relu_bwd_apply");
     if (rc) return rc;

@@ -63,11 +63,20 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// mean / rstd of InstanceNorm3d (biased variance, eps 1e-5) from (sum, sumsq) over s voxels
-__device__ __forceinline__ void in_mean_rstd(const float* st, float inv_s, float& mean, float& rstd) {
-    mean = st[0] * inv_s;
-    float var = fmaxf(st[1] * inv_s - mean * mean, 0.f);
-    rstd = rsqrtf(var + 1e-5f);
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// mean / rstd of InstanceNorm3d (biased variance, eps 1e-5) from (sum, sumsq) over s voxels.
+// The sums are fp64: E[x^2]-E[x]^2 cancels catastrophically in fp32 when |mean| >> sigma
+// (e.g. the VAE in_block on a mostly-constant mask), and B200 has full-rate-enough FP64.
+__device__ __forceinline__ void in_mean_rstd(const double* st, double inv_s, float& mean, float& rstd) {
+    const double m = st[0] * inv_s;
+    const double var = fmax(st[1] * inv_s - m * m, 0.0);
+    mean = (float)m;
+    rstd = (float)(1.0 / sqrt(var + 1e-5));
 }
 
 static inline int vs_ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -19,6 +19,16 @@ from . import ops
 
 C3IN, K2DOWN, K2UP, HEAD = "c3in", "k2down", "k2up", "head"
 
+# tools/precision_probe*.py only: names of tensor classes to round through bf16 while running the fp32
+# check mode ("y", "a", "g", "dy", "k2"), to attribute bf16-mode error to a storage point.  Empty in production.
+SIMULATE_BF16 = set()
+
+
+def _sim(t, what):
+    if what in SIMULATE_BF16 and t is not None and t.dtype == torch.float32:
+        return t.bfloat16().float()
+    return t
+
 
 class Layer(object):
     __slots__ = ("kind", "name", "cin", "cout", "wi", "bi", "save_as", "skip_from", "in_planar")
@@ -97,18 +107,19 @@ def program_forward(layers, tensors, x, dims, dtype, cache, record=True):
             # the conv bias is a no-op ahead of InstanceNorm(affine=False): skipped
             y, stats = ops.conv3_fprop(cur, wf, None, (n, d, h, w), L.cin, L.cout, dtype, in_planar=L.in_planar)
             skip = slots[L.skip_from] if L.skip_from is not None else None
-            a = ops.inorm_relu_apply(y, stats, skip)
+            y = _sim(y, "y")
+            a = _sim(ops.inorm_relu_apply(y, stats, skip), "a")
             if record:
                 tape.append((L, cur, y, stats, (n, d, h, w), wd))
             cur = a
         elif L.kind == K2DOWN:
             d, h, w = d // 2, h // 2, w // 2
-            out = ops.k2s2_gather(cur, tensors[L.wi].detach(), tensors[L.bi].detach(), (n, d, h, w), L.cout, L.cin)
+            out = _sim(ops.k2s2_gather(cur, tensors[L.wi].detach(), tensors[L.bi].detach(), (n, d, h, w), L.cout, L.cin), "k2")
             if record:
                 tape.append((L, cur, None, None, (n, d, h, w), None))
             cur = out
         elif L.kind == K2UP:
-            out = ops.k2s2_scatter(cur, tensors[L.wi].detach(), tensors[L.bi].detach(), (n, d, h, w), L.cin, L.cout)
+            out = _sim(ops.k2s2_scatter(cur, tensors[L.wi].detach(), tensors[L.bi].detach(), (n, d, h, w), L.cin, L.cout), "k2")
             if record:
                 tape.append((L, cur, None, None, (n, d, h, w), None))
             d, h, w = d * 2, h * 2, w * 2
@@ -142,7 +153,7 @@ def program_backward(tape, g, dtype, need, grads, param_refs, need_input_grad):
         if L.kind == C3IN:
             if L.skip_from is not None:
                 pending[L.skip_from] = g
-            dy = ops.inorm_relu_bwd(g, y, stats)
+            dy = _sim(ops.inorm_relu_bwd(g, y, stats), "dy")
             if need[L.wi]:
                 tgt, acc = _grad_target(param_refs[L.wi], True)
                 dw, _ = ops.conv3_wgrad(x_in, dy, dims, L.cin, L.cout, dw=tgt, in_planar=L.in_planar, accumulate=acc)
@@ -151,29 +162,29 @@ def program_backward(tape, g, dtype, need, grads, param_refs, need_input_grad):
                 # exactly zero: the bias cancels in InstanceNorm
                 tgt, acc = _grad_target(param_refs[L.bi], True)
                 grads[L.bi] = None if acc else torch.zeros(L.cout, device=dy.device, dtype=torch.float32)
-            g = ops.conv3_dgrad(dy, wd, dims, L.cin, L.cout, dtype, out_planar=L.in_planar) if want_dx else None
+            g = _sim(ops.conv3_dgrad(dy, wd, dims, L.cin, L.cout, dtype, out_planar=L.in_planar), "g") if want_dx else None
         elif L.kind == K2DOWN:
             # dims are the coarse (output) dims; g is the coarse gradient
             if need[L.wi] or need[L.bi]:
                 tw, tb, acc = _pair_targets(param_refs, need, L.wi, L.bi, (L.cout, L.cin, 2, 2, 2), (L.cout,), g.device)
                 ops.k2s2_wgrad(g, x_in, dims, L.cout, L.cin, dwt=tw, dbias_coarse=tb, accumulate=acc)
                 _hand_back(grads, need, L.wi, L.bi, tw, tb, acc)
-            g = ops.k2s2_scatter(g, wt, None, dims, L.cout, L.cin) if want_dx else None
+            g = _sim(ops.k2s2_scatter(g, wt, None, dims, L.cout, L.cin), "g") if want_dx else None
         elif L.kind == K2UP:
             # dims are the coarse (input) dims; g is the fine gradient
             if need[L.wi] or need[L.bi]:
                 tw, tb, acc = _pair_targets(param_refs, need, L.wi, L.bi, (L.cin, L.cout, 2, 2, 2), (L.cout,), g.device)
                 ops.k2s2_wgrad(x_in, g, dims, L.cin, L.cout, dwt=tw, dbias_fine=tb, accumulate=acc)
                 _hand_back(grads, need, L.wi, L.bi, tw, tb, acc)
-            g = ops.k2s2_gather(g, wt, None, dims, L.cin, L.cout) if want_dx else None
+            g = _sim(ops.k2s2_gather(g, wt, None, dims, L.cin, L.cout), "g") if want_dx else None
         elif L.kind == HEAD:
             probs = y
-            dlogits = ops.softmax2_bwd(g, probs, dims, dtype)
+            dlogits = _sim(ops.softmax2_bwd(g, probs, dims, dtype), "dy")
             if need[L.wi] or need[L.bi]:
                 tw, tb, acc = _pair_targets(param_refs, need, L.wi, L.bi, (L.cout, L.cin, 3, 3, 3), (L.cout,), g.device)
                 ops.conv3_wgrad(x_in, dlogits, dims, L.cin, L.cout, dw=tw, db=tb, in_planar=L.in_planar, accumulate=acc)
                 _hand_back(grads, need, L.wi, L.bi, tw, tb, acc)
-            g = ops.conv3_dgrad(dlogits, wd, dims, L.cin, L.cout, dtype, out_planar=L.in_planar) if want_dx else None
+            g = _sim(ops.conv3_dgrad(dlogits, wd, dims, L.cin, L.cout, dtype, out_planar=L.in_planar), "g") if want_dx else None
     return g
 
 
@@ -212,7 +223,6 @@ class ProgramFn(torch.autograd.Function):
         grads = [None] * ctx.ntensors
         gx = program_backward(ctx.tape, g.contiguous(), ctx.dtype, need, grads, ctx.param_refs,
                               ctx.needs_input_grad[1])
-        ctx.tape = None
         return (None, gx) + tuple(grads)
 
 
@@ -287,7 +297,6 @@ class VAEFn(torch.autograd.Function):
             for i in (i_wm, i_bm, i_ws, i_bs):
                 grads[i] = None if (acc or not need[i]) else tgts[i]
             gx = program_backward(ctx.tape_e, dhe, dtype, need, grads, param_refs, ctx.needs_input_grad[1])
-        ctx.tape_e = ctx.tape_d = ctx.fc_saved = None
         return (None, gx, None, None, None) + tuple(grads)
 
 
@@ -326,5 +335,4 @@ class DecodeFn(torch.autograd.Function):
             _hand_back(grads, need, i_w2, i_b2, tw, tb, acc)
         else:
             dlat = ops.fc_decode_bwd(dh, lat, w2_, n, s3, c, dim)
-        ctx.tape = ctx.saved = None
         return (None, dlat if ctx.needs_input_grad[1] else None) + tuple(grads)

@@ -53,17 +53,22 @@ def pack_conv3_weight(w, want_dgrad=True):
     return wf, wd
 
 
-def conv3_fprop(x, wf, bias, dims, cin, cout, out_dtype, in_planar=False, out_planar=False, want_stats=True):
-    """dims = (N, D, H, W).  Returns (y, stats)."""
+def conv3_fprop(x, wf, bias, dims, cin, cout, out_dtype, in_planar=False, out_planar=False, want_stats=True,
+                shifted=None):
+    """dims = (N, D, H, W).  Returns (y, stats).  `shifted` (default: same as want_stats) subtracts the
+    per-(n,co) reference-voxel value from the output (InstanceNorm-invariant, see the header)."""
     n, d, h, w = dims
     dev = x.device
     if out_planar:
         y = torch.empty(n, cout, d, h, w, device=dev, dtype=torch.float32)
     else:
         y = torch.empty(n, d, h, w, cout, device=dev, dtype=out_dtype)
-    stats = torch.empty(n, cout, 2, device=dev, dtype=torch.float32) if want_stats else None
+    stats = torch.empty(n, cout, 2, device=dev, dtype=torch.float64) if want_stats else None
+    if shifted is None:
+        shifted = want_stats
+    shift = torch.empty(n, cout, device=dev, dtype=torch.float32) if shifted else None
     _cabi.call("vs_conv3x3x3_fprop", _dt(x), _dt(y), int(in_planar), int(out_planar), _p(x), _p(_f32(wf, "wf")),
-               _p(_f32(bias, "bias")), _p(y), _p(stats), n, d, h, w, cin, cout, _stream())
+               _p(_f32(bias, "bias")), _p(y), _p(stats), _p(shift), n, d, h, w, cin, cout, _stream())
     return y, stats
 
 
@@ -131,7 +136,7 @@ def inorm_relu_bwd(g, y, stats):
     """Returns dy (gradient w.r.t. the raw conv output)."""
     n, c = y.shape[0], y.shape[-1]
     s = y.numel() // (n * c)
-    sums = torch.empty(n, c, 2, device=y.device, dtype=torch.float32)
+    sums = torch.empty(n, c, 2, device=y.device, dtype=torch.float64)
     _cabi.call("vs_inorm_relu_bwd_reduce", _dt(y), _p(g), _p(y), _p(stats), _p(sums), n, s, c, _stream())
     dy = torch.empty_like(y)
     _cabi.call("vs_inorm_relu_bwd_apply", _dt(y), _p(g), _p(y), _p(stats), _p(sums), _p(dy), n, s, c, _stream())

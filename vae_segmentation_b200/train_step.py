@@ -1,0 +1,227 @@
+"""Train-step harness: the hot-loop bodies of the reference drivers as reusable objects.
+
+  SegTrainer    main_source.py:415-437,660-661   seg_train   (1 - Dice_fg, SGD m=.9)
+  VAETrainer    main_source.py:389-406,660-661   vae_train   (1 - Dice_fg + 2e-5 KL, if_random, scale .35)
+  JointTrainer  main_target.py:508-592,734-736   domain_adaptation teacher-student step incl.
+                EMA teacher (:508-518), dynamic lambda type 8 (:550-560), KL option, confident
+                pseudo labels, and the test-time-training inner loop (:807-900)
+
+The reference's module-level script code is restated as methods; the arithmetic is the
+drop-in modules + fused losses.  Differences that do not change results: parameters and
+gradients live in flat fp32 arenas so the optimiser / EMA / gradient all-reduce are ONE
+kernel / collective each; pseudo labels and one-hot targets are never materialised (the
+Dice reduction thresholds / compares on the fly); the dynamic-lambda thresholds are
+evaluated on the device (no .item() sync).  Data parallelism = one process per
+GPU (torch.distributed, NCCL): per-rank batch shards, one gradient all-reduce per step and,
+for type 8, a 1-float all-reduce of the recon Dice so every rank takes the same branch.
+"""
+import torch
+import torch.distributed as dist
+
+from . import evaluation as ev
+from . import ops
+
+
+class FlatArena(object):
+    """Re-homes a module's parameters (and their .grad) into contiguous fp32 arenas."""
+
+    def __init__(self, module, with_grad=True):
+        self.module = module
+        self.params = [p for p in module.parameters()]
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("FlatArena: move the module to CUDA first")
+        self.data = torch.empty(n, device=dev, dtype=torch.float32)
+        self.grad = torch.zeros(n, device=dev, dtype=torch.float32) if with_grad else None
+        off = 0
+        for p in self.params:
+            k = p.numel()
+            self.data[off:off + k].copy_(p.data.reshape(-1))
+            p.data = self.data[off:off + k].view(p.shape)
+            if with_grad and p.requires_grad:
+                p.grad = self.grad[off:off + k].view(p.shape)
+            off += k
+        self.numel = n
+        if hasattr(module, "invalidate_packs"):
+            module.invalidate_packs()
+
+    def zero_grad(self):
+        if self.grad is not None:
+            self.grad.zero_()
+
+
+class FusedSGD(object):
+    """torch.optim.SGD(lr, momentum, dampening 0, wd 0) over a FlatArena in one launch."""
+
+    def __init__(self, arena, lr=1e-2, momentum=0.9):
+        self.arena, self.lr, self.momentum = arena, lr, momentum
+        self.buf = torch.zeros_like(arena.data) if momentum != 0 else None
+        self.steps = 0
+
+    def step(self, gscale=1.0):
+        ops.sgd_step(self.arena.data, self.arena.grad, self.buf, self.lr, self.momentum, first=(self.steps == 0),
+                     gscale=gscale)
+        self.steps += 1
+        self.arena.module.invalidate_packs()
+
+
+class FusedAdam(object):
+    def __init__(self, arena, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        self.arena, self.lr, self.betas, self.eps = arena, lr, betas, eps
+        self.m = torch.zeros_like(arena.data)
+        self.v = torch.zeros_like(arena.data)
+        self.steps = 0
+
+    def step(self, gscale=1.0):
+        self.steps += 1
+        ops.adam_step(self.arena.data, self.arena.grad, self.m, self.v, self.lr, self.betas[0], self.betas[1],
+                      self.eps, self.steps, gscale=gscale)
+        self.arena.module.invalidate_packs()
+
+
+def _world():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def allreduce_mean_(flat_grad):
+    """Sum over ranks in place; returns the scale (1/world) the optimiser kernel applies, so
+    the averaging costs no extra pass.  Matches DataParallel's loss-on-gathered-batch mean
+    for equal per-rank batches."""
+    world = _world()
+    if world > 1:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
+    return 1.0 / world
+
+
+def _fg(per):
+    return per
+
+
+class SegTrainer(object):
+    def __init__(self, seg, lr=1e-2, momentum=0.9, eps=0.0001):
+        self.seg = seg
+        self.arena = FlatArena(seg)
+        self.opt = FusedSGD(self.arena, lr, momentum)
+        self.eps = eps                       # main_source.py:150-182 uses 1e-4
+
+    def loss(self, img, label):
+        pred = self.seg.predict(img)
+        return 1 - ev.avg_dsc_fused(pred, label, "label", botindex=1, topindex=2, eps=self.eps), pred
+
+    def step(self, img, label):
+        self.arena.zero_grad()
+        loss, _ = self.loss(img, label)
+        loss.backward()
+        self.opt.step(allreduce_mean_(self.arena.grad))
+        return {"dice_loss": loss.detach()}
+
+
+class VAETrainer(object):
+    def __init__(self, vae, lr=1e-2, momentum=0.9, scale=0.35, eps=0.0001):
+        self.vae = vae
+        self.arena = FlatArena(vae)
+        self.opt = FusedSGD(self.arena, lr, momentum)
+        self.scale, self.eps = scale, eps
+
+    def loss(self, label, z=None):
+        onehot = ev.one_hot(label, 2)
+        recon, mean, std = self.vae(onehot, if_random=True, scale=self.scale, z=z)
+        kl = ev.KLloss({"mean": mean, "std": std})
+        dsc = 1 - ev.avg_dsc_fused(recon, label, "label", botindex=1, topindex=2, eps=self.eps)
+        return dsc + 0.00002 * kl, dsc, kl, recon
+
+    def step(self, label, z=None):
+        self.arena.zero_grad()
+        loss, dsc, kl, _ = self.loss(label, z)
+        loss.backward()
+        self.opt.step(allreduce_mean_(self.arena.grad))
+        return {"final_loss": loss.detach(), "dice_loss": dsc.detach(), "kl_loss": kl.detach()}
+
+
+class JointTrainer(object):
+    """Teacher-student target-domain step.  `student` / `teacher` are Joint modules sharing
+    the frozen VAE architecture; only student.Seg trains (main_target.py:396-433)."""
+
+    def __init__(self, student, teacher, lr=1e-2, momentum=0.9, lambda_vae=1.0, loss_type=0, kl=False,
+                 confident=False, only_pseudo=False, alpha=0.995, adam=False, faithful_teacher=True):
+        self.student, self.teacher = student, teacher
+        for p in student.Vae.parameters():
+            p.requires_grad = False
+        for p in teacher.parameters():
+            p.requires_grad = False
+        self.arena = FlatArena(student.Seg)
+        self.teacher_arena = FlatArena(teacher.Seg, with_grad=False)
+        self.opt = FusedAdam(self.arena, lr) if adam else FusedSGD(self.arena, lr, momentum)
+        self.lambda_vae, self.loss_type, self.kl = lambda_vae, loss_type, kl
+        self.confident, self.only_pseudo, self.alpha = confident, only_pseudo, alpha
+        self.faithful_teacher = faithful_teacher
+
+    def ema_teacher(self):
+        # main_target.py:512-516 on the Seg state_dict
+        ops.ema_update(self.teacher_arena.data, self.arena.data, self.alpha)
+        self.teacher.invalidate_packs()
+
+    def losses(self, img, label, student=None):
+        """Forward of one step; returns (final_loss, dict of monitored terms)."""
+        student = student or self.student
+        batch = {"img": img}
+        batch = student(batch, "img", "pred", "recon_pred", dropout=True)            # main_target.py:531
+        with torch.no_grad():                                                         # :532 (frozen teacher)
+            if self.faithful_teacher or self.kl:
+                tb = self.teacher({"img": img}, "img", "only_fake", "unused_recon")
+            else:
+                tb = self.teacher.Seg({"img": img}, "img", "only_fake")
+                tb["mean"] = tb["std"] = None
+        pred = batch["pred"]
+        recon_loss = 1 - ev.avg_dsc_fused(pred, batch["recon_pred"], "tensor", botindex=1, topindex=2)      # :543
+        dsc_loss = 1 - ev.avg_dsc_fused(pred.detach(), label, "label", botindex=1, topindex=2)             # :545 (monitor)
+        dsc_loss_fake = 1 - ev.avg_dsc_fused(pred, tb["only_fake"], "confident" if self.confident else "binarize",
+                                             botindex=1, topindex=2)                                        # :534-537,546
+        klloss = ev.KLloss(tb) if tb.get("mean") is not None else torch.zeros((), device=img.device)       # :544 (teacher's, F8)
+        if self.only_pseudo:
+            final = dsc_loss_fake
+        else:
+            terms = torch.stack([recon_loss.detach(), dsc_loss_fake.detach(), klloss.detach()])
+            if self.loss_type == 8 and _world() > 1:
+                # every rank must take the same lambda branch: threshold the global-batch mean
+                g = terms[0:1].clone()
+                dist.all_reduce(g, op=dist.ReduceOp.SUM)
+                terms = torch.cat([g / _world(), terms[1:]])
+            _, wts = ops.compose_target_loss(terms, self.lambda_vae, self.loss_type, self.kl)
+            final = wts[0] * recon_loss + wts[1] * dsc_loss_fake + (wts[2] * klloss if self.kl else 0)
+        mon = {"final_loss": final.detach(), "recon_loss": recon_loss.detach(), "dice_loss": dsc_loss.detach(),
+               "dice_loss_fake": dsc_loss_fake.detach(), "kl_loss": klloss.detach()}
+        return final, mon, batch
+
+    def step(self, img, label, update_teacher=False):
+        if update_teacher:
+            self.ema_teacher()
+        self.arena.zero_grad()
+        final, mon, _ = self.losses(img, label)
+        final.backward()
+        self.opt.step(allreduce_mean_(self.arena.grad))
+        return mon
+
+    def test_time_train(self, finetune, img, label, iters=1, lr_finetune=1e-2):
+        """main_target.py:807-900: per validation case, `finetune` (a Joint) starts from the
+        student's weights and takes `iters` plain-SGD (momentum 0, fresh optimiser) steps on
+        the same loss; cases are independent, so under data parallelism they are simply
+        distributed over ranks with no collective.  Returns (student pred, finetuned pred)."""
+        ft = getattr(self, "_ft_arena", None)
+        if ft is None or ft.module is not finetune.Seg:
+            for p in finetune.Vae.parameters():
+                p.requires_grad = False
+            ft = self._ft_arena = FlatArena(finetune.Seg)
+        ft.data.copy_(self.arena.data)                                                # :810 load_state_dict
+        finetune.invalidate_packs()
+        for _ in range(iters):
+            ft.zero_grad()
+            final, _, _ = self.losses(img, label, student=finetune)
+            final.backward()
+            ops.sgd_step(ft.data, ft.grad, None, lr_finetune, 0.0, first=True)       # :886 SGD(lr_finetune, momentum 0)
+            finetune.invalidate_packs()
+        with torch.no_grad():                                                         # :902-914
+            p0 = self.student.Seg.predict(img)
+            p1 = finetune.Seg.predict(img)
+        return p0, p1
