@@ -40,10 +40,17 @@ int vs_has_tcgen05(void);
 /* Conv3d 3x3x3 weight [Cout,Cin,27] -> wf[27][Cin][Cout] (fprop) and, when wd != NULL,
  * wd[27 (flipped)][Cout][Cin] (dgrad operand).  joint_model.py:40,43,46,106,224,366 */
 int vs_pack_conv3_weight(const float* w, float* wf, float* wd, int cin, int cout, void* stream);
+/* bf16 UMMA B-operand pack of the same weight for the tcgen05 path (dgrad=1: flipped taps, channels swapped).
+ * vs_conv3_tc_pack_bytes() returns 0 when the tensor-core path does not take the shape
+ * (it takes Cin == 8 or Cin %% 16 == 0, Cout %% 8 == 0).                                                   */
+size_t vs_conv3_tc_pack_bytes(int cin, int cout, int dgrad);
+int vs_pack_conv3_weight_tc(const float* w, void* out, int cin, int cout, int dgrad, void* stream);
 
 /* ---- 3x3x3 convolution, padding 1 (Conv3d at joint_model.py:40-46,106,224,366) ------- */
 /* x: NDHWC `in_dtype` (or planar fp32 when in_planar=1, used by the in_blocks whose input is
- * the module's NCDHW fp32 tensor); wpk: fp32 [27][Cin][Cout]; bias fp32 [Cout] or NULL;
+ * the module's NCDHW fp32 tensor); wpk: fp32 [27][Cin][Cout]; wtc: bf16 tensor-core pack or NULL
+ * (non-NULL + bf16 NDHWC in/out + no bias -> tcgen05/TMEM/TMA implicit GEMM, else the CUDA-core
+ * direct kernel); bias fp32 [Cout] or NULL;
  * y: NDHWC `out_dtype` (or planar fp32 when out_planar=1); stats: fp64 [N][Cout][2]
  * (sum, sum of squares of the fp32 accumulators, accumulated in double because
  * E[x^2]-E[x]^2 cancels in fp32; zeroed by the call) or NULL.            */
@@ -52,12 +59,12 @@ int vs_pack_conv3_weight(const float* w, float* wf, float* wd, int cin, int cout
  * before statistics and storage: InstanceNorm is invariant to a per-(n,c) shift, and storing
  * deviations keeps bf16 precision on channels with |mean| >> sigma (VAE layers on masks).     */
 int vs_conv3x3x3_fprop(int in_dtype, int out_dtype, int in_planar, int out_planar,
-                       const void* x, const float* wpk, const float* bias, void* y, double* stats,
+                       const void* x, const float* wpk, const void* wtc, const float* bias, void* y, double* stats,
                        float* shift, int n, int d, int h, int w, int cin, int cout, void* stream);
 /* dgrad is the same contraction with the flipped/transposed pack (wd of vs_pack_conv3_weight):
  * dx = conv3(dy, wd), Cin/Cout swapped.  Provided as its own symbol for the binding's clarity. */
 int vs_conv3x3x3_dgrad(int in_dtype, int out_dtype, int out_planar,
-                       const void* dy, const float* wdpk, void* dx,
+                       const void* dy, const float* wdpk, const void* wdtc, void* dx,
                        int n, int d, int h, int w, int cin, int cout, void* stream);
 /* dw[Cout,Cin,27] (+)= sum_v dy[v,co] * x[v+tap,ci]; db[Cout] (+)= sum_v dy (db may be NULL).
  * x may be planar fp32 (in_planar=1).  accumulate=0 overwrites.  workspace: fp32

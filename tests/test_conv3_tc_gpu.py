@@ -1,0 +1,64 @@
+"""tcgen05/TMEM/TMA implicit-GEMM convolution against torch.nn.functional (CPU fp32) and against the
+CUDA-core direct kernel on identical bf16 operands: fprop (+ shifted output + fp64 statistics) and dgrad."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from vae_segmentation_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+# (n, d, h, w, cin, cout): ragged extents exercise partial tiles (tile = 4 x 16 x 8) and TMA zero fill
+CASES = [(1, 4, 16, 8, 16, 16), (2, 5, 17, 9, 16, 16), (1, 7, 20, 19, 8, 8), (2, 6, 9, 11, 8, 16), (1, 8, 18, 10, 16, 8),
+         (1, 9, 12, 12, 32, 32), (1, 6, 6, 6, 64, 64), (2, 3, 3, 3, 128, 64), (1, 6, 6, 6, 64, 128), (1, 5, 7, 6, 32, 16),
+         (1, 3, 3, 3, 256, 256), (1, 12, 24, 24, 16, 32)]
+
+
+def to_ndhwc(x):
+    return x.permute(0, 2, 3, 4, 1).contiguous().to(DEV, torch.bfloat16)
+
+
+def from_ndhwc(x):
+    return x.float().cpu().permute(0, 4, 1, 2, 3).contiguous()
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_tc_fprop_and_dgrad(case):
+    if not ops.has_tcgen05():
+        pytest.fail("library built without the tcgen05 kernels")
+    n, d, h, w, cin, cout = case
+    torch.manual_seed(sum(case))
+    x = torch.randn(n, cin, d, h, w).bfloat16().float()
+    wt = (torch.randn(cout, cin, 3, 3, 3) * 0.1)
+    wq = wt.bfloat16().float()                       # the tensor-core path rounds weights to bf16
+    y_ref = F.conv3d(x, wq, None, padding=1)
+    wd = wt.to(DEV)
+    wf, wdg = ops.pack_conv3_weight(wd)
+    wtc = ops.pack_conv3_weight_tc(wd, dgrad=False)
+    wdtc = ops.pack_conv3_weight_tc(wd, dgrad=True)
+    assert wtc is not None and wdtc is not None
+    xd = to_ndhwc(x)
+    dims = (n, d, h, w)
+    y, stats = ops.conv3_fprop(xd, wf, None, dims, cin, cout, torch.bfloat16, shifted=False, wtc=wtc)
+    torch.cuda.synchronize()
+    got = from_ndhwc(y)
+    scale = y_ref.abs().max().item()
+    assert (got - y_ref).abs().max().item() < 1e-2 * scale, "tc fprop max err %.3e (scale %.3e)" % ((got - y_ref).abs().max().item(), scale)
+    s_ref = torch.stack([y_ref.double().sum((2, 3, 4)), (y_ref.double() ** 2).sum((2, 3, 4))], -1)
+    assert torch.allclose(stats.cpu(), s_ref, rtol=2e-3, atol=2e-3 * s_ref.abs().max().item())
+    # shifted variant (what the InstanceNorm layers use)
+    ys, st2 = ops.conv3_fprop(xd, wf, None, dims, cin, cout, torch.bfloat16, shifted=True, wtc=wtc)
+    ys_ref = y_ref - F.conv3d(x, wt, None, padding=1)[:, :, 1:2, 1:2, 1:2]
+    assert (from_ndhwc(ys) - ys_ref).abs().max().item() < 1.5e-2 * scale
+    # dgrad
+    gy = torch.randn_like(y_ref).bfloat16().float()
+    dx_ref = F.conv_transpose3d(gy, wq, None, padding=1)
+    dx = ops.conv3_dgrad(to_ndhwc(gy), wdg, dims, cin, cout, torch.bfloat16, wdtc=wdtc)
+    torch.cuda.synchronize()
+    gscale = dx_ref.abs().max().item()
+    assert (from_ndhwc(dx) - dx_ref).abs().max().item() < 1e-2 * gscale
+    # same operands through the CUDA-core kernel agree to bf16 output rounding
+    y2, _ = ops.conv3_fprop(xd, wq.to(DEV).reshape(cout, cin, 27).permute(2, 1, 0).contiguous(), None, dims, cin, cout,
+                            torch.bfloat16, shifted=False, wtc=None)
+    assert (y2.float() - y.float()).abs().max().item() < 1e-2 * scale

@@ -21,8 +21,10 @@ _SIGNATURES = {
     "vs_version": [],
     "vs_has_tcgen05": [],
     "vs_pack_conv3_weight": [_P, _P, _P, _I, _I, _P],
-    "vs_conv3x3x3_fprop": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
-    "vs_conv3x3x3_dgrad": [_I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "vs_conv3_tc_pack_bytes": [_I, _I, _I],
+    "vs_pack_conv3_weight_tc": [_P, _P, _I, _I, _I, _P],
+    "vs_conv3x3x3_fprop": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "vs_conv3x3x3_dgrad": [_I, _I, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "vs_conv3_wgrad_workspace_bytes": [_I, _I, _I, _I, _I, _I],
     "vs_conv3x3x3_wgrad": [_I, _I, _P, _P, _P, _P, _P, _Z, _I, _I, _I, _I, _I, _I, _I, _P],
     "vs_k2s2_gather": [_I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
@@ -49,7 +51,8 @@ _SIGNATURES = {
     "vs_ema_update": [_P, _P, _L, _F, _P],
     "vs_compose_target_loss": [_P, _F, _I, _I, _P, _P, _P],
 }
-_RESTYPES = {"vs_last_error_string": c_char_p, "vs_conv3_wgrad_workspace_bytes": c_size_t}
+_RESTYPES = {"vs_last_error_string": c_char_p, "vs_conv3_wgrad_workspace_bytes": c_size_t,
+             "vs_conv3_tc_pack_bytes": c_size_t}
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -29,6 +29,18 @@ extern "C" int vs_conv3x3x3_fprop_direct(int in_dtype, int out_dtype, int in_pla
                                          const float* wpk, const float* bias, void* y, double* stats, float* shift,
                                          int n, int d, int h, int w, int cin, int cout, void* stream);
 
+extern "C" int vs_conv3_shift_internal(int in_dtype, int in_planar, const void* x, const float* wpk, float* shift, int n,
+                                       int d, int h, int w, int cin, int cout, void* stream);
+#ifdef VS_WITH_TCGEN05
+extern "C" int vs_conv3x3x3_tc(const void* x, const void* wtc, void* y, double* stats, const float* shift, int n, int d,
+                               int h, int w, int gin, int gout, void* stream);
+extern "C" size_t vs_conv3_tc_pack_bytes(int cin, int cout, int dgrad);
+#endif
+
+static bool tc_eligible(int gin, int gout) {
+    return (gin == 8 || (gin % 16 == 0 && gin >= 16)) && gout % 8 == 0 && gout >= 8;
+}
+
 extern "C" const char* vs_last_error_string(void) { return g_err; }
 extern "C" int vs_version(void) { return 100; }
 extern "C" int vs_has_tcgen05(void) {
@@ -40,15 +52,40 @@ extern "C" int vs_has_tcgen05(void) {
 }
 
 extern "C" int vs_conv3x3x3_fprop(int in_dtype, int out_dtype, int in_planar, int out_planar, const void* x,
-                                  const float* wpk, const float* bias, void* y, double* stats, float* shift, int n,
-                                  int d, int h, int w, int cin, int cout, void* stream) {
+                                  const float* wpk, const void* wtc, const float* bias, void* y, double* stats,
+                                  float* shift, int n, int d, int h, int w, int cin, int cout, void* stream) {
+#ifdef VS_WITH_TCGEN05
+    if (wtc != nullptr && in_dtype == VS_BF16 && out_dtype == VS_BF16 && !in_planar && !out_planar && bias == nullptr &&
+        tc_eligible(cin, cout)) {
+        if (shift != nullptr) {
+            int rc = vs_conv3_shift_internal(in_dtype, 0, x, wpk, shift, n, d, h, w, cin, cout, stream);
+            if (rc) return rc;
+        }
+        return vs_conv3x3x3_tc(x, wtc, y, stats, shift, n, d, h, w, cin, cout, stream);
+    }
+#else
+    (void)wtc;
+#endif
     return vs_conv3x3x3_fprop_direct(in_dtype, out_dtype, in_planar, out_planar, x, wpk, bias, y, stats, shift, n, d, h,
                                      w, cin, cout, stream);
 }
 
 extern "C" int vs_conv3x3x3_dgrad(int in_dtype, int out_dtype, int out_planar, const void* dy, const float* wdpk,
-                                  void* dx, int n, int d, int h, int w, int cin, int cout, void* stream) {
+                                  const void* wdtc, void* dx, int n, int d, int h, int w, int cin, int cout, void* stream) {
     // dx[.., cin] = conv3(dy[.., cout], wd[27][cout][cin]): the fprop contraction with channels swapped
+#ifdef VS_WITH_TCGEN05
+    if (wdtc != nullptr && in_dtype == VS_BF16 && out_dtype == VS_BF16 && !out_planar && tc_eligible(cout, cin))
+        return vs_conv3x3x3_tc(dy, wdtc, dx, nullptr, nullptr, n, d, h, w, cout, cin, stream);
+#else
+    (void)wdtc;
+#endif
     return vs_conv3x3x3_fprop_direct(in_dtype, out_dtype, 0, out_planar, dy, wdpk, nullptr, dx, nullptr, nullptr, n, d, h, w,
                                      cout, cin, stream);
 }
+
+#ifndef VS_WITH_TCGEN05
+extern "C" size_t vs_conv3_tc_pack_bytes(int, int, int) { return 0; }
+extern "C" int vs_pack_conv3_weight_tc(const float*, void*, int, int, int, void*) {
+    VS_FAIL(VS_ERR_UNSUPPORTED, "library built without the tcgen05 kernels");
+}
+#endif

@@ -416,6 +416,19 @@ extern "C" int vs_conv3x3x3_fprop_direct(int in_dtype, int out_dtype, int in_pla
                         stream);
 }
 
+// internal: per-(n,co) reference-voxel value used as the InstanceNorm-invariant shift (see header)
+extern "C" int vs_conv3_shift_internal(int in_dtype, int in_planar, const void* x, const float* wpk, float* shift, int n,
+                                       int d, int h, int w, int cin, int cout, void* stream) {
+    ConvDims p = make_dims(n, d, h, w, cin, cout);
+    dim3 sgrid((cout + 31) / 32, n);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (in_planar) conv3_shift_kernel<float, true><<<sgrid, 256, 0, st>>>((const float*)x, wpk, shift, p);
+    else if (in_dtype == VS_F32) conv3_shift_kernel<float, false><<<sgrid, 256, 0, st>>>((const float*)x, wpk, shift, p);
+    else conv3_shift_kernel<bf16, false><<<sgrid, 256, 0, st>>>((const bf16*)x, wpk, shift, p);
+    VS_CHECK_LAUNCH("conv3_shift_kernel");
+    return VS_OK;
+}
+
 extern "C" size_t vs_conv3_wgrad_workspace_bytes(int, int, int, int, int, int) { return 0; }
 
 extern "C" int vs_conv3x3x3_wgrad(int dtype, int in_planar, const void* x, const void* dy, float* dw, float* db,

@@ -1,0 +1,479 @@
+// 3x3x3 convolution (padding 1) as an implicit GEMM on the 5th-gen tensor cores (sm_100a):
+//   tcgen05.mma (kind::f16, bf16 x bf16 -> fp32 in TMEM), operands staged by TMA, warp-specialised,
+//   persistent over output tiles.  Replaces cuDNN fprop / dgrad for joint_model.py:40-46,106,224,366.
+//
+// GEMM view:  D[128 voxels, NC couts] += A[128 voxels, 16 cin] * B[NC couts, 16 cin]^T   per filter tap.
+//
+// A operand = the input halo tile itself.  A CTA owns a 4x16x8 (d,h,w) block of output voxels and
+// stages the 6x18x10 halo of 16 input channels in shared memory as two "planes" of 8 channels
+// ([halo voxel][8 ch] = 16 B per voxel), each filled by ONE 5-D TMA box load whose out-of-bounds
+// zero fill implements the padding.  In the K-major no-swizzle UMMA layout a core matrix is 8 rows x 16 B
+// stored contiguously, so 8 consecutive w-voxels of one plane ARE a core matrix; the 16 h-rows of the
+// tile are the 16 row groups (SBO = one halo row = 160 B) and the two planes are the two K chunks
+// (LBO = plane stride).  A filter tap (kd,kh,kw) is then nothing but a different start address in the
+// same halo: every input voxel is fetched from L2/HBM once per CTA and reused by all 27 taps x 4 planes.
+// For Cin = 8 two taps (kw, kw+1) are paired into one K=16 MMA by setting LBO = 16 B (the next voxel).
+//
+// Pipeline: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread) + TMEM allocator,
+// warps 2-5 = epilogue (tcgen05.ld -> shift -> InstanceNorm statistics -> bf16 -> global).  smem stages
+// ring over (tile, 16-channel slice); TMEM accumulators are double buffered across tiles so the epilogue
+// of tile i overlaps the MMAs of tile i+1.
+#include <cuda.h>
+#include "vs_common.cuh"
+
+namespace {
+
+constexpr int TD = 4, TH = 16, TW = 8;                 // output tile (d,h,w); 128 rows per d-plane
+constexpr int HD = TD + 2, HH = TH + 2, HW = TW + 2;   // halo 6 x 18 x 10
+constexpr int HV = HD * HH * HW;                       // 1080 halo voxels
+constexpr int PLANE_BYTES = HV * 16;                   // 17280 (multiple of 128)
+constexpr int PLANE_PAD = 256;                         // slack read by the zero-weighted third tap of the Cin=8 pairs
+constexpr int NTHREADS = 192;
+
+struct TcParams {
+    int n, d, h, w, cin, cout;
+    int tiles_d, tiles_h, tiles_w, tiles_per_n;
+    int nchunks;            // cout chunks of NC
+    int kslices;            // cin / 16 (1 for cin == 8)
+    long long work_items;   // n * tiles_per_n * nchunks
+    const bf16* wpack;
+    bf16* y;
+    double* stats;          // [n][cout][2] or null
+    const float* shift;     // [n][cout] or null
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1 = sm_100)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) | (1ull << 46);
+}
+// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M = 128
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+__device__ __forceinline__ void decode_work(long long item, const TcParams& p, int& n, int& d0, int& h0, int& w0, int& chunk) {
+    chunk = (int)(item % p.nchunks);
+    long long t = item / p.nchunks;
+    n = (int)(t / p.tiles_per_n);
+    int r = (int)(t % p.tiles_per_n);
+    w0 = (r % p.tiles_w) * TW; r /= p.tiles_w;
+    h0 = (r % p.tiles_h) * TH; r /= p.tiles_h;
+    d0 = r * TD;
+}
+
+// ---------------------------------------------------------------------------------------------
+// NC: output channels per CTA (MMA N); CIN8: single 8-channel plane with paired taps.
+// Shared memory: NSTAGE x { A planes | B taps } + barriers; sized by the host.
+// ---------------------------------------------------------------------------------------------
+template <int NC, bool CIN8, int NSTAGE>
+__global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_constant__ CUtensorMap xmap, TcParams p) {
+    constexpr int A_BYTES = CIN8 ? (PLANE_BYTES + PLANE_PAD) : 2 * PLANE_BYTES;
+    constexpr int NMMA = CIN8 ? 18 : 27;                      // MMAs per d-plane per stage
+    constexpr int B_BYTES = NMMA * NC * 32;                   // [mma][kc 2][NC/8][8 rows][16 B]
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr int NBUF = 2;
+    constexpr int TMEM_COLS = NBUF * TD * NC;                 // 128 / 256 / 512
+    static_assert(STAGE_BYTES % 128 == 0, "stage alignment");
+
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + NSTAGE;
+    uint64_t* tfull_bar = empty_bar + NSTAGE;
+    uint64_t* tempty_bar = tfull_bar + NBUF;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + NBUF);
+    float* sshift = reinterpret_cast<float*>(tmem_slot + 4);          // [NC]
+    double* sstat = reinterpret_cast<double*>(sshift + NC);           // [NC][2]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < NBUF; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+        fence_barrier_init();
+    }
+    if (CIN8) {
+        // zero the pad behind each stage's plane once (read only under zero weights, but must not be NaN)
+        for (int i = threadIdx.x; i < NSTAGE * (PLANE_PAD / 4); i += NTHREADS) {
+            int s = i / (PLANE_PAD / 4), k = i % (PLANE_PAD / 4);
+            reinterpret_cast<uint32_t*>(smem + s * STAGE_BYTES + PLANE_BYTES)[k] = 0u;
+        }
+        fence_proxy_async();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (long long item = blockIdx.x; item < p.work_items; item += gridDim.x) {
+                int n, d0, h0, w0, chunk;
+                decode_work(item, p, n, d0, h0, w0, chunk);
+                for (int ks = 0; ks < p.kslices; ++ks) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[stage], (CIN8 ? PLANE_BYTES : 2 * PLANE_BYTES) + B_BYTES);
+                    tma_load_5d(sa, &xmap, &full_bar[stage], ks * 16, w0 - 1, h0 - 1, d0 - 1, n);
+                    if (!CIN8) tma_load_5d(sa + PLANE_BYTES, &xmap, &full_bar[stage], ks * 16 + 8, w0 - 1, h0 - 1, d0 - 1, n);
+                    const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) +
+                                          ((long long)chunk * p.kslices + ks) * B_BYTES;
+                    bulk_load(sa + A_BYTES, wsrc, B_BYTES, &full_bar[stage]);
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(NC);
+            uint32_t stage = 0, phase = 0, buf = 0, bphase = 0;
+            for (long long item = blockIdx.x; item < p.work_items; item += gridDim.x) {
+                int n, d0, h0, w0, chunk;
+                decode_work(item, p, n, d0, h0, w0, chunk);
+                const int jmax = min(TD, p.d - d0);
+                mbar_wait(&tempty_bar[buf], bphase ^ 1);
+                tc_fence_after();
+                for (int ks = 0; ks < p.kslices; ++ks) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_base = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint32_t b_base = a_base + A_BYTES;
+                    for (int j = 0; j < jmax; ++j) {
+                        const uint32_t dcol = tmem_base + (buf * TD + j) * NC;
+                        int m = 0;
+#pragma unroll 1
+                        for (int kd = 0; kd < 3; ++kd) {
+#pragma unroll 1
+                            for (int kh = 0; kh < 3; ++kh) {
+                                const uint32_t row = a_base + (uint32_t)(((j + kd) * HH + kh) * HW) * 16u;
+                                if (CIN8) {
+#pragma unroll
+                                    for (int pr = 0; pr < 2; ++pr, ++m) {
+                                        const uint64_t ad = make_desc(row + pr * 32u, 16u, HW * 16u);
+                                        const uint64_t bd = make_desc(b_base + m * (NC * 32), NC * 16, 128u);
+                                        tc_mma(dcol, ad, bd, idesc, (ks | m) != 0);
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int kw = 0; kw < 3; ++kw, ++m) {
+                                        const uint64_t ad = make_desc(row + kw * 16u, PLANE_BYTES, HW * 16u);
+                                        const uint64_t bd = make_desc(b_base + m * (NC * 32), NC * 16, 128u);
+                                        tc_mma(dcol, ad, bd, idesc, (ks | m) != 0);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    tc_commit(&empty_bar[stage]);               // frees the smem stage when these MMAs retire
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&tfull_bar[buf]);                     // accumulators of this tile complete
+                if (++buf == NBUF) { buf = 0; bphase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int q = warp & 3;                                  // TMEM lane quadrant this warp may read
+        const int et = threadIdx.x - 64;                         // 0..127 within the epilogue group
+        const int row = q * 32 + lane;                           // accumulator row = voxel in the d-plane
+        const int lh = row >> 3, lw = row & 7;
+        uint32_t buf = 0, bphase = 0;
+        int stat_n = -1, stat_chunk = -1;
+        for (int i = et; i < NC * 2; i += 128) sstat[i] = 0.0;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (long long item = blockIdx.x; item < p.work_items; item += gridDim.x) {
+            int n, d0, h0, w0, chunk;
+            decode_work(item, p, n, d0, h0, w0, chunk);
+            const int co0 = chunk * NC;
+            // everyone is done with the previous tile's sshift / sstat before they are touched again
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (p.stats != nullptr && (n != stat_n || chunk != stat_chunk)) {
+                // flush the statistics accumulated for the previous (n, chunk)
+                if (stat_n >= 0) {
+                    for (int i = et; i < NC * 2; i += 128) {
+                        const int c = stat_chunk * NC + (i >> 1);
+                        if (c < p.cout) atomicAdd(&p.stats[((long long)stat_n * p.cout + c) * 2 + (i & 1)], sstat[i]);
+                        sstat[i] = 0.0;
+                    }
+                }
+                stat_n = n; stat_chunk = chunk;
+            }
+            if (et < NC) sshift[et] = (p.shift != nullptr && co0 + et < p.cout) ? p.shift[(long long)n * p.cout + co0 + et] : 0.f;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(&tfull_bar[buf], bphase);
+            tc_fence_after();
+            const int jmax = min(TD, p.d - d0);
+            const int gh = h0 + lh, gw = w0 + lw;
+            const bool rc_ok = gh < p.h && gw < p.w;
+            for (int j = 0; j < jmax; ++j) {
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (buf * TD + j) * NC;
+                bf16* py = p.y + (((long long)n * p.d + d0 + j) * p.h + gh) * (long long)p.w * p.cout + (long long)gw * p.cout + co0;
+#pragma unroll
+                for (int c16 = 0; c16 < NC / 16; ++c16) {
+                    uint32_t r[16];
+                    tmem_ld16(taddr + c16 * 16, r);
+                    tmem_ld_wait();
+                    float v[16];
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) v[k] = rc_ok ? __uint_as_float(r[k]) - sshift[c16 * 16 + k] : 0.f;
+                    if (p.stats != nullptr) {
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) {
+                            const float s = warp_sum(v[k]);
+                            const float s2 = warp_sum(v[k] * v[k]);
+                            if (lane == k) {
+                                atomicAdd(&sstat[(c16 * 16 + k) * 2], (double)s);
+                                atomicAdd(&sstat[(c16 * 16 + k) * 2 + 1], (double)s2);
+                            }
+                        }
+                    }
+                    if (rc_ok) {
+#pragma unroll
+                        for (int h8 = 0; h8 < 2; ++h8) {
+                            if (co0 + c16 * 16 + h8 * 8 < p.cout) {
+                                float o[8];
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) o[k] = v[h8 * 8 + k];
+                                Store<bf16>::st8(py + c16 * 16 + h8 * 8, o);
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+            if (++buf == NBUF) { buf = 0; bphase ^= 1; }
+        }
+        if (p.stats != nullptr && stat_n >= 0) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int i = et; i < NC * 2; i += 128) {
+                const int c = stat_chunk * NC + (i >> 1);
+                if (c < p.cout) atomicAdd(&p.stats[((long long)stat_n * p.cout + c) * 2 + (i & 1)], sstat[i]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing: fp32 master [Cout][Cin][27] -> bf16 UMMA B operand blocks
+//   general: [chunk][kslice][tap 27][kc 2][NC/8][8 rows][8 ch]
+//   cin8   : [chunk][1][kdkh 9 x pair 2][kc 2][NC/8][8 rows][8 ch]  (kc0 = tap kw=2*pair, kc1 = kw=2*pair+1 or 0)
+// dgrad = same contraction with (ci,co) swapped and taps flipped.
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_tc_kernel(const float* __restrict__ w, bf16* __restrict__ out, int cin_l, int cout_l, int dgrad,
+                               int nc, int cin8, long long total) {
+    // GEMM-side channel counts
+    const int gin = dgrad ? cout_l : cin_l, gout = dgrad ? cin_l : cout_l;
+    const int kslices = cin8 ? 1 : gin / 16;
+    const int nmma = cin8 ? 18 : 27;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long r = i;
+        const int ch8 = (int)(r % 8); r /= 8;
+        const int r8 = (int)(r % 8); r /= 8;
+        const int ng = (int)(r % (nc / 8)); r /= (nc / 8);
+        const int kc = (int)(r % 2); r /= 2;
+        const int m = (int)(r % nmma); r /= nmma;
+        const int ks = (int)(r % kslices); r /= kslices;
+        const int chunk = (int)r;
+        const int go = chunk * nc + ng * 8 + r8;               // GEMM output channel
+        int gi, tap;
+        if (cin8) {
+            const int kdkh = m / 2, pr = m % 2, kw = pr * 2 + kc;
+            gi = ch8;
+            tap = kw <= 2 ? kdkh * 3 + kw : -1;
+        } else {
+            gi = ks * 16 + kc * 8 + ch8;
+            tap = m;
+        }
+        float v = 0.f;
+        if (go < gout && gi < gin && tap >= 0) {
+            if (dgrad) v = w[((long long)gi * cin_l + go) * 27 + (26 - tap)];      // w[co=gi][ci=go][flipped tap]
+            else v = w[((long long)go * cin_l + gi) * 27 + tap];
+        }
+        out[i] = __float2bfloat16_rn(v);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+int nc_for(int gout) { return gout >= 64 ? 64 : (gout >= 32 ? 32 : 16); }
+
+template <int NC, bool CIN8, int NSTAGE>
+int launch_tc(const CUtensorMap& map, const TcParams& p, cudaStream_t st) {
+    constexpr int A_BYTES = CIN8 ? (PLANE_BYTES + PLANE_PAD) : 2 * PLANE_BYTES;
+    constexpr int B_BYTES = (CIN8 ? 18 : 27) * NC * 32;
+    constexpr int SMEM = NSTAGE * (A_BYTES + B_BYTES) + 128 /*align*/ + 8 * (2 * NSTAGE + 4) + 16 + NC * 4 + NC * 16 + 64;
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
+    auto kern = conv3_tc_kernel<NC, CIN8, NSTAGE>;
+    static bool configured = false;
+    if (!configured) {
+        VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM), "conv3_tc smem attribute");
+        configured = true;
+    }
+    const long long grid = p.work_items < (long long)vs_sm_count() ? p.work_items : (long long)vs_sm_count();
+    kern<<<(unsigned)grid, NTHREADS, SMEM, st>>>(map, p);
+    VS_CHECK_LAUNCH("conv3_tc_kernel");
+    return VS_OK;
+}
+
+}  // namespace
+
+// bytes of the bf16 tensor-core weight pack for a layer (fprop: dgrad=0, dgrad: dgrad=1); 0 = unsupported shape
+extern "C" size_t vs_conv3_tc_pack_bytes(int cin, int cout, int dgrad) {
+    const int gin = dgrad ? cout : cin, gout = dgrad ? cin : cout;
+    if (!(gin == 8 || (gin % 16 == 0 && gin >= 16)) || gout % 8 != 0 || gout < 8) return 0;
+    const int nc = nc_for(gout);
+    const int nchunks = (gout + nc - 1) / nc;
+    const int kslices = gin == 8 ? 1 : gin / 16;
+    return (size_t)nchunks * kslices * (gin == 8 ? 18 : 27) * nc * 32;
+}
+
+extern "C" int vs_pack_conv3_weight_tc(const float* w, void* out, int cin, int cout, int dgrad, void* stream) {
+    const size_t bytes = vs_conv3_tc_pack_bytes(cin, cout, dgrad);
+    VS_REQUIRE(w && out && bytes > 0, VS_ERR_UNSUPPORTED, "pack_conv3_weight_tc: unsupported shape Cin=%d Cout=%d", cin, cout);
+    const int gin = dgrad ? cout : cin, gout = dgrad ? cin : cout;
+    const long long total = (long long)(bytes / 2);
+    pack_tc_kernel<<<(unsigned)min(1024LL, (total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        w, (bf16*)out, cin, cout, dgrad, nc_for(gout), gin == 8, total);
+    VS_CHECK_LAUNCH("pack_tc_kernel");
+    return VS_OK;
+}
+
+// y[n,d,h,w,gout] = conv3(x[n,d,h,w,gin], wtc) on the tensor cores; bf16 NDHWC in and out.
+extern "C" int vs_conv3x3x3_tc(const void* x, const void* wtc, void* y, double* stats, const float* shift, int n, int d,
+                               int h, int w, int gin, int gout, void* stream) {
+    VS_REQUIRE(x && wtc && y, VS_ERR_SHAPE, "conv3_tc: null pointer");
+    VS_REQUIRE((gin == 8 || (gin % 16 == 0 && gin >= 16)) && gout % 8 == 0 && gout >= 8, VS_ERR_UNSUPPORTED,
+               "conv3_tc: unsupported channels Cin=%d Cout=%d", gin, gout);
+    VS_REQUIRE(vs_aligned16(x) && vs_aligned16(y) && vs_aligned16(wtc), VS_ERR_ALIGN, "conv3_tc: pointers must be 16B aligned");
+    EncodeTiledFn encode = get_encode_fn();
+    VS_REQUIRE(encode != nullptr, VS_ERR_CUDA, "conv3_tc: cuTensorMapEncodeTiled unavailable");
+    cudaStream_t st = (cudaStream_t)stream;
+
+    CUtensorMap map;
+    const cuuint64_t gdim[5] = {(cuuint64_t)gin, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)d, (cuuint64_t)n};
+    const cuuint64_t gstr[4] = {(cuuint64_t)gin * 2, (cuuint64_t)w * gin * 2, (cuuint64_t)h * w * gin * 2,
+                                (cuuint64_t)d * h * w * gin * 2};
+    const cuuint32_t box[5] = {8, HW, HH, HD, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult cr = encode(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VS_REQUIRE(cr == CUDA_SUCCESS, VS_ERR_CUDA, "conv3_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+
+    TcParams p;
+    p.n = n; p.d = d; p.h = h; p.w = w; p.cin = gin; p.cout = gout;
+    p.tiles_d = (d + TD - 1) / TD; p.tiles_h = (h + TH - 1) / TH; p.tiles_w = (w + TW - 1) / TW;
+    p.tiles_per_n = p.tiles_d * p.tiles_h * p.tiles_w;
+    const int nc = nc_for(gout);
+    p.nchunks = (gout + nc - 1) / nc;
+    p.kslices = gin == 8 ? 1 : gin / 16;
+    p.work_items = (long long)n * p.tiles_per_n * p.nchunks;
+    p.wpack = (const bf16*)wtc; p.y = (bf16*)y; p.stats = stats; p.shift = shift;
+    if (stats) VS_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * n * gout, st), "conv3_tc stats memset");
+
+    if (gin == 8) {
+        if (nc == 16) return launch_tc<16, true, 4>(map, p, st);
+        if (nc == 32) return launch_tc<32, true, 4>(map, p, st);
+        return launch_tc<64, true, 3>(map, p, st);
+    }
+    if (nc == 16) return launch_tc<16, false, 4>(map, p, st);
+    if (nc == 32) return launch_tc<32, false, 3>(map, p, st);
+    return launch_tc<64, false, 2>(map, p, st);
+}

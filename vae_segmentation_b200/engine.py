@@ -13,11 +13,18 @@ the softmax head writes planar probabilities, so no layout-conversion kernels ru
 Reference semantics implemented here: joint_model.py:35-52,101-136 (blocks), :369-390
 (Segmentation.forward incl. the two additive skips), :227-272 (VAE.forward).
 """
+import os
+
 import torch
 
 from . import ops
 
 C3IN, K2DOWN, K2UP, HEAD = "c3in", "k2down", "k2up", "head"
+
+# bf16 mode routes eligible 3x3x3 convolutions (fprop + dgrad) to the tcgen05/TMEM/TMA kernel; the CUDA-core
+# direct kernel remains for the fp32 check mode and the Cin in {1,2} / Cout = 2 layers.  VAESEG_NO_TC=1 forces
+# the direct kernel everywhere (A/B measurements).
+USE_TENSOR_CORES = os.environ.get("VAESEG_NO_TC", "0") != "1"
 
 # tools/precision_probe*.py only: names of tensor classes to round through bf16 while running the fp32
 # check mode ("y", "a", "g", "dy", "k2"), to attribute bf16-mode error to a storage point.  Empty in production.
@@ -52,14 +59,22 @@ class PackCache(object):
         self.epoch += 1
         self._store.clear()
 
-    def conv3(self, w):
-        key = (w.data_ptr(), w._version, self.epoch)
+    def conv3(self, w, tc=False):
+        """Returns (wf, wd, wtc_fprop, wtc_dgrad); the tensor-core packs are None unless tc=True (bf16
+        mode) and the tcgen05 path takes the shape."""
+        key = (w.data_ptr(), w._version, self.epoch, tc)
         hit = self._store.get(w.data_ptr())
         if hit is not None and hit[0] == key:
-            return hit[1], hit[2]
-        wf, wd = ops.pack_conv3_weight(w.detach(), want_dgrad=True)
-        self._store[w.data_ptr()] = (key, wf, wd)
-        return wf, wd
+            return hit[1]
+        wdet = w.detach()
+        wf, wd = ops.pack_conv3_weight(wdet, want_dgrad=True)
+        tf = td = None
+        if tc and USE_TENSOR_CORES:
+            tf = ops.pack_conv3_weight_tc(wdet, dgrad=False)
+            td = ops.pack_conv3_weight_tc(wdet, dgrad=True)
+        packs = (wf, wd, tf, td)
+        self._store[w.data_ptr()] = (key, packs)
+        return packs
 
 
 def _grad_target(p_ref, need):
@@ -103,14 +118,15 @@ def program_forward(layers, tensors, x, dims, dtype, cache, record=True):
     cur = x
     for L in layers:
         if L.kind == C3IN:
-            wf, wd = cache.conv3(tensors[L.wi])
+            wf, wd, wtc, wdtc = cache.conv3(tensors[L.wi], tc=(dtype == torch.bfloat16))
             # the conv bias is a no-op ahead of InstanceNorm(affine=False): skipped
-            y, stats = ops.conv3_fprop(cur, wf, None, (n, d, h, w), L.cin, L.cout, dtype, in_planar=L.in_planar)
+            y, stats = ops.conv3_fprop(cur, wf, None, (n, d, h, w), L.cin, L.cout, dtype, in_planar=L.in_planar,
+                                       wtc=None if L.in_planar else wtc)
             skip = slots[L.skip_from] if L.skip_from is not None else None
             y = _sim(y, "y")
             a = _sim(ops.inorm_relu_apply(y, stats, skip), "a")
             if record:
-                tape.append((L, cur, y, stats, (n, d, h, w), wd))
+                tape.append((L, cur, y, stats, (n, d, h, w), (wd, wdtc)))
             cur = a
         elif L.kind == K2DOWN:
             d, h, w = d // 2, h // 2, w // 2
@@ -125,12 +141,12 @@ def program_forward(layers, tensors, x, dims, dtype, cache, record=True):
             d, h, w = d * 2, h * 2, w * 2
             cur = out
         elif L.kind == HEAD:
-            wf, wd = cache.conv3(tensors[L.wi])
+            wf, wd, _, wdtc = cache.conv3(tensors[L.wi], tc=(dtype == torch.bfloat16))
             logits, _ = ops.conv3_fprop(cur, wf, tensors[L.bi].detach(), (n, d, h, w), L.cin, L.cout, torch.float32,
                                         in_planar=L.in_planar, want_stats=False)
             probs = ops.softmax2_fwd(logits, (n, d, h, w))
             if record:
-                tape.append((L, cur, probs, None, (n, d, h, w), wd))
+                tape.append((L, cur, probs, None, (n, d, h, w), (wd, wdtc)))
             cur = probs
         else:
             raise RuntimeError("unknown layer kind %r" % (L.kind,))
@@ -162,7 +178,8 @@ def program_backward(tape, g, dtype, need, grads, param_refs, need_input_grad):
                 # exactly zero: the bias cancels in InstanceNorm
                 tgt, acc = _grad_target(param_refs[L.bi], True)
                 grads[L.bi] = None if acc else torch.zeros(L.cout, device=dy.device, dtype=torch.float32)
-            g = _sim(ops.conv3_dgrad(dy, wd, dims, L.cin, L.cout, dtype, out_planar=L.in_planar), "g") if want_dx else None
+            g = _sim(ops.conv3_dgrad(dy, wd[0], dims, L.cin, L.cout, dtype, out_planar=L.in_planar, wdtc=wd[1]), "g") \
+                if want_dx else None
         elif L.kind == K2DOWN:
             # dims are the coarse (output) dims; g is the coarse gradient
             if need[L.wi] or need[L.bi]:
@@ -184,7 +201,8 @@ def program_backward(tape, g, dtype, need, grads, param_refs, need_input_grad):
                 tw, tb, acc = _pair_targets(param_refs, need, L.wi, L.bi, (L.cout, L.cin, 3, 3, 3), (L.cout,), g.device)
                 ops.conv3_wgrad(x_in, dlogits, dims, L.cin, L.cout, dw=tw, db=tb, in_planar=L.in_planar, accumulate=acc)
                 _hand_back(grads, need, L.wi, L.bi, tw, tb, acc)
-            g = _sim(ops.conv3_dgrad(dlogits, wd, dims, L.cin, L.cout, dtype, out_planar=L.in_planar), "g") if want_dx else None
+            g = _sim(ops.conv3_dgrad(dlogits, wd[0], dims, L.cin, L.cout, dtype, out_planar=L.in_planar, wdtc=wd[1]), "g") \
+                if want_dx else None
     return g
 
 

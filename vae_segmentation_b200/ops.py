@@ -53,8 +53,20 @@ def pack_conv3_weight(w, want_dgrad=True):
     return wf, wd
 
 
+def pack_conv3_weight_tc(w, dgrad=False):
+    """bf16 tensor-core (UMMA B operand) pack of a [Cout,Cin,3,3,3] weight, or None if the tcgen05
+    path does not take this shape / the library was built without it."""
+    cout, cin = w.shape[0], w.shape[1]
+    nbytes = _cabi.lib().vs_conv3_tc_pack_bytes(cin, cout, int(dgrad))
+    if nbytes == 0:
+        return None
+    out = torch.empty(nbytes // 2, device=w.device, dtype=torch.bfloat16)
+    _cabi.call("vs_pack_conv3_weight_tc", _p(_f32(w, "weight")), _p(out), cin, cout, int(dgrad), _stream())
+    return out
+
+
 def conv3_fprop(x, wf, bias, dims, cin, cout, out_dtype, in_planar=False, out_planar=False, want_stats=True,
-                shifted=None):
+                shifted=None, wtc=None):
     """dims = (N, D, H, W).  Returns (y, stats).  `shifted` (default: same as want_stats) subtracts the
     per-(n,co) reference-voxel value from the output (InstanceNorm-invariant, see the header)."""
     n, d, h, w = dims
@@ -67,19 +79,19 @@ def conv3_fprop(x, wf, bias, dims, cin, cout, out_dtype, in_planar=False, out_pl
     if shifted is None:
         shifted = want_stats
     shift = torch.empty(n, cout, device=dev, dtype=torch.float32) if shifted else None
-    _cabi.call("vs_conv3x3x3_fprop", _dt(x), _dt(y), int(in_planar), int(out_planar), _p(x), _p(_f32(wf, "wf")),
+    _cabi.call("vs_conv3x3x3_fprop", _dt(x), _dt(y), int(in_planar), int(out_planar), _p(x), _p(_f32(wf, "wf")), _p(wtc),
                _p(_f32(bias, "bias")), _p(y), _p(stats), _p(shift), n, d, h, w, cin, cout, _stream())
     return y, stats
 
 
-def conv3_dgrad(dy, wd, dims, cin, cout, out_dtype, out_planar=False):
+def conv3_dgrad(dy, wd, dims, cin, cout, out_dtype, out_planar=False, wdtc=None):
     """dy: [N,D,H,W,Cout] -> dx [N,D,H,W,Cin] (or planar fp32 [N,Cin,D,H,W])."""
     n, d, h, w = dims
     if out_planar:
         dx = torch.empty(n, cin, d, h, w, device=dy.device, dtype=torch.float32)
     else:
         dx = torch.empty(n, d, h, w, cin, device=dy.device, dtype=out_dtype)
-    _cabi.call("vs_conv3x3x3_dgrad", _dt(dy), _dt(dx), int(out_planar), _p(dy), _p(_f32(wd, "wd")), _p(dx),
+    _cabi.call("vs_conv3x3x3_dgrad", _dt(dy), _dt(dx), int(out_planar), _p(dy), _p(_f32(wd, "wd")), _p(wdtc), _p(dx),
                n, d, h, w, cin, cout, _stream())
     return dx
 
