@@ -178,15 +178,20 @@ class KernelTimer(object):
 
     def __init__(self, only=None):
         self.only = only
+        self.only_name = only[0] if only is not None else None
         self.events = {}
+        from vae_segmentation_b200 import _cabi
+        self._key = _cabi.call_key
 
-    def __call__(self, name, key, launch):
-        sig = (name, key)
+    def __call__(self, name, args, fn):
+        if self.only_name is not None and name != self.only_name:
+            return fn(*args)
+        sig = (name, self._key(name, args))
         if self.only is not None and sig != self.only:
-            return launch()
+            return fn(*args)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        rc = launch()
+        rc = fn(*args)
         e1.record()
         self.events.setdefault(sig, []).append((e0, e1))
         return rc

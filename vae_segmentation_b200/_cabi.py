@@ -101,7 +101,7 @@ def call(name, *args):
     N_CALLS += 1
     fn = getattr(lib(), name)
     if _profiler is not None:
-        rc = _profiler(name, call_key(name, args), lambda: fn(*args))
+        rc = _profiler(name, args, fn)
     else:
         rc = fn(*args)
     if rc != 0:

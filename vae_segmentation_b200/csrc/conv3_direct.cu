@@ -185,18 +185,18 @@ __global__ void __launch_bounds__(NT) conv3_direct_kernel(const TI* __restrict__
     }
 }
 
-// shift[n][co] = conv3(x, w) at voxel (1,1,1): lanes <-> 32 consecutive output channels
-// (coalesced weight reads), the 8 warps split the 27*Cin terms.
+// shift[n][co] = conv3(x, w) at voxel (1,1,1).  One CTA per (n, 8 output channels): the 27*Cin input values of
+// the reference neighbourhood are staged in shared memory, thread = (co, one of 32 term partitions) with
+// four independent accumulators so the weight loads pipeline; deterministic tree reduction.
 template <typename TI, bool IN_PLANAR>
 __global__ void __launch_bounds__(256) conv3_shift_kernel(const TI* __restrict__ x, const float* __restrict__ wpk,
                                                           float* __restrict__ shift, ConvDims p) {
-    __shared__ float red[8][32];
-    const int n = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int co = blockIdx.x * 32 + lane;
+    extern __shared__ float xs_ref[];          // [27 * cin]
+    __shared__ float red[32][9];
+    const int n = blockIdx.y, t = threadIdx.x;
     const long long S = (long long)p.d * p.h * p.w;
     const int terms = 27 * p.cin;
-    float acc = 0.f;
-    for (int i = warp; i < terms; i += 8) {
+    for (int i = t; i < terms; i += 256) {
         const int tap = i / p.cin, ci = i - tap * p.cin;
         const int gd = tap / 9, gh = (tap / 3) % 3, gw = tap % 3;       // voxel (1,1,1) + tap - 1
         float xv = 0.f;
@@ -205,15 +205,30 @@ __global__ void __launch_bounds__(256) conv3_shift_kernel(const TI* __restrict__
             if (IN_PLANAR) xv = reinterpret_cast<const float*>(x)[((long long)n * p.cin + ci) * S + vox];
             else xv = Store<TI>::ld(x + ((long long)n * S + vox) * p.cin + ci);
         }
-        if (co < p.cout) acc = fmaf(xv, wpk[(long long)i * p.cout + co], acc);
+        xs_ref[i] = xv;
     }
-    red[warp][lane] = acc;
     __syncthreads();
-    if (warp == 0 && co < p.cout) {
+    const int col = t & 7, part = t >> 3;
+    const int co = blockIdx.x * 8 + col;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (co < p.cout) {
+        const float* pw = wpk + co;
+        int i = part;
+        for (; i + 96 < terms; i += 128) {
+            a0 = fmaf(xs_ref[i], pw[(long long)i * p.cout], a0);
+            a1 = fmaf(xs_ref[i + 32], pw[(long long)(i + 32) * p.cout], a1);
+            a2 = fmaf(xs_ref[i + 64], pw[(long long)(i + 64) * p.cout], a2);
+            a3 = fmaf(xs_ref[i + 96], pw[(long long)(i + 96) * p.cout], a3);
+        }
+        for (; i < terms; i += 32) a0 = fmaf(xs_ref[i], pw[(long long)i * p.cout], a0);
+    }
+    red[part][col] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (t < 8 && blockIdx.x * 8 + t < p.cout) {
         float s = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) s += red[k][lane];
-        shift[(long long)n * p.cout + co] = s;
+        for (int k = 0; k < 32; ++k) s += red[k][t];
+        shift[(long long)n * p.cout + blockIdx.x * 8 + t] = s;
     }
 }
 
@@ -327,8 +342,8 @@ template <typename TI, typename TO, bool IN_PLANAR, bool OUT_PLANAR>
 int launch_conv3(const void* x, const float* wpk, const float* bias, void* y, double* stats, float* shift,
                  const ConvDims& p, cudaStream_t st) {
     if (shift != nullptr) {
-        dim3 sgrid((p.cout + 31) / 32, p.n);
-        conv3_shift_kernel<TI, IN_PLANAR><<<sgrid, 256, 0, st>>>((const TI*)x, wpk, shift, p);
+        dim3 sgrid((p.cout + 7) / 8, p.n);
+        conv3_shift_kernel<TI, IN_PLANAR><<<sgrid, 256, 27 * p.cin * sizeof(float), st>>>((const TI*)x, wpk, shift, p);
         VS_CHECK_LAUNCH("conv3_shift_kernel");
     }
     const long long tiles = (long long)p.n * p.tiles_d * p.tiles_h * p.tiles_w;
@@ -420,11 +435,12 @@ extern "C" int vs_conv3x3x3_fprop_direct(int in_dtype, int out_dtype, int in_pla
 extern "C" int vs_conv3_shift_internal(int in_dtype, int in_planar, const void* x, const float* wpk, float* shift, int n,
                                        int d, int h, int w, int cin, int cout, void* stream) {
     ConvDims p = make_dims(n, d, h, w, cin, cout);
-    dim3 sgrid((cout + 31) / 32, n);
+    dim3 sgrid((cout + 7) / 8, n);
     cudaStream_t st = (cudaStream_t)stream;
-    if (in_planar) conv3_shift_kernel<float, true><<<sgrid, 256, 0, st>>>((const float*)x, wpk, shift, p);
-    else if (in_dtype == VS_F32) conv3_shift_kernel<float, false><<<sgrid, 256, 0, st>>>((const float*)x, wpk, shift, p);
-    else conv3_shift_kernel<bf16, false><<<sgrid, 256, 0, st>>>((const bf16*)x, wpk, shift, p);
+    const size_t sm = 27 * (size_t)cin * sizeof(float);
+    if (in_planar) conv3_shift_kernel<float, true><<<sgrid, 256, sm, st>>>((const float*)x, wpk, shift, p);
+    else if (in_dtype == VS_F32) conv3_shift_kernel<float, false><<<sgrid, 256, sm, st>>>((const float*)x, wpk, shift, p);
+    else conv3_shift_kernel<bf16, false><<<sgrid, 256, sm, st>>>((const bf16*)x, wpk, shift, p);
     VS_CHECK_LAUNCH("conv3_shift_kernel");
     return VS_OK;
 }

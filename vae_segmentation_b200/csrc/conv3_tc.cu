@@ -121,6 +121,24 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
+// Column sums of a 32-lane x 16-value register tile in 31 shuffles: afterwards v[0] of lane L holds the
+// sum over all lanes of column (L & 15).
+__device__ __forceinline__ float transpose_reduce16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], 16);
+#pragma unroll
+    for (int h = 8; h >= 1; h >>= 1) {
+        const bool up = (lane & h) != 0;
+#pragma unroll
+        for (int k = 0; k < h; ++k) {
+            const float send = up ? v[k] : v[k + h];
+            const float keep = up ? v[k + h] : v[k];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+        }
+    }
+    return v[0];
+}
+
 __device__ __forceinline__ void decode_work(long long item, const TcParams& p, int& n, int& d0, int& h0, int& w0, int& chunk) {
     chunk = (int)(item % p.nchunks);
     long long t = item / p.nchunks;
@@ -253,25 +271,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
         const int lh = row >> 3, lw = row & 7;
         uint32_t buf = 0, bphase = 0;
         int stat_n = -1, stat_chunk = -1;
-        for (int i = et; i < NC * 2; i += 128) sstat[i] = 0.0;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // per-warp running statistics: lane L (< 16) owns columns c16*16 + L of this warp's 32 rows
+        double racc[NC / 16][2];
+#pragma unroll
+        for (int c = 0; c < NC / 16; ++c) { racc[c][0] = 0.0; racc[c][1] = 0.0; }
+        auto flush_stats = [&]() {
+            if (stat_n >= 0 && lane < 16) {
+#pragma unroll
+                for (int c = 0; c < NC / 16; ++c) {
+                    const int co = stat_chunk * NC + c * 16 + lane;
+                    if (co < p.cout) {
+                        atomicAdd(&p.stats[((long long)stat_n * p.cout + co) * 2], racc[c][0]);
+                        atomicAdd(&p.stats[((long long)stat_n * p.cout + co) * 2 + 1], racc[c][1]);
+                    }
+                    racc[c][0] = 0.0; racc[c][1] = 0.0;
+                }
+            }
+        };
         for (long long item = blockIdx.x; item < p.work_items; item += gridDim.x) {
             int n, d0, h0, w0, chunk;
             decode_work(item, p, n, d0, h0, w0, chunk);
             const int co0 = chunk * NC;
-            // everyone is done with the previous tile's sshift / sstat before they are touched again
-            asm volatile("bar.sync 1, 128;" ::: "memory");
             if (p.stats != nullptr && (n != stat_n || chunk != stat_chunk)) {
-                // flush the statistics accumulated for the previous (n, chunk)
-                if (stat_n >= 0) {
-                    for (int i = et; i < NC * 2; i += 128) {
-                        const int c = stat_chunk * NC + (i >> 1);
-                        if (c < p.cout) atomicAdd(&p.stats[((long long)stat_n * p.cout + c) * 2 + (i & 1)], sstat[i]);
-                        sstat[i] = 0.0;
-                    }
-                }
+                flush_stats();
                 stat_n = n; stat_chunk = chunk;
             }
+            // everyone is done with the previous tile's sshift before it is overwritten
+            asm volatile("bar.sync 1, 128;" ::: "memory");
             if (et < NC) sshift[et] = (p.shift != nullptr && co0 + et < p.cout) ? p.shift[(long long)n * p.cout + co0 + et] : 0.f;
             asm volatile("bar.sync 1, 128;" ::: "memory");
             mbar_wait(&tfull_bar[buf], bphase);
@@ -290,17 +316,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
                     float v[16];
 #pragma unroll
                     for (int k = 0; k < 16; ++k) v[k] = rc_ok ? __uint_as_float(r[k]) - sshift[c16 * 16 + k] : 0.f;
-                    if (p.stats != nullptr) {
-#pragma unroll
-                        for (int k = 0; k < 16; ++k) {
-                            const float s = warp_sum(v[k]);
-                            const float s2 = warp_sum(v[k] * v[k]);
-                            if (lane == k) {
-                                atomicAdd(&sstat[(c16 * 16 + k) * 2], (double)s);
-                                atomicAdd(&sstat[(c16 * 16 + k) * 2 + 1], (double)s2);
-                            }
-                        }
-                    }
                     if (rc_ok) {
 #pragma unroll
                         for (int h8 = 0; h8 < 2; ++h8) {
@@ -312,6 +327,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
                             }
                         }
                     }
+                    if (p.stats != nullptr) {
+                        float sq[16];
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) sq[k] = v[k] * v[k];
+                        racc[c16][0] += (double)transpose_reduce16(v, lane);
+                        racc[c16][1] += (double)transpose_reduce16(sq, lane);
+                    }
                 }
             }
             tc_fence_before();
@@ -319,13 +341,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
             if (lane == 0) mbar_arrive(&tempty_bar[buf]);
             if (++buf == NBUF) { buf = 0; bphase ^= 1; }
         }
-        if (p.stats != nullptr && stat_n >= 0) {
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            for (int i = et; i < NC * 2; i += 128) {
-                const int c = stat_chunk * NC + (i >> 1);
-                if (c < p.cout) atomicAdd(&p.stats[((long long)stat_n * p.cout + c) * 2 + (i & 1)], sstat[i]);
-            }
-        }
+        if (p.stats != nullptr) flush_stats();
     }
     tc_fence_before();
     __syncthreads();
