@@ -156,6 +156,7 @@ class JointTrainer(object):
         self.lambda_vae, self.loss_type, self.kl = lambda_vae, loss_type, kl
         self.confident, self.only_pseudo, self.alpha = confident, only_pseudo, alpha
         self.faithful_teacher = faithful_teacher
+        self.stream = torch.cuda.Stream()        # see capture()
 
     def ema_teacher(self):
         # main_target.py:512-516 on the Seg state_dict
@@ -202,6 +203,35 @@ class JointTrainer(object):
         final.backward()
         self.opt.step(allreduce_mean_(self.arena.grad))
         return mon
+
+    def capture(self, img_static, label_static, warmup=2):
+        """CUDA-graph capture of zero_grad + forward (student, teacher, losses) + backward on the given static
+        input buffers; the gradient all-reduce and the fused optimiser kernel stay eager (two launches).  At
+        ~600 kernel launches per step the Python/launch path, not the GPU, bounds an eager step.
+        Autograd pins each parameter's gradient-accumulation node to the stream of its first backward, and a
+        capture may not depend on the legacy default stream: run EVERY step of this trainer under
+        `with torch.cuda.stream(trainer.stream)` if it will be captured later."""
+        side = self.stream
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):            # autograd's stream bookkeeping must see the capture stream
+            for _ in range(max(warmup, 1)):      # also runs every lazy one-time init (smem attributes, caches)
+                self.step(img_static, label_static)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph, stream=side):
+            self.arena.zero_grad()
+            final, mon, _ = self.losses(img_static, label_static)
+            final.backward()
+        self._graph_mon = mon
+        return self
+
+    def step_graphed(self, update_teacher=False):
+        if update_teacher:
+            self.ema_teacher()
+        self._graph.replay()
+        self.opt.step(allreduce_mean_(self.arena.grad))
+        return self._graph_mon
 
     def test_time_train(self, finetune, img, label, iters=1, lr_finetune=1e-2):
         """main_target.py:807-900: per validation case, `finetune` (a Joint) starts from the
