@@ -142,7 +142,10 @@ def test_segmentation_train_step_vs_oracle(precision, otol, gtol):
     # logit margin is ~N(.46,.51) so 16-bit storage cannot reach it -- bf16 is held to 97 %
     assert agree >= (0.999 if precision == "fp32" else 0.97), "argmax agreement %.5f" % agree
     if precision == "fp32":
-        check_grads(grads_of(seg), grads_ref, gtol)
+        # the ConvTranspose3d biases feed a zero-padded conv + InstanceNorm: their gradient is a boundary-only
+        # residual of cancelling sums, on which the fp32 reference itself is ~1e-3 off float64 -> calibrate
+        _, grads64, _ = R.seg_train_step(sd, img, label, eps=0.0001, dtype=torch.float64)
+        check_grads(grads_of(seg), grads_ref, gtol, truth=grads64)
     else:
         check_grads_bf16(grads_of(seg), grads_ref)
 

@@ -14,10 +14,16 @@
 // same halo: every input voxel is fetched from L2/HBM once per CTA and reused by all 27 taps x 4 planes.
 // For Cin = 8 two taps (kw, kw+1) are paired into one K=16 MMA by setting LBO = 16 B (the next voxel).
 //
-// Pipeline: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread) + TMEM allocator,
-// warps 2-5 = epilogue (tcgen05.ld -> shift -> InstanceNorm statistics -> bf16 -> global).  smem stages
-// ring over (tile, 16-channel slice); TMEM accumulators are double buffered across tiles so the epilogue
-// of tile i overlaps the MMAs of tile i+1.
+// Pipeline: warp 0 = TMA producer, warps 1-4 = MMA issuers (one per d-plane of the tile; warp 1 also owns the
+// TMEM allocation), warps 5-8 = epilogue (tcgen05.ld -> shift -> InstanceNorm statistics -> bf16 -> global).
+// smem stages ring over (tile, 16-channel slice); TMEM accumulators are double buffered across tiles so the
+// epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Why four issuing warps: with N = 16..64 one MMA occupies the tensor pipe for only ~40-48 cycles
+// (tools/mma_probe.cu: SS-mode floor ~ 32 + N/4 cycles at M = 128), but a single thread cannot issue them
+// faster than one per ~75-130 cycles (each UTCHMMA needs its descriptors moved into uniform registers).
+// Four warps issuing to four independent accumulators hide that issue latency; all role branches are
+// warp-uniform (shfl-derived warp index, elect.sync inside the asm) so no divergent-region waterfall is emitted.
 #include <cuda.h>
 #include "vs_common.cuh"
 
@@ -28,7 +34,7 @@ constexpr int HD = TD + 2, HH = TH + 2, HW = TW + 2;   // halo 6 x 18 x 10
 constexpr int HV = HD * HH * HW;                       // 1080 halo voxels
 constexpr int PLANE_BYTES = HV * 16;                   // 17280 (multiple of 128)
 constexpr int PLANE_PAD = 256;                         // slack read by the zero-weighted third tap of the Cin=8 pairs
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 288;                          // 1 producer + 4 MMA + 4 epilogue warps
 
 struct TcParams {
     int n, d, h, w, cin, cout;
@@ -77,6 +83,12 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m
         ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -101,6 +113,24 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// whole warp executes, one elected lane issues (no C++-level branch around the instruction)
+__device__ __forceinline__ void tc_mma_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pe, pa;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "setp.ne.b32 pa, %4, 0;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pa;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_commit_elect(uint64_t* bar) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pe;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
@@ -173,11 +203,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
     float* sshift = reinterpret_cast<float*>(tmem_slot + 4);          // [NC]
     double* sstat = reinterpret_cast<double*>(sshift + NC);           // [NC][2]
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);      // warp-uniform for the compiler
+    const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int b = 0; b < NBUF; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], TD); }
+        for (int b = 0; b < NBUF; ++b) { mbar_init(&tfull_bar[b], TD); mbar_init(&tempty_bar[b], 4); }
         fence_barrier_init();
     }
     if (CIN8) {
@@ -192,7 +223,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -205,7 +236,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * STAGE_BYTES;
                     mbar_expect_tx(&full_bar[stage], (CIN8 ? PLANE_BYTES : 2 * PLANE_BYTES) + B_BYTES);
-                    tma_load_5d(sa, &xmap, &full_bar[stage], ks * 16, w0 - 1, h0 - 1, d0 - 1, n);
+                    if (CIN8) tma_load_4d(sa, &xmap, &full_bar[stage], (w0 - 1) * 8, h0 - 1, d0 - 1, n);   // (w,c) merged: 160 B rows
+                    else tma_load_5d(sa, &xmap, &full_bar[stage], ks * 16, w0 - 1, h0 - 1, d0 - 1, n);
                     if (!CIN8) tma_load_5d(sa + PLANE_BYTES, &xmap, &full_bar[stage], ks * 16 + 8, w0 - 1, h0 - 1, d0 - 1, n);
                     const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) +
                                           ((long long)chunk * p.kslices + ks) * B_BYTES;
@@ -214,59 +246,50 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(NC);
-            uint32_t stage = 0, phase = 0, buf = 0, bphase = 0;
-            for (long long item = blockIdx.x; item < p.work_items; item += gridDim.x) {
-                int n, d0, h0, w0, chunk;
-                decode_work(item, p, n, d0, h0, w0, chunk);
-                const int jmax = min(TD, p.d - d0);
-                mbar_wait(&tempty_bar[buf], bphase ^ 1);
+    } else if (warp <= TD) {
+        // ===================== MMA issuers: warp 1 + j owns d-plane j of every tile =====================
+        const int j = warp - 1;
+        constexpr uint32_t idesc = make_idesc(NC);
+        uint32_t stage = 0, phase = 0, buf = 0, bphase = 0;
+        for (long long item = blockIdx.x; item < p.work_items; item += gridDim.x) {
+            int n, d0, h0, w0, chunk;
+            decode_work(item, p, n, d0, h0, w0, chunk);
+            const bool active = j < min(TD, p.d - d0);
+            mbar_wait(&tempty_bar[buf], bphase ^ 1);
+            tc_fence_after();
+            const uint32_t dcol = tmem_base + (buf * TD + j) * NC;
+            for (int ks = 0; ks < p.kslices; ++ks) {
+                mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                for (int ks = 0; ks < p.kslices; ++ks) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t a_base = smem_u32(smem + stage * STAGE_BYTES);
-                    const uint32_t b_base = a_base + A_BYTES;
-                    for (int j = 0; j < jmax; ++j) {
-                        const uint32_t dcol = tmem_base + (buf * TD + j) * NC;
-                        int m = 0;
+                if (active) {
+                    const uint32_t a_base = smem_u32(smem + stage * STAGE_BYTES) + (uint32_t)(j * HH * HW) * 16u;
+                    const uint32_t b_base = smem_u32(smem + stage * STAGE_BYTES) + A_BYTES;
+                    int m = 0;
 #pragma unroll 1
-                        for (int kd = 0; kd < 3; ++kd) {
-#pragma unroll 1
-                            for (int kh = 0; kh < 3; ++kh) {
-                                const uint32_t row = a_base + (uint32_t)(((j + kd) * HH + kh) * HW) * 16u;
-                                if (CIN8) {
+                    for (int kd = 0; kd < 3; ++kd) {
 #pragma unroll
-                                    for (int pr = 0; pr < 2; ++pr, ++m) {
-                                        const uint64_t ad = make_desc(row + pr * 32u, 16u, HW * 16u);
-                                        const uint64_t bd = make_desc(b_base + m * (NC * 32), NC * 16, 128u);
-                                        tc_mma(dcol, ad, bd, idesc, (ks | m) != 0);
-                                    }
-                                } else {
+                        for (int kh = 0; kh < 3; ++kh) {
+                            const uint32_t row = a_base + (uint32_t)((kd * HH + kh) * HW) * 16u;
 #pragma unroll
-                                    for (int kw = 0; kw < 3; ++kw, ++m) {
-                                        const uint64_t ad = make_desc(row + kw * 16u, PLANE_BYTES, HW * 16u);
-                                        const uint64_t bd = make_desc(b_base + m * (NC * 32), NC * 16, 128u);
-                                        tc_mma(dcol, ad, bd, idesc, (ks | m) != 0);
-                                    }
-                                }
+                            for (int kx = 0; kx < (CIN8 ? 2 : 3); ++kx, ++m) {
+                                const uint64_t ad = CIN8 ? make_desc(row + kx * 32u, 16u, HW * 16u)
+                                                         : make_desc(row + kx * 16u, PLANE_BYTES, HW * 16u);
+                                const uint64_t bd = make_desc(b_base + m * (NC * 32), NC * 16, 128u);
+                                tc_mma_elect(dcol, ad, bd, idesc, (ks | m) != 0);
                             }
                         }
                     }
-                    tc_commit(&empty_bar[stage]);               // frees the smem stage when these MMAs retire
-                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(&tfull_bar[buf]);                     // accumulators of this tile complete
-                if (++buf == NBUF) { buf = 0; bphase ^= 1; }
+                tc_commit_elect(&empty_bar[stage]);             // this warp's reads of the smem stage have retired
+                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
+            tc_commit_elect(&tfull_bar[buf]);                   // this warp's accumulator plane is complete
+            if (++buf == NBUF) { buf = 0; bphase ^= 1; }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
+        // ===================== epilogue (warps 5..8) =====================
         const int q = warp & 3;                                  // TMEM lane quadrant this warp may read
-        const int et = threadIdx.x - 64;                         // 0..127 within the epilogue group
+        const int et = threadIdx.x - 32 * (TD + 1);              // 0..127 within the epilogue group
         const int row = q * 32 + lane;                           // accumulator row = voxel in the d-plane
         const int lh = row >> 3, lw = row & 7;
         uint32_t buf = 0, bphase = 0;
@@ -468,7 +491,18 @@ extern "C" int vs_conv3x3x3_tc(const void* x, const void* wtc, void* y, double* 
                                 (cuuint64_t)d * h * w * gin * 2};
     const cuuint32_t box[5] = {8, HW, HH, HD, 1};
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult cr = encode(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), gdim, gstr, box, estr,
+    CUresult cr;
+    if (gin == 8) {
+        // Cin = 8: a w-row of the halo is 10 voxels x 16 B contiguous in memory; merging (w, c) into one
+        // dimension makes it ONE 160 B TMA row instead of ten 16 B rows (TMA cost is per row)
+        const cuuint64_t gdim4[4] = {(cuuint64_t)w * 8, (cuuint64_t)h, (cuuint64_t)d, (cuuint64_t)n};
+        const cuuint64_t gstr4[3] = {(cuuint64_t)w * 16, (cuuint64_t)h * w * 16, (cuuint64_t)d * h * w * 16};
+        const cuuint32_t box4[4] = {HW * 8, HH, HD, 1};
+        cr = encode(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), gdim4, gstr4, box4, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else
+    cr = encode(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), gdim, gstr, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     VS_REQUIRE(cr == CUDA_SUCCESS, VS_ERR_CUDA, "conv3_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr);

@@ -183,28 +183,28 @@ __global__ void __launch_bounds__(8 * BCH) k2s2_wgrad_kernel(const T* __restrict
 template <typename T>
 __global__ void __launch_bounds__(256) channel_sum_kernel(const T* __restrict__ x, float* __restrict__ out,
                                                           long long rows, int c) {
-    __shared__ float red[256][8];
+    __shared__ double red[256][8];            // fp64 partials: these bias gradients are residuals of cancelling sums
     const int groups = c / 8;                 // <= 32
     const int t = threadIdx.x;
     const int lanes = 256 / groups;
     const int g = t % groups, lane = t / groups;
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    double acc[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
     if (lane < lanes) {
         for (long long r = (long long)blockIdx.x * lanes + lane; r < rows; r += (long long)gridDim.x * lanes) {
             float v[8];
             Store<T>::ld8(x + r * c + g * 8, v);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) acc[q] += v[q];
+            for (int q = 0; q < 8; ++q) acc[q] += (double)v[q];
         }
     }
 #pragma unroll
-    for (int q = 0; q < 8; ++q) red[t][q] = (lane < lanes) ? acc[q] : 0.f;
+    for (int q = 0; q < 8; ++q) red[t][q] = (lane < lanes) ? acc[q] : 0.;
     __syncthreads();
     if (t < c) {
         const int gg = t / 8, q = t % 8;
-        float s = 0.f;
+        double s = 0.;
         for (int l = 0; l < lanes; ++l) s += red[l * groups + gg][q];
-        atomicAdd(out + t, s);
+        atomicAdd(out + t, (float)s);
     }
 }
 
