@@ -1,0 +1,80 @@
+"""Data-parallel host logic on CPU: world_size 2, gloo backend.
+
+The CUDA kernels cannot run here, so the per-rank gradients come from the oracle; what is under
+test is the PRODUCT's collective logic (`train_step.allreduce_mean_`, `train_step.sync_first_term_`):
+sum over ranks + 1/world scale must equal the reference's DataParallel semantics, i.e. the gradient
+of the loss on the gathered (concatenated) batch (main_target.py:436-438,734-736)."""
+import os
+import socket
+import tempfile
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import ref_torch as R
+from vae_segmentation_b200 import train_step as ts
+from vae_segmentation_b200.synthetic import synth_image, synth_label
+
+PATCH = 32
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, outdir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(7)                              # identical replicas on every rank
+        sd = R.init_seg_state()
+        torch.manual_seed(100)                            # the global batch, identical on every rank ...
+        img, label = synth_image(world, PATCH), synth_label(world, PATCH)
+        loss, grads, _ = R.seg_train_step(sd, img[rank:rank + 1], label[rank:rank + 1], eps=0.0001,
+                                          dtype=torch.float64)                            # ... sharded (fp64:
+        # fp32 gradients of this net carry ~1e-2 conditioning noise)
+        flat = torch.cat([g.reshape(-1) for g in grads.values()])
+        scale = ts.allreduce_mean_(flat)                  # product code: SUM all-reduce, returns 1/world
+        terms = torch.tensor([0.1 + 0.2 * rank, 1.0 + rank, 2.0 + rank], dtype=torch.float64)
+        synced = ts.sync_first_term_(terms)
+        torch.save({"flat": flat * scale, "scale": scale, "terms": synced, "loss": loss.detach()},
+                   os.path.join(outdir, "rank%d.pt" % rank))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_gradient_allreduce_equals_gathered_batch():
+    world = 2
+    with tempfile.TemporaryDirectory() as outdir:
+        mp.spawn(_worker, args=(world, _free_port(), outdir), nprocs=world, join=True)
+        outs = [torch.load(os.path.join(outdir, "rank%d.pt" % r)) for r in range(world)]
+    assert all(o["scale"] == 0.5 for o in outs)
+    assert torch.equal(outs[0]["flat"], outs[1]["flat"])                    # every rank holds the same averaged gradient
+    # dynamic lambda: terms[0] replaced by the global mean on every rank, the rest untouched
+    assert torch.allclose(outs[0]["terms"], torch.tensor([0.2, 1.0, 2.0], dtype=torch.float64))
+    assert torch.allclose(outs[1]["terms"], torch.tensor([0.2, 2.0, 3.0], dtype=torch.float64))
+    # single-process result on the gathered batch: Dice is per-sample then batch-mean, InstanceNorm is per-(n,c),
+    # so mean-of-shard-gradients == gradient of the gathered-batch loss
+    torch.manual_seed(7)
+    sd = R.init_seg_state()
+    torch.manual_seed(100)
+    img, label = synth_image(world, PATCH), synth_label(world, PATCH)
+    loss, grads, _ = R.seg_train_step(sd, img, label, eps=0.0001, dtype=torch.float64)
+    want = torch.cat([g.reshape(-1) for g in grads.values()])
+    got = outs[0]["flat"]
+    assert ((got - want).norm() / want.norm()).item() < 1e-9
+    assert abs(0.5 * (outs[0]["loss"] + outs[1]["loss"]).item() - loss.item()) < 1e-9
+
+
+def test_single_process_is_identity():
+    g = torch.arange(6.0)
+    assert ts.allreduce_mean_(g) == 1.0 and torch.equal(g, torch.arange(6.0))
+    t = torch.tensor([0.3, 1.0, 2.0])
+    assert ts.sync_first_term_(t) is t

@@ -94,8 +94,16 @@ def allreduce_mean_(flat_grad):
     return 1.0 / world
 
 
-def _fg(per):
-    return per
+def sync_first_term_(terms):
+    """Dynamic lambda (type 8, main_target.py:550-560) thresholds recon_loss on the host of the single
+    DataParallel process, i.e. on the GLOBAL batch.  Under process-per-GPU every rank must take the same
+    branch: replace terms[0] by its mean over ranks (equal per-rank batches), one 1-float all-reduce."""
+    world = _world()
+    if world == 1:
+        return terms
+    g = terms[0:1].clone()
+    dist.all_reduce(g, op=dist.ReduceOp.SUM)
+    return torch.cat([g / world, terms[1:]])
 
 
 class SegTrainer(object):
@@ -184,11 +192,8 @@ class JointTrainer(object):
             final = dsc_loss_fake
         else:
             terms = torch.stack([recon_loss.detach(), dsc_loss_fake.detach(), klloss.detach()])
-            if self.loss_type == 8 and _world() > 1:
-                # every rank must take the same lambda branch: threshold the global-batch mean
-                g = terms[0:1].clone()
-                dist.all_reduce(g, op=dist.ReduceOp.SUM)
-                terms = torch.cat([g / _world(), terms[1:]])
+            if self.loss_type == 8:
+                terms = sync_first_term_(terms)
             _, wts = ops.compose_target_loss(terms, self.lambda_vae, self.loss_type, self.kl)
             final = wts[0] * recon_loss + wts[1] * dsc_loss_fake + (wts[2] * klloss if self.kl else 0)
         mon = {"final_loss": final.detach(), "recon_loss": recon_loss.detach(), "dice_loss": dsc_loss.detach(),
