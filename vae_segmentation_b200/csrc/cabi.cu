@@ -32,7 +32,7 @@ extern "C" int vs_conv3x3x3_fprop_direct(int in_dtype, int out_dtype, int in_pla
 extern "C" int vs_conv3_shift_internal(int in_dtype, int in_planar, const void* x, const float* wpk, float* shift, int n,
                                        int d, int h, int w, int cin, int cout, void* stream);
 #ifdef VS_WITH_TCGEN05
-extern "C" int vs_conv3x3x3_tc(const void* x, const void* wtc, void* y, double* stats, const float* shift, int n, int d,
+extern "C" int vs_conv3x3x3_tc(const void* x, const void* wtc, void* y, double* stats, float* shift, int n, int d,
                                int h, int w, int gin, int gout, void* stream);
 extern "C" size_t vs_conv3_tc_pack_bytes(int cin, int cout, int dgrad);
 #endif
@@ -57,10 +57,7 @@ extern "C" int vs_conv3x3x3_fprop(int in_dtype, int out_dtype, int in_planar, in
 #ifdef VS_WITH_TCGEN05
     if (wtc != nullptr && in_dtype == VS_BF16 && out_dtype == VS_BF16 && !in_planar && !out_planar && bias == nullptr &&
         tc_eligible(cin, cout)) {
-        if (shift != nullptr) {
-            int rc = vs_conv3_shift_internal(in_dtype, 0, x, wpk, shift, n, d, h, w, cin, cout, stream);
-            if (rc) return rc;
-        }
+        // the tensor-core kernel derives and publishes the shift itself (no separate launch)
         return vs_conv3x3x3_tc(x, wtc, y, stats, shift, n, d, h, w, cin, cout, stream);
     }
 #else

@@ -45,7 +45,7 @@ struct TcParams {
     const bf16* wpack;
     bf16* y;
     double* stats;          // [n][cout][2] or null
-    const float* shift;     // [n][cout] or null
+    float* shift;           // [n][cout] or null; zeroed by the host, published in-kernel (see epilogue)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -138,6 +138,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr));
+}
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -294,35 +299,89 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
         const int lh = row >> 3, lw = row & 7;
         uint32_t buf = 0, bphase = 0;
         int stat_n = -1, stat_chunk = -1;
-        // per-warp running statistics: lane L (< 16) owns columns c16*16 + L of this warp's 32 rows
-        double racc[NC / 16][2];
+        // running statistics: every thread keeps fp32 (sum, sum of squares) of ITS accumulator row for each of the
+        // NC columns across all tiles of a (n, chunk) group -- two FP ops per element in the hot loop; the cross-lane
+        // reduction (31 shuffles per 16 columns) and the fp64 atomics run once per group, not once per tile.  The
+        // values are deviations from the shift, so fp32 partial sums of a few hundred terms lose nothing.
+        float rs[NC / 16][16], rq[NC / 16][16];
 #pragma unroll
-        for (int c = 0; c < NC / 16; ++c) { racc[c][0] = 0.0; racc[c][1] = 0.0; }
+        for (int c = 0; c < NC / 16; ++c)
+#pragma unroll
+            for (int k = 0; k < 16; ++k) { rs[c][k] = 0.f; rq[c][k] = 0.f; }
         auto flush_stats = [&]() {
-            if (stat_n >= 0 && lane < 16) {
+            if (p.stats != nullptr && stat_n >= 0) {
 #pragma unroll
                 for (int c = 0; c < NC / 16; ++c) {
+                    const float s1 = transpose_reduce16(rs[c], lane);
+                    const float s2 = transpose_reduce16(rq[c], lane);
                     const int co = stat_chunk * NC + c * 16 + lane;
-                    if (co < p.cout) {
-                        atomicAdd(&p.stats[((long long)stat_n * p.cout + co) * 2], racc[c][0]);
-                        atomicAdd(&p.stats[((long long)stat_n * p.cout + co) * 2 + 1], racc[c][1]);
+                    if (lane < 16 && co < p.cout) {
+                        atomicAdd(&p.stats[((long long)stat_n * p.cout + co) * 2], (double)s1);
+                        atomicAdd(&p.stats[((long long)stat_n * p.cout + co) * 2 + 1], (double)s2);
                     }
-                    racc[c][0] = 0.0; racc[c][1] = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) { rs[c][k] = 0.f; rq[c][k] = 0.f; }
                 }
             }
         };
+        if (et < NC) sshift[et] = 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // The per-(n,c) shift (see header: InstanceNorm-invariant, keeps bf16 precision when |mean| >> sigma) is the
+        // fp32 accumulator of a reference voxel of the sample.  It is produced by the CTA that owns the tile holding
+        // that voxel (tile 0 of the sample = the lowest work item of its (n, chunk) group), published through global
+        // memory as (bits | 1) into the host-zeroed `shift` array, and every other CTA spins on "non-zero" before its
+        // first tile of the group.  Progress: a waiter only ever waits on a strictly lower work item and each CTA
+        // walks its items in increasing order; the grid is <= #SMs with one CTA per SM, so all CTAs are resident.
+        const int rd = min(1, p.d - 1), rh = min(1, p.h - 1), rw = min(1, p.w - 1);
+        const bool has_shift = p.shift != nullptr;
+        const bool has_stats = p.stats != nullptr;
+        const uint32_t sshift_addr = smem_u32(sshift);
+        const int ref_row = rh * TW + rw;
         for (long long item = blockIdx.x; item < p.work_items; item += gridDim.x) {
             int n, d0, h0, w0, chunk;
             decode_work(item, p, n, d0, h0, w0, chunk);
             const int co0 = chunk * NC;
-            if (p.stats != nullptr && (n != stat_n || chunk != stat_chunk)) {
+            if (n != stat_n || chunk != stat_chunk) {
                 flush_stats();
                 stat_n = n; stat_chunk = chunk;
+                if (p.shift != nullptr) {
+                    asm volatile("bar.sync 1, 128;" ::: "memory");       // everyone is done with the previous group's sshift
+                    if (d0 == 0 && h0 == 0 && w0 == 0) {
+                        mbar_wait(&tfull_bar[buf], bphase);
+                        tc_fence_after();
+                        if (q == (ref_row >> 5)) {
+#pragma unroll
+                            for (int c16 = 0; c16 < NC / 16; ++c16) {
+                                uint32_t r[16];
+                                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (buf * TD + rd) * NC + c16 * 16, r);
+                                tmem_ld_wait();
+                                if (lane == (ref_row & 31)) {
+#pragma unroll
+                                    for (int k = 0; k < 16; ++k) {
+                                        const uint32_t bits = r[k] | 1u;
+                                        sshift[c16 * 16 + k] = __uint_as_float(bits);
+                                        if (co0 + c16 * 16 + k < p.cout)
+                                            *reinterpret_cast<volatile uint32_t*>(p.shift + (long long)n * p.cout + co0 + c16 * 16 + k) = bits;
+                                    }
+                                }
+                            }
+                        }
+                    } else if (et < NC) {
+                        float sv = 0.f;
+                        if (co0 + et < p.cout) {
+                            const volatile uint32_t* flag = reinterpret_cast<const volatile uint32_t*>(p.shift + (long long)n * p.cout + co0 + et);
+                            uint32_t bits, spins = 0;
+                            while ((bits = *flag) == 0u) {
+                                __nanosleep(64);
+                                if (++spins > (1u << 23)) __trap();                // never hang the GPU on a protocol bug
+                            }
+                            sv = __uint_as_float(bits);
+                        }
+                        sshift[et] = sv;
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
             }
-            // everyone is done with the previous tile's sshift before it is overwritten
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (et < NC) sshift[et] = (p.shift != nullptr && co0 + et < p.cout) ? p.shift[(long long)n * p.cout + co0 + et] : 0.f;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
             mbar_wait(&tfull_bar[buf], bphase);
             tc_fence_after();
             const int jmax = min(TD, p.d - d0);
@@ -337,8 +396,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
                     tmem_ld16(taddr + c16 * 16, r);
                     tmem_ld_wait();
                     float v[16];
+                    if (has_shift) {
+                        // explicit 128-bit shared loads (warp-broadcast, conflict-free); a generic LD through the
+                        // reinterpret-cast pointer costs ~8 wavefronts each on the pipe the MMA operands share
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) v[k] = rc_ok ? __uint_as_float(r[k]) - sshift[c16 * 16 + k] : 0.f;
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            const float4 sh = lds128(sshift_addr + (c16 * 16 + k4 * 4) * 4);
+                            v[k4 * 4 + 0] = __uint_as_float(r[k4 * 4 + 0]) - sh.x;
+                            v[k4 * 4 + 1] = __uint_as_float(r[k4 * 4 + 1]) - sh.y;
+                            v[k4 * 4 + 2] = __uint_as_float(r[k4 * 4 + 2]) - sh.z;
+                            v[k4 * 4 + 3] = __uint_as_float(r[k4 * 4 + 3]) - sh.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(r[k]);
+                    }
+                    if (!rc_ok) {
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) v[k] = 0.f;
+                    }
                     if (rc_ok) {
 #pragma unroll
                         for (int h8 = 0; h8 < 2; ++h8) {
@@ -350,12 +426,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
                             }
                         }
                     }
-                    if (p.stats != nullptr) {
-                        float sq[16];
+                    if (has_stats) {
 #pragma unroll
-                        for (int k = 0; k < 16; ++k) sq[k] = v[k] * v[k];
-                        racc[c16][0] += (double)transpose_reduce16(v, lane);
-                        racc[c16][1] += (double)transpose_reduce16(sq, lane);
+                        for (int k = 0; k < 16; ++k) { rs[c16][k] += v[k]; rq[c16][k] = fmaf(v[k], v[k], rq[c16][k]); }
                     }
                 }
             }
@@ -364,7 +437,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
             if (lane == 0) mbar_arrive(&tempty_bar[buf]);
             if (++buf == NBUF) { buf = 0; bphase ^= 1; }
         }
-        if (p.stats != nullptr) flush_stats();
+        flush_stats();
     }
     tc_fence_before();
     __syncthreads();
@@ -475,7 +548,7 @@ extern "C" int vs_pack_conv3_weight_tc(const float* w, void* out, int cin, int c
 }
 
 // y[n,d,h,w,gout] = conv3(x[n,d,h,w,gin], wtc) on the tensor cores; bf16 NDHWC in and out.
-extern "C" int vs_conv3x3x3_tc(const void* x, const void* wtc, void* y, double* stats, const float* shift, int n, int d,
+extern "C" int vs_conv3x3x3_tc(const void* x, const void* wtc, void* y, double* stats, float* shift, int n, int d,
                                int h, int w, int gin, int gout, void* stream) {
     VS_REQUIRE(x && wtc && y, VS_ERR_SHAPE, "conv3_tc: null pointer");
     VS_REQUIRE((gin == 8 || (gin % 16 == 0 && gin >= 16)) && gout % 8 == 0 && gout >= 8, VS_ERR_UNSUPPORTED,
@@ -516,7 +589,14 @@ extern "C" int vs_conv3x3x3_tc(const void* x, const void* wtc, void* y, double* 
     p.kslices = gin == 8 ? 1 : gin / 16;
     p.work_items = (long long)n * p.tiles_per_n * p.nchunks;
     p.wpack = (const bf16*)wtc; p.y = (bf16*)y; p.stats = stats; p.shift = shift;
-    if (stats) VS_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * n * gout, st), "conv3_tc stats memset");
+    // zero the statistics and the shift/flag words (one memset when the caller laid them out back to back)
+    const size_t stat_bytes = sizeof(double) * 2 * (size_t)n * gout, shift_bytes = sizeof(float) * (size_t)n * gout;
+    if (stats && shift && reinterpret_cast<char*>(shift) == reinterpret_cast<char*>(stats) + stat_bytes) {
+        VS_CUDA(cudaMemsetAsync(stats, 0, stat_bytes + shift_bytes, st), "conv3_tc stats+shift memset");
+    } else {
+        if (stats) VS_CUDA(cudaMemsetAsync(stats, 0, stat_bytes, st), "conv3_tc stats memset");
+        if (shift) VS_CUDA(cudaMemsetAsync(shift, 0, shift_bytes, st), "conv3_tc shift memset");
+    }
 
     if (gin == 8) {
         if (nc == 16) return launch_tc<16, true, 4>(map, p, st);

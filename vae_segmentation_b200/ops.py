@@ -75,10 +75,19 @@ def conv3_fprop(x, wf, bias, dims, cin, cout, out_dtype, in_planar=False, out_pl
         y = torch.empty(n, cout, d, h, w, device=dev, dtype=torch.float32)
     else:
         y = torch.empty(n, d, h, w, cout, device=dev, dtype=out_dtype)
-    stats = torch.empty(n, cout, 2, device=dev, dtype=torch.float64) if want_stats else None
     if shifted is None:
         shifted = want_stats
-    shift = torch.empty(n, cout, device=dev, dtype=torch.float32) if shifted else None
+    stats = shift = None
+    if want_stats and shifted:
+        # one allocation, statistics first and the shift words right behind them: the library zeroes both with a
+        # single memset (the tensor-core kernel publishes the shift through those words, see conv3_tc.cu)
+        buf = torch.empty(n * cout * 2 + (n * cout + 1) // 2, device=dev, dtype=torch.float64)
+        stats = buf[:n * cout * 2].view(n, cout, 2)
+        shift = buf[n * cout * 2:].view(torch.float32)[:n * cout].view(n, cout)
+    elif want_stats:
+        stats = torch.empty(n, cout, 2, device=dev, dtype=torch.float64)
+    elif shifted:
+        shift = torch.empty(n, cout, device=dev, dtype=torch.float32)
     _cabi.call("vs_conv3x3x3_fprop", _dt(x), _dt(y), int(in_planar), int(out_planar), _p(x), _p(_f32(wf, "wf")), _p(wtc),
                _p(_f32(bias, "bias")), _p(y), _p(stats), _p(shift), n, d, h, w, cin, cout, _stream())
     return y, stats
