@@ -62,3 +62,26 @@ def test_tc_fprop_and_dgrad(case):
     y2, _ = ops.conv3_fprop(xd, wq.to(DEV).reshape(cout, cin, 27).permute(2, 1, 0).contiguous(), None, dims, cin, cout,
                             torch.bfloat16, shifted=False, wtc=None)
     assert (y2.float() - y.float()).abs().max().item() < 1e-2 * scale
+
+
+@pytest.mark.parametrize("case", CASES + [(2, 8, 32, 16, 8, 8), (1, 4, 16, 8, 16, 128), (1, 5, 6, 7, 128, 256)])
+def test_tc_wgrad(case):
+    """tcgen05 backward-filter (voxel = K, MN-major operands) against torch autograd on the same bf16 operands;
+    ragged extents exercise the TMA zero fill of BOTH operands, Cout > 64 the 64-row chunks, accumulate=True the
+    add-onto semantics."""
+    n, d, h, w, cin, cout = case
+    torch.manual_seed(sum(case) + 1)
+    x = torch.randn(n, cin, d, h, w).bfloat16().float()
+    gy = torch.randn(n, cout, d, h, w).bfloat16().float()
+    wt = torch.zeros(cout, cin, 3, 3, 3, requires_grad=True)
+    F.conv3d(x, wt, None, padding=1).backward(gy)
+    want = wt.grad
+    dims = (n, d, h, w)
+    xd, gyd = to_ndhwc(x), to_ndhwc(gy)
+    dw, _ = ops.conv3_wgrad(xd, gyd, dims, cin, cout)
+    torch.cuda.synchronize()
+    scale = want.abs().max().item()
+    err = (dw.cpu() - want).abs().max().item()
+    assert err < 2e-3 * scale, "tc wgrad max err %.3e (scale %.3e)" % (err, scale)
+    dw2, _ = ops.conv3_wgrad(xd, gyd, dims, cin, cout, dw=dw.clone(), accumulate=True)
+    assert (dw2.cpu() - 2 * want).abs().max().item() < 4e-3 * scale

@@ -447,6 +447,15 @@ extern "C" int vs_conv3_shift_internal(int in_dtype, int in_planar, const void* 
 
 extern "C" size_t vs_conv3_wgrad_workspace_bytes(int, int, int, int, int, int) { return 0; }
 
+#ifdef VS_WITH_TCGEN05
+extern "C" int vs_conv3_wgrad_tc_eligible(int cin, int cout);
+extern "C" int vs_conv3x3x3_wgrad_tc(const void* x, const void* dy, float* dw, int n, int d, int h, int w, int cin, int cout,
+                                     void* stream);
+#endif
+static int g_wgrad_tc = 1;
+// development switch (tools/kbench.py A/B runs): 0 forces the CUDA-core wgrad kernel
+extern "C" void vs_debug_set_wgrad_tc(int on) { g_wgrad_tc = on; }
+
 extern "C" int vs_conv3x3x3_wgrad(int dtype, int in_planar, const void* x, const void* dy, float* dw, float* db,
                                   void* workspace, size_t ws_bytes, int accumulate, int n, int d, int h, int w,
                                   int cin, int cout, void* stream) {
@@ -459,6 +468,11 @@ extern "C" int vs_conv3x3x3_wgrad(int dtype, int in_planar, const void* x, const
         VS_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * 27 * cin * cout, st), "wgrad memset");
         if (db) VS_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * cout, st), "wgrad memset db");
     }
+#ifdef VS_WITH_TCGEN05
+    // bf16 NDHWC operands without a bias gradient -> tcgen05 kernel (conv3_wgrad_tc.cu)
+    if (g_wgrad_tc && dtype == VS_BF16 && !in_planar && db == nullptr && vs_conv3_wgrad_tc_eligible(cin, cout))
+        return vs_conv3x3x3_wgrad_tc(x, dy, dw, n, d, h, w, cin, cout, stream);
+#endif
     if (in_planar) {
         if (dtype == VS_F32) return launch_wgrad<float, true>(x, dy, dw, db, p, st);
         return launch_wgrad<bf16, true>(x, dy, dw, db, p, st);

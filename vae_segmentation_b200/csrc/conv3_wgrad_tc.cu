@@ -1,0 +1,300 @@
+// 3x3x3 convolution backward-filter on the 5th-gen tensor cores (sm_100a).
+// Replaces cuDNN wgrad for joint_model.py:40-46,106 (the Conv3d layers with Cin = 8 or a multiple of 16).
+//
+//   dw[co][ci][kd,kh,kw] = sum over voxels v of  dy[v][co] * x[v + (kd,kh,kw) - 1][ci]
+//
+// GEMM view: the reduction (K) dimension is the VOXEL, 16 voxels per tcgen05.mma (kind::f16, bf16 -> fp32 in TMEM):
+//     D[64 co, 24 = (kw, 8 ci)] += A[64 co, 16 vox] * B[24, 16 vox]^T        for every (kd, kh, 8-channel group of ci).
+// Both operands are "MN-major" (the voxel is the slow dimension of NDHWC data), which tcgen05 takes directly from
+// shared memory through the descriptor's major-ness bits -- nothing is transposed or im2col'ed:
+//   * A = a 4x16x8-voxel tile of dy, staged by TMA as 8-channel planes [voxel][8 co] (16 B per voxel).  A core matrix
+//     is 8 consecutive w-voxels x 16 B; the two K core matrices of one MMA are two consecutive h-rows (LBO = 128 B),
+//     the eight M groups are the eight channel planes (SBO = plane stride).
+//   * B = the 6x18x10 halo of x for the same tile, staged ONCE by TMA (out-of-bounds zero fill = the padding) as
+//     8-channel planes.  For a filter tap (kd, kh) the operand is just a different start address in that halo; the
+//     three kw taps are the three N groups (SBO = 16 B = the next voxel), the K core matrices are consecutive halo
+//     rows (LBO = 160 B).  Every input voxel is fetched once per CTA and reused by all 27 taps.
+// The 9 (or 18 for a 16-channel slice) accumulators D live in TMEM for the CTA's whole life (persistent over tiles);
+// they are read back once and added to dw with fp32 atomics (dw is zeroed by the host unless accumulating).
+//
+// Roles: warp 0 = TMA producer, warps 1-4 = MMA issuers (each owns every fourth accumulator, so concurrent issue
+// never targets the same TMEM columns) and, at the end, the read-back of their TMEM lane quadrant.
+#include "tc_ptx.cuh"
+
+namespace {
+
+constexpr int TD = 4, TH = 16, TW = 8;
+constexpr int HD = TD + 2, HH = TH + 2, HW = TW + 2;
+constexpr int HV = HD * HH * HW;
+constexpr int PLANE_BYTES = HV * 16;                    // 17280: one 8-channel plane of the x halo
+constexpr int DYPLANE_BYTES = TD * TH * TW * 16;        // 8192: one 8-channel plane of the dy tile
+constexpr int NTHREADS = 160;
+constexpr int MROWS = 64;                               // MMA M (output channels per CTA)
+
+struct WgParams {
+    int n, d, h, w, cin, cout;
+    int tiles_d, tiles_h, tiles_w, tiles_per_n;
+    int tiles;              // n * tiles_per_n
+    int kslices;            // cin / 16 (1 for cin == 8)
+    int dy_merged;          // dy map is the 4-D (w*c merged) one (cout == 8)
+    float* dw;
+};
+
+// kind::f16 instruction descriptor, D fp32, A/B bf16, BOTH operands MN-major, M = 64
+__host__ __device__ constexpr uint32_t make_idesc_mn(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) |
+           ((uint32_t)(MROWS >> 4) << 24);
+}
+
+template <bool CIN8, int NCOG, int NSTAGE>
+__global__ void __launch_bounds__(NTHREADS, 1) conv3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap xmap,
+                                                                     const __grid_constant__ CUtensorMap dymap, WgParams p) {
+    constexpr int XP = CIN8 ? 1 : 2;                          // x planes per stage
+    constexpr int NG = 9 * XP;                                // accumulators: (8-channel group, kd, kh)
+    constexpr int DY_BYTES = NCOG * DYPLANE_BYTES;
+    constexpr int STAGE_BYTES = DY_BYTES + XP * PLANE_BYTES;
+    constexpr int TAIL = (8 * DYPLANE_BYTES > STAGE_BYTES) ? (8 * DYPLANE_BYTES - STAGE_BYTES) : 0;   // see launch_wg
+    constexpr int TMEM_COLS = NG * 24 <= 256 ? 256 : 512;
+    static_assert(STAGE_BYTES % 128 == 0, "stage alignment");
+
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE_BYTES + TAIL);
+    uint64_t* empty_bar = full_bar + NSTAGE;
+    uint64_t* done_bar = empty_bar + NSTAGE;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    const int ks = blockIdx.y % p.kslices;                    // 16-channel slice of ci
+    const int mc = blockIdx.y / p.kslices;                    // 64-channel chunk of co
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 4); }
+        mbar_init(done_bar, 4);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    const bool has_work = (int)blockIdx.x < p.tiles;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+                const int n = tile / p.tiles_per_n;
+                int r = tile % p.tiles_per_n;
+                const int w0 = (r % p.tiles_w) * TW; r /= p.tiles_w;
+                const int h0 = (r % p.tiles_h) * TH; r /= p.tiles_h;
+                const int d0 = r * TD;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sdy = smem + stage * STAGE_BYTES;
+                uint8_t* sx = sdy + DY_BYTES;
+                mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+                if (p.dy_merged) {
+                    tma_load_4d(sdy, &dymap, &full_bar[stage], w0 * 8, h0, d0, n);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < NCOG; ++c)            // planes past Cout are zero-filled by TMA
+                        tma_load_5d(sdy + c * DYPLANE_BYTES, &dymap, &full_bar[stage], (mc * 8 + c) * 8, w0, h0, d0, n);
+                }
+                if (CIN8) {
+                    tma_load_4d(sx, &xmap, &full_bar[stage], (w0 - 1) * 8, h0 - 1, d0 - 1, n);
+                } else {
+                    tma_load_5d(sx, &xmap, &full_bar[stage], ks * 16, w0 - 1, h0 - 1, d0 - 1, n);
+                    tma_load_5d(sx + PLANE_BYTES, &xmap, &full_bar[stage], ks * 16 + 8, w0 - 1, h0 - 1, d0 - 1, n);
+                }
+                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== MMA issuers (warps 1-4), then TMEM read-back =====================
+        const int j = warp - 1;
+        constexpr uint32_t idesc = make_idesc_mn(24);
+        // this warp's accumulators g = j, j+4, ...: start-address offset (16-byte units) of tap (cg, kd, kh) in the
+        // halo and TMEM column, computed once
+        constexpr int MAXG = (NG + 3) / 4;
+        uint32_t goff[MAXG], gcol[MAXG];
+#pragma unroll
+        for (int i = 0; i < MAXG; ++i) {
+            const int g = j + 4 * i;
+            const int cg = g / 9, kd = (g % 9) / 3, kh = g % 3;
+            goff[i] = (uint32_t)(cg * PLANE_BYTES + ((kd * HH + kh) * HW) * 16) >> 4;
+            gcol[i] = tmem_base + g * 24;
+        }
+        uint32_t stage = 0, phase = 0;
+        bool first = true;
+        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+            int r = tile % p.tiles_per_n;
+            r /= p.tiles_w;
+            const int h0 = (r % p.tiles_h) * TH;
+            const int d0 = (r / p.tiles_h) * TD;
+            const int jd_end = min(TD, p.d - d0), h2_end = min(TH / 2, (p.h - h0 + 1) / 2);   // rows past the volume are zero
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sdy = smem_u32(smem + stage * STAGE_BYTES);
+            const uint64_t ad0 = make_desc(sdy, TW * 16u, DYPLANE_BYTES);
+            const uint64_t bd0 = make_desc(sdy + DY_BYTES, HW * 16u, 16u);
+            // the first K-step of the first tile overwrites the accumulators; every tile has >= 1 valid K-step
+            uint32_t acc = first ? 0u : 1u;
+#pragma unroll 1
+            for (int jd = 0; jd < jd_end; ++jd) {
+#pragma unroll 1
+                for (int h2 = 0; h2 < h2_end; ++h2) {        // 16 voxels = two h-rows of one d-plane
+                    const uint64_t ad = ad0 + (uint64_t)((jd * TH * TW + h2 * 2 * TW));           // 16-byte units
+                    const uint64_t bdk = bd0 + (uint64_t)((jd * HH + h2 * 2) * HW);
+#pragma unroll
+                    for (int i = 0; i < MAXG; ++i)
+                        if (j + 4 * i < NG) tc_mma_elect(gcol[i], ad, bdk + goff[i], idesc, acc);
+                    acc = 1u;
+                }
+            }
+            tc_commit_elect(&empty_bar[stage]);
+            first = false;
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        }
+        tc_commit_elect(done_bar);
+        if (has_work) {
+            mbar_wait(done_bar, 0);
+            tc_fence_after();
+            // M = 64 accumulator rows live in lanes (row & 15) + 32 * (row >> 4): warp quadrant q holds rows 16q..16q+15
+            const int q = warp & 3;
+            const int co = mc * MROWS + q * 16 + lane;
+            const bool valid = lane < 16 && co < p.cout;
+#pragma unroll 1
+            for (int g = 0; g < NG; ++g) {
+                const int cg = g / 9, t9 = g % 9;
+                uint32_t r[24];
+                uint32_t r0[8], r1[8], r2[8];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + g * 24;
+                tmem_ld8(taddr, r0);
+                tmem_ld8(taddr + 8, r1);
+                tmem_ld8(taddr + 16, r2);
+                tmem_ld_wait();
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { r[k] = r0[k]; r[8 + k] = r1[k]; r[16 + k] = r2[k]; }
+                if (valid) {
+                    float* base = p.dw + ((long long)co * p.cin + ks * 16 + cg * 8) * 27 + t9 * 3;
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+                        for (int c8 = 0; c8 < 8; ++c8)
+                            atomicAdd(base + c8 * 27 + kw, __uint_as_float(r[kw * 8 + c8]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+template <bool CIN8, int NCOG, int NSTAGE>
+int launch_wg(const CUtensorMap& xmap, const CUtensorMap& dymap, const WgParams& p, int slices, cudaStream_t st) {
+    constexpr int XP = CIN8 ? 1 : 2;
+    constexpr int STAGE_BYTES = NCOG * DYPLANE_BYTES + XP * PLANE_BYTES;
+    // The M = 64 operand always spans eight dy planes; with fewer real planes the MMA reads whatever follows
+    // (rows of D that are never read back).  TAIL keeps that over-read of the LAST stage inside the allocation.
+    constexpr int TAIL = (8 * DYPLANE_BYTES > STAGE_BYTES) ? (8 * DYPLANE_BYTES - STAGE_BYTES) : 0;
+    constexpr int SMEM = NSTAGE * STAGE_BYTES + TAIL + 128 + 8 * (2 * NSTAGE + 1) + 16 + 64;
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
+    auto kern = conv3_wgrad_tc_kernel<CIN8, NCOG, NSTAGE>;
+    static bool configured = false;
+    if (!configured) {
+        VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM), "conv3_wgrad_tc smem attribute");
+        configured = true;
+    }
+    int parts = vs_sm_count() / slices;
+    if (parts < 1) parts = 1;
+    if (parts > p.tiles) parts = p.tiles;
+    dim3 grid((unsigned)parts, (unsigned)slices);
+    kern<<<grid, NTHREADS, SMEM, st>>>(xmap, dymap, p);
+    VS_CHECK_LAUNCH("conv3_wgrad_tc_kernel");
+    return VS_OK;
+}
+
+template <bool CIN8>
+int dispatch_wg(int ncog, const CUtensorMap& xmap, const CUtensorMap& dymap, const WgParams& p, int slices, cudaStream_t st) {
+    if (ncog <= 1) return launch_wg<CIN8, 1, 4>(xmap, dymap, p, slices, st);
+    if (ncog <= 2) return launch_wg<CIN8, 2, 4>(xmap, dymap, p, slices, st);
+    if (ncog <= 4) return launch_wg<CIN8, 4, 3>(xmap, dymap, p, slices, st);
+    return launch_wg<CIN8, 8, 2>(xmap, dymap, p, slices, st);
+}
+
+}  // namespace
+
+extern "C" int vs_conv3_wgrad_tc_eligible(int cin, int cout) {
+    return (cin == 8 || (cin % 16 == 0 && cin >= 16)) && cout % 8 == 0 && cout >= 8;
+}
+
+// dw[Cout][Cin][27] += sum_v dy[v,co] * x[v+tap,ci]; x, dy bf16 NDHWC; dw fp32 (already zeroed or holding the value to
+// accumulate onto).
+extern "C" int vs_conv3x3x3_wgrad_tc(const void* x, const void* dy, float* dw, int n, int d, int h, int w, int cin, int cout,
+                                     void* stream) {
+    VS_REQUIRE(x && dy && dw, VS_ERR_SHAPE, "conv3_wgrad_tc: null pointer");
+    VS_REQUIRE(vs_conv3_wgrad_tc_eligible(cin, cout), VS_ERR_UNSUPPORTED, "conv3_wgrad_tc: unsupported channels Cin=%d Cout=%d", cin, cout);
+    VS_REQUIRE(vs_aligned16(x) && vs_aligned16(dy), VS_ERR_ALIGN, "conv3_wgrad_tc: pointers must be 16B aligned");
+    EncodeTiledFn encode = get_encode_fn();
+    VS_REQUIRE(encode != nullptr, VS_ERR_CUDA, "conv3_wgrad_tc: cuTensorMapEncodeTiled unavailable");
+    cudaStream_t st = (cudaStream_t)stream;
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUtensorMap xmap, dymap;
+    CUresult cr;
+    if (cin == 8) {
+        const cuuint64_t gdim[4] = {(cuuint64_t)w * 8, (cuuint64_t)h, (cuuint64_t)d, (cuuint64_t)n};
+        const cuuint64_t gstr[3] = {(cuuint64_t)w * 16, (cuuint64_t)h * w * 16, (cuuint64_t)d * h * w * 16};
+        const cuuint32_t box[4] = {HW * 8, HH, HD, 1};
+        cr = encode(&xmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        const cuuint64_t gdim[5] = {(cuuint64_t)cin, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)d, (cuuint64_t)n};
+        const cuuint64_t gstr[4] = {(cuuint64_t)cin * 2, (cuuint64_t)w * cin * 2, (cuuint64_t)h * w * cin * 2,
+                                    (cuuint64_t)d * h * w * cin * 2};
+        const cuuint32_t box[5] = {8, HW, HH, HD, 1};
+        cr = encode(&xmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    VS_REQUIRE(cr == CUDA_SUCCESS, VS_ERR_CUDA, "conv3_wgrad_tc: cuTensorMapEncodeTiled(x) failed (%d)", (int)cr);
+    if (cout == 8) {
+        const cuuint64_t gdim[4] = {(cuuint64_t)w * 8, (cuuint64_t)h, (cuuint64_t)d, (cuuint64_t)n};
+        const cuuint64_t gstr[3] = {(cuuint64_t)w * 16, (cuuint64_t)h * w * 16, (cuuint64_t)d * h * w * 16};
+        const cuuint32_t box[4] = {TW * 8, TH, TD, 1};
+        cr = encode(&dymap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dy), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        const cuuint64_t gdim[5] = {(cuuint64_t)cout, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)d, (cuuint64_t)n};
+        const cuuint64_t gstr[4] = {(cuuint64_t)cout * 2, (cuuint64_t)w * cout * 2, (cuuint64_t)h * w * cout * 2,
+                                    (cuuint64_t)d * h * w * cout * 2};
+        const cuuint32_t box[5] = {8, TW, TH, TD, 1};
+        cr = encode(&dymap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(dy), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    VS_REQUIRE(cr == CUDA_SUCCESS, VS_ERR_CUDA, "conv3_wgrad_tc: cuTensorMapEncodeTiled(dy) failed (%d)", (int)cr);
+
+    WgParams p;
+    p.n = n; p.d = d; p.h = h; p.w = w; p.cin = cin; p.cout = cout;
+    p.tiles_d = (d + TD - 1) / TD; p.tiles_h = (h + TH - 1) / TH; p.tiles_w = (w + TW - 1) / TW;
+    p.tiles_per_n = p.tiles_d * p.tiles_h * p.tiles_w;
+    const long long tiles = (long long)n * p.tiles_per_n;
+    VS_REQUIRE(tiles < 2147483647LL, VS_ERR_SHAPE, "conv3_wgrad_tc: too many tiles");
+    p.tiles = (int)tiles;
+    p.kslices = cin == 8 ? 1 : cin / 16;
+    p.dy_merged = cout == 8;
+    p.dw = dw;
+    const int mchunks = (cout + MROWS - 1) / MROWS;
+    const int slices = p.kslices * mchunks;
+    const int ncog = cout >= MROWS ? 8 : cout / 8;            // planes of the (possibly only) 64-channel chunk
+    if (cin == 8) return dispatch_wg<true>(ncog, xmap, dymap, p, slices, st);
+    return dispatch_wg<false>(ncog, xmap, dymap, p, slices, st);
+}
