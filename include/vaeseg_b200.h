@@ -110,6 +110,14 @@ int vs_softmax2_fwd(const float* logits, float* probs, int n, long long s, void*
 int vs_softmax2_bwd(int dtype, const float* dprobs, const float* probs, void* dlogits,
                     int n, long long s, void* stream);
 
+/* same gradient written as an 8-channel bf16 NDHWC tensor [N][S][8] (channels 2..7 zero) so the head's wgrad / dgrad
+ * take the tensor-core kernels; db[2] += sum_v dlogits (the out_block bias gradient) when non-NULL.       */
+int vs_softmax2_bwd_pad8(const float* dprobs, const float* probs, void* dlogits8, float* db,
+                         int n, long long s, void* stream);
+/* planar fp32 [N][C][S], C <= 8 -> NDHWC bf16 [N][S][8] (zero channels C..7): the in-block input as a
+ * tensor-core wgrad operand (joint_model.py:210,355 in_block Conv3d(n_channels, 8))                          */
+int vs_planar_to_ndhwc8(const float* x, void* out, int n, int c, long long s, void* stream);
+
 /* ---- Linear layers + reparameterisation of the VAE (joint_model.py:216-218,241-250) --- */
 /* x: NDHWC `dtype` [B][S3][C] read in the reference's NCDHW flatten order i = c*S3 + v.
  * mean = Wm x + bm; std = relu(Ws x + bs); lat = mean + z*std*scale (use_z) or mean.       */

@@ -36,6 +36,8 @@ _SIGNATURES = {
     "vs_add_inplace": [_I, _P, _P, _L, _P],
     "vs_softmax2_fwd": [_P, _P, _I, _L, _P],
     "vs_softmax2_bwd": [_I, _P, _P, _P, _I, _L, _P],
+    "vs_softmax2_bwd_pad8": [_P, _P, _P, _P, _I, _L, _P],
+    "vs_planar_to_ndhwc8": [_P, _P, _I, _I, _L, _P],
     "vs_fc_encode_fwd": [_I, _P, _P, _P, _P, _P, _P, _F, _I, _P, _P, _P, _I, _I, _I, _I, _P],
     "vs_fc_decode_fwd": [_I, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "vs_fc_decode_bwd": [_I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],

@@ -154,6 +154,50 @@ __global__ void __launch_bounds__(NT) softmax2_bwd_kernel(const float* __restric
     }
 }
 
+// 2-class softmax backward writing the logit gradient as an 8-channel bf16 NDHWC tensor (channels 2..7 zero) so that
+// the head's wgrad / dgrad run on the tensor-core kernels (which take channel counts in multiples of 8), plus the
+// head's bias gradient db[c] += sum_v dlogit[v][c] (fp64 block partials, one atomic pair per CTA).
+__global__ void __launch_bounds__(NT) softmax2_bwd_pad8_kernel(const float* __restrict__ dprobs, const float* __restrict__ probs,
+                                                               bf16* __restrict__ dlogits8, float* __restrict__ db, long long s) {
+    __shared__ double red[NT / 32][2];
+    const int n = blockIdx.y;
+    const float* g0 = dprobs + (long long)n * 2 * s; const float* g1 = g0 + s;
+    const float* p0 = probs + (long long)n * 2 * s; const float* p1 = p0 + s;
+    uint4* dl = reinterpret_cast<uint4*>(dlogits8) + (long long)n * s;
+    double s0 = 0.0, s1 = 0.0;
+    for (long long v = (long long)blockIdx.x * NT + threadIdx.x; v < s; v += (long long)gridDim.x * NT) {
+        const float a = p0[v], b = p1[v], ga = g0[v], gb = g1[v];
+        const float dot = ga * a + gb * b;
+        const __nv_bfloat162 h = __floats2bfloat162_rn(a * (ga - dot), b * (gb - dot));
+        dl[v] = make_uint4(*reinterpret_cast<const uint32_t*>(&h), 0u, 0u, 0u);
+        const float2 r = __bfloat1622float2(h);           // the bias gradient sums exactly what wgrad / dgrad consume
+        s0 += (double)r.x; s1 += (double)r.y;
+    }
+    if (db != nullptr) {
+        s0 = warp_sum(s0); s1 = warp_sum(s1);
+        if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = s0; red[threadIdx.x >> 5][1] = s1; }
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            double t = 0.0;
+            for (int k = 0; k < NT / 32; ++k) t += red[k][threadIdx.x];
+            atomicAdd(db + threadIdx.x, (float)t);
+        }
+    }
+}
+
+// planar fp32 [N][C][S] (C < 8) -> NDHWC bf16 [N][S][8] with zero channels C..7: the in-block input as a
+// tensor-core wgrad operand.
+__global__ void __launch_bounds__(NT) planar_to_ndhwc8_kernel(const float* __restrict__ x, bf16* __restrict__ out, int c, long long s) {
+    const int n = blockIdx.y;
+    const float* xp = x + (long long)n * c * s;
+    bf16* op = out + (long long)n * s * 8;
+    for (long long v = (long long)blockIdx.x * NT + threadIdx.x; v < s; v += (long long)gridDim.x * NT) {
+        float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int k = 0; k < c; ++k) f[k] = xp[(long long)k * s + v];
+        Store<bf16>::st8(op + v * 8, f);
+    }
+}
+
 int stream_grid(long long work_items) {
     long long blocks = (work_items + NT - 1) / NT;
     long long cap = (long long)vs_sm_count() * 8;
@@ -230,5 +274,24 @@ extern "C" int vs_softmax2_bwd(int dtype, const float* dprobs, const float* prob
     dim3 grid(stream_grid(s / 4 + 1), n);
     VS_DISPATCH_DTYPE(dtype, T, { softmax2_bwd_kernel<T><<<grid, NT, 0, (cudaStream_t)stream>>>(dprobs, probs, (T*)dlogits, s); });
     VS_CHECK_LAUNCH("softmax2_bwd_kernel");
+    return VS_OK;
+}
+
+extern "C" int vs_softmax2_bwd_pad8(const float* dprobs, const float* probs, void* dlogits8, float* db, int n, long long s,
+                                    void* stream) {
+    VS_REQUIRE(dprobs && probs && dlogits8 && n > 0 && s > 0, VS_ERR_SHAPE, "softmax2_bwd_pad8: bad arguments");
+    VS_REQUIRE(vs_aligned16(dlogits8), VS_ERR_ALIGN, "softmax2_bwd_pad8: output must be 16B aligned");
+    dim3 grid(stream_grid(s / 4 + 1), n);
+    softmax2_bwd_pad8_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(dprobs, probs, (bf16*)dlogits8, db, s);
+    VS_CHECK_LAUNCH("softmax2_bwd_pad8_kernel");
+    return VS_OK;
+}
+
+extern "C" int vs_planar_to_ndhwc8(const float* x, void* out, int n, int c, long long s, void* stream) {
+    VS_REQUIRE(x && out && n > 0 && s > 0 && c > 0 && c <= 8, VS_ERR_SHAPE, "planar_to_ndhwc8: bad arguments (C=%d)", c);
+    VS_REQUIRE(vs_aligned16(out), VS_ERR_ALIGN, "planar_to_ndhwc8: output must be 16B aligned");
+    dim3 grid(stream_grid(s / 2 + 1), n);
+    planar_to_ndhwc8_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(x, (bf16*)out, c, s);
+    VS_CHECK_LAUNCH("planar_to_ndhwc8_kernel");
     return VS_OK;
 }

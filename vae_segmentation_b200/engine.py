@@ -77,6 +77,27 @@ class PackCache(object):
         return packs
 
 
+    def head_dgrad_tc(self, w):
+        """bf16 tensor-core dgrad pack of the head weight [n_class,Cin,3,3,3] zero-padded to 8 output channels (the
+        head's logit gradient is produced as an 8-channel tensor, ops.softmax2_bwd_pad8), or None."""
+        if not USE_TENSOR_CORES:
+            return None
+        key = (w.data_ptr(), w._version, self.epoch, "head8")
+        hit = self._store.get(("head8", w.data_ptr()))
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        wdet = w.detach()
+        w8 = torch.zeros(8, wdet.shape[1], 3, 3, 3, device=wdet.device, dtype=torch.float32)
+        w8[:wdet.shape[0]].copy_(wdet)
+        pack = ops.pack_conv3_weight_tc(w8, dgrad=True)
+        self._store[("head8", w.data_ptr())] = (key, pack)
+        return pack
+
+
+def _tc_channels(c):
+    return c == 8 or (c >= 16 and c % 16 == 0)
+
+
 def _grad_target(p_ref, need):
     """Where a parameter gradient goes: into an existing .grad (accumulate in place, return
     None to autograd) or into a fresh tensor returned to autograd."""
@@ -141,7 +162,10 @@ def program_forward(layers, tensors, x, dims, dtype, cache, record=True):
             d, h, w = d * 2, h * 2, w * 2
             cur = out
         elif L.kind == HEAD:
-            wf, wd, _, wdtc = cache.conv3(tensors[L.wi], tc=(dtype == torch.bfloat16))
+            wf, wd, _, _ = cache.conv3(tensors[L.wi], tc=(dtype == torch.bfloat16))
+            wdtc = None
+            if record and dtype == torch.bfloat16 and L.cout <= 8 and _tc_channels(L.cin) and not L.in_planar:
+                wdtc = cache.head_dgrad_tc(tensors[L.wi])
             logits, _ = ops.conv3_fprop(cur, wf, tensors[L.bi].detach(), (n, d, h, w), L.cin, L.cout, torch.float32,
                                         in_planar=L.in_planar, want_stats=False)
             probs = ops.softmax2_fwd(logits, (n, d, h, w))
@@ -172,7 +196,17 @@ def program_backward(tape, g, dtype, need, grads, param_refs, need_input_grad):
             dy = _sim(ops.inorm_relu_bwd(g, y, stats), "dy")
             if need[L.wi]:
                 tgt, acc = _grad_target(param_refs[L.wi], True)
-                dw, _ = ops.conv3_wgrad(x_in, dy, dims, L.cin, L.cout, dw=tgt, in_planar=L.in_planar, accumulate=acc)
+                if L.in_planar and dtype == torch.bfloat16 and USE_TENSOR_CORES and L.cin < 8 and L.cout % 8 == 0:
+                    # in-block (Cin 1 or 2, planar fp32 input): pad the input to 8 bf16 channels and take the
+                    # tensor-core wgrad; the padded input channels give zero rows that are dropped
+                    dw8, _ = ops.conv3_wgrad(ops.planar_to_ndhwc8(x_in), dy, dims, 8, L.cout)
+                    if acc:
+                        tgt.add_(dw8[:, :L.cin])
+                        dw = tgt
+                    else:
+                        dw = dw8[:, :L.cin].contiguous()
+                else:
+                    dw, _ = ops.conv3_wgrad(x_in, dy, dims, L.cin, L.cout, dw=tgt, in_planar=L.in_planar, accumulate=acc)
                 grads[L.wi] = None if acc else dw
             if need[L.bi]:
                 # exactly zero: the bias cancels in InstanceNorm
@@ -196,6 +230,25 @@ def program_backward(tape, g, dtype, need, grads, param_refs, need_input_grad):
             g = _sim(ops.k2s2_gather(g, wt, None, dims, L.cin, L.cout), "g") if want_dx else None
         elif L.kind == HEAD:
             probs = y
+            if wd[1] is not None:
+                # bf16 mode: 8-channel padded logit gradient -> tensor-core wgrad / dgrad; bias gradient fused
+                tw = tb = None
+                acc = False
+                if need[L.wi] or need[L.bi]:
+                    tw, tb, acc = _pair_targets(param_refs, need, L.wi, L.bi, (L.cout, L.cin, 3, 3, 3), (L.cout,), g.device)
+                    if tb is not None and not acc:
+                        tb.zero_()
+                dl8 = ops.softmax2_bwd_pad8(g, probs, dims, db=tb)
+                if need[L.wi]:
+                    dw8, _ = ops.conv3_wgrad(x_in, dl8, dims, L.cin, 8)
+                    if acc:
+                        tw.add_(dw8[:L.cout])
+                    else:
+                        tw.copy_(dw8[:L.cout])
+                if need[L.wi] or need[L.bi]:
+                    _hand_back(grads, need, L.wi, L.bi, tw, tb, acc)
+                g = ops.conv3_dgrad(dl8, None, dims, L.cin, 8, dtype, wdtc=wd[1]) if want_dx else None
+                continue
             dlogits = _sim(ops.softmax2_bwd(g, probs, dims, dtype), "dy")
             if need[L.wi] or need[L.bi]:
                 tw, tb, acc = _pair_targets(param_refs, need, L.wi, L.bi, (L.cout, L.cin, 3, 3, 3), (L.cout,), g.device)

@@ -186,6 +186,23 @@ def softmax2_bwd(dprobs, probs, dims, out_dtype):
     return dlogits
 
 
+def softmax2_bwd_pad8(dprobs, probs, dims, db=None):
+    """Logit gradient as bf16 NDHWC [N,D,H,W,8] (channels 2..7 zero); db[2] (+)= the bias gradient."""
+    n, d, h, w = dims
+    dlogits8 = torch.empty(n, d, h, w, 8, device=probs.device, dtype=torch.bfloat16)
+    _cabi.call("vs_softmax2_bwd_pad8", _p(_f32(dprobs, "dprobs")), _p(_f32(probs, "probs")), _p(dlogits8),
+               _p(_f32(db, "db")), n, d * h * w, _stream())
+    return dlogits8
+
+
+def planar_to_ndhwc8(x):
+    """[N,C,D,H,W] fp32 (C <= 8) -> [N,D,H,W,8] bf16, zero padded channels."""
+    n, c = x.shape[0], x.shape[1]
+    out = torch.empty(n, x.shape[2], x.shape[3], x.shape[4], 8, device=x.device, dtype=torch.bfloat16)
+    _cabi.call("vs_planar_to_ndhwc8", _p(_f32(x, "x")), _p(out), n, c, x.numel() // (n * c), _stream())
+    return out
+
+
 # ---- VAE linear layers -----------------------------------------------------------------
 def fc_encode_fwd(x, wm, bm, ws, bs, z, scale, use_z, batch, s3, c, dim):
     dev = x.device
