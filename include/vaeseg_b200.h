@@ -46,6 +46,20 @@ int vs_pack_conv3_weight(const float* w, float* wf, float* wd, int cin, int cout
 size_t vs_conv3_tc_pack_bytes(int cin, int cout, int dgrad);
 int vs_pack_conv3_weight_tc(const float* w, void* out, int cin, int cout, int dgrad, void* stream);
 
+/* All derived packs of many layers in one launch.  jobs_dev: DEVICE array of njobs vs_pack_job; NULL outputs are
+ * skipped.  cout_pad > cout zero-pads the output channels of the dgrad tensor-core pack (the 2-class head is
+ * run as an 8-channel layer in backward); otherwise cout_pad == cout.  *_elems = vs_conv3_tc_pack_bytes()/2.   */
+typedef struct {
+    const void* w;        /* fp32 [Cout][Cin][27] master weight                         */
+    void* wf;             /* fp32 [27][Cin][Cout] or NULL                               */
+    void* wd;             /* fp32 [27 flipped][Cout][Cin] or NULL                       */
+    void* tcf;            /* bf16 tensor-core fprop pack or NULL                        */
+    void* tcd;            /* bf16 tensor-core dgrad pack (of [cout_pad][Cin][27]) or NULL */
+    long long tcf_elems, tcd_elems;
+    int cin, cout, cout_pad, reserved;
+} vs_pack_job;
+int vs_pack_conv3_batched(const void* jobs_dev, int njobs, void* stream);
+
 /* ---- 3x3x3 convolution, padding 1 (Conv3d at joint_model.py:40-46,106,224,366) ------- */
 /* x: NDHWC `in_dtype` (or planar fp32 when in_planar=1, used by the in_blocks whose input is
  * the module's NCDHW fp32 tensor); wpk: fp32 [27][Cin][Cout]; wtc: bf16 tensor-core pack or NULL

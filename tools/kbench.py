@@ -161,11 +161,15 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--patch", type=int, default=96)
     ap.add_argument("--batch", type=int, default=2)
+    ap.add_argument("--k2-ksplit-max", type=int, default=None, help="override the k-split threshold of the k2s2 kernels")
     ap.add_argument("--only", default=None, help="conv set: 'size,cin,cout' of the single shape to run")
     a = ap.parse_args()
     global ONLY
     if a.only:
         ONLY = tuple(int(v) for v in a.only.split(","))
+    if a.k2_ksplit_max is not None:
+        from vae_segmentation_b200 import _cabi
+        _cabi.lib().vs_debug_set_k2_ksplit_max(a.k2_ksplit_max)
     torch.manual_seed(0)
     fns = {"conv": bench_conv, "wgrad": bench_wgrad, "k2s2": bench_k2s2, "norm": bench_norm}
     for k in a.set.split(","):

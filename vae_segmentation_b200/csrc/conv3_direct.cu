@@ -53,7 +53,9 @@ __device__ __forceinline__ void load_halo(float4 (*xs)[HV], const TI* __restrict
 }
 
 // y = conv3(x, wpk) (+bias), optional per-(n,c) sum / sum-of-squares of the fp32 accumulators.
-template <typename TI, typename TO, int COB, bool IN_PLANAR, bool OUT_PLANAR>
+// NCI > 0: the layer has exactly NCI (1 or 2) input channels (the in-blocks): only those channels are multiplied
+// instead of a zero-padded channel quad.
+template <typename TI, typename TO, int COB, bool IN_PLANAR, bool OUT_PLANAR, int NCI = 0>
 __global__ void __launch_bounds__(NT) conv3_direct_kernel(const TI* __restrict__ x, const float* __restrict__ wpk,
                                                           const float* __restrict__ bias, TO* __restrict__ y,
                                                           double* __restrict__ stats,
@@ -87,7 +89,7 @@ __global__ void __launch_bounds__(NT) conv3_direct_kernel(const TI* __restrict__
             ws[tap][cc][j] = make_float4(wv[0], wv[1], wv[2], wv[3]);
         }
         __syncthreads();
-        const int nplane = cib > 4 ? 2 : 1;
+        const int nplane = NCI > 0 ? 1 : (cib > 4 ? 2 : 1);
 #pragma unroll 1
         for (int kd = 0; kd < 3; ++kd) {
 #pragma unroll 1
@@ -102,7 +104,7 @@ __global__ void __launch_bounds__(NT) conv3_direct_kernel(const TI* __restrict__
                         const float a0v[4] = {a0.x, a0.y, a0.z, a0.w};
                         const float a1v[4] = {a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-                        for (int cc = 0; cc < 4; ++cc) {
+                        for (int cc = 0; cc < (NCI > 0 ? NCI : 4); ++cc) {
 #pragma unroll
                             for (int j = 0; j < COB / 4; ++j) {
                                 const float4 wv = ws[tap][pl * 4 + cc][j];
@@ -352,6 +354,10 @@ int launch_conv3(const void* x, const float* wpk, const float* bias, void* y, do
     dim3 grid((unsigned)tiles, (p.cout + cob - 1) / cob);
     if (cob == 16)
         conv3_direct_kernel<TI, TO, 16, IN_PLANAR, OUT_PLANAR><<<grid, NT, 0, st>>>((const TI*)x, wpk, bias, (TO*)y, stats, shift, p);
+    else if (cob == 8 && p.cin == 1)
+        conv3_direct_kernel<TI, TO, 8, IN_PLANAR, OUT_PLANAR, 1><<<grid, NT, 0, st>>>((const TI*)x, wpk, bias, (TO*)y, stats, shift, p);
+    else if (cob == 8 && p.cin == 2)
+        conv3_direct_kernel<TI, TO, 8, IN_PLANAR, OUT_PLANAR, 2><<<grid, NT, 0, st>>>((const TI*)x, wpk, bias, (TO*)y, stats, shift, p);
     else if (cob == 8)
         conv3_direct_kernel<TI, TO, 8, IN_PLANAR, OUT_PLANAR><<<grid, NT, 0, st>>>((const TI*)x, wpk, bias, (TO*)y, stats, shift, p);
     else

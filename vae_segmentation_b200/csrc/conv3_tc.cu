@@ -344,41 +344,48 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
 //   cin8   : [chunk][1][kdkh 9 x pair 2][kc 2][NC/8][8 rows][8 ch]  (kc0 = tap kw=2*pair, kc1 = kw=2*pair+1 or 0)
 // dgrad = same contraction with (ci,co) swapped and taps flipped.
 // ---------------------------------------------------------------------------------------------
-__global__ void pack_tc_kernel(const float* __restrict__ w, bf16* __restrict__ out, int cin_l, int cout_l, int dgrad,
-                               int nc, int cin8, long long total) {
+// One element of the bf16 UMMA B-operand pack.  cout_real < cout_l zero-pads the output channels (the head's
+// 2 -> 8 channel dgrad pack).
+__device__ __forceinline__ float pack_tc_elem(const float* __restrict__ w, long long i, int cin_l, int cout_l, int cout_real,
+                                              int dgrad, int nc, int cin8) {
     // GEMM-side channel counts
     const int gin = dgrad ? cout_l : cin_l, gout = dgrad ? cin_l : cout_l;
     const int kslices = cin8 ? 1 : gin / 16;
     const int nmma = cin8 ? 18 : 27;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        long long r = i;
-        const int ch8 = (int)(r % 8); r /= 8;
-        const int r8 = (int)(r % 8); r /= 8;
-        const int ng = (int)(r % (nc / 8)); r /= (nc / 8);
-        const int kc = (int)(r % 2); r /= 2;
-        const int m = (int)(r % nmma); r /= nmma;
-        const int ks = (int)(r % kslices); r /= kslices;
-        const int chunk = (int)r;
-        const int go = chunk * nc + ng * 8 + r8;               // GEMM output channel
-        int gi, tap;
-        if (cin8) {
-            const int kdkh = m / 2, pr = m % 2, kw = pr * 2 + kc;
-            gi = ch8;
-            tap = kw <= 2 ? kdkh * 3 + kw : -1;
-        } else {
-            gi = ks * 16 + kc * 8 + ch8;
-            tap = m;
-        }
-        float v = 0.f;
-        if (go < gout && gi < gin && tap >= 0) {
-            if (dgrad) v = w[((long long)gi * cin_l + go) * 27 + (26 - tap)];      // w[co=gi][ci=go][flipped tap]
-            else v = w[((long long)go * cin_l + gi) * 27 + tap];
-        }
-        out[i] = __float2bfloat16_rn(v);
+    long long r = i;
+    const int ch8 = (int)(r % 8); r /= 8;
+    const int r8 = (int)(r % 8); r /= 8;
+    const int ng = (int)(r % (nc / 8)); r /= (nc / 8);
+    const int kc = (int)(r % 2); r /= 2;
+    const int m = (int)(r % nmma); r /= nmma;
+    const int ks = (int)(r % kslices); r /= kslices;
+    const int chunk = (int)r;
+    const int go = chunk * nc + ng * 8 + r8;               // GEMM output channel
+    int gi, tap;
+    if (cin8) {
+        const int kdkh = m / 2, pr = m % 2, kw = pr * 2 + kc;
+        gi = ch8;
+        tap = kw <= 2 ? kdkh * 3 + kw : -1;
+    } else {
+        gi = ks * 16 + kc * 8 + ch8;
+        tap = m;
     }
+    float v = 0.f;
+    if (go < gout && gi < gin && tap >= 0) {
+        if (dgrad) { if (gi < cout_real) v = w[((long long)gi * cin_l + go) * 27 + (26 - tap)]; }   // w[co=gi][ci=go][flipped tap]
+        else if (go < cout_real) v = w[((long long)go * cin_l + gi) * 27 + tap];
+    }
+    return v;
 }
 
-int nc_for(int gout) { return gout >= 64 ? 64 : (gout >= 32 ? 32 : 16); }
+__global__ void pack_tc_kernel(const float* __restrict__ w, bf16* __restrict__ out, int cin_l, int cout_l, int dgrad,
+                               int nc, int cin8, long long total) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+        out[i] = __float2bfloat16_rn(pack_tc_elem(w, i, cin_l, cout_l, cout_l, dgrad, nc, cin8));
+}
+
+__host__ __device__ constexpr int nc_for_dev(int gout) { return gout >= 64 ? 64 : (gout >= 32 ? 32 : 16); }
+int nc_for(int gout) { return nc_for_dev(gout); }
 
 template <int NC, bool CIN8, int NSTAGE>
 int launch_tc(const CUtensorMap& map, const TcParams& p, cudaStream_t st) {
@@ -419,6 +426,37 @@ extern "C" int vs_pack_conv3_weight_tc(const float* w, void* out, int cin, int c
         w, (bf16*)out, cin, cout, dgrad, nc_for(gout), gin == 8, total);
     VS_CHECK_LAUNCH("pack_tc_kernel");
     return VS_OK;
+}
+
+// All derived weight packs of a network in ONE launch (the fused optimiser changes every weight every step):
+// blockIdx.y = job; see vs_pack_job in the header.
+__global__ void __launch_bounds__(256) pack_batched_kernel(const vs_pack_job* __restrict__ jobs) {
+    const vs_pack_job j = jobs[blockIdx.y];
+    const float* w = (const float*)j.w;
+    const int cin = j.cin, cout = j.cout, cpad = j.cout_pad;
+    const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j.wf != nullptr || j.wd != nullptr) {
+        float* wf = (float*)j.wf; float* wd = (float*)j.wd;
+        const long long total = (long long)cout * cin * 27;
+        for (long long i = t0; i < total; i += stride) {
+            const int tap = (int)(i % 27), ci = (int)((i / 27) % cin), co = (int)(i / (27 * cin));
+            const float v = w[i];
+            if (wf != nullptr) wf[((long long)tap * cin + ci) * cout + co] = v;
+            if (wd != nullptr) wd[((long long)(26 - tap) * cout + co) * cin + ci] = v;
+        }
+    }
+    if (j.tcf != nullptr) {
+        bf16* o = (bf16*)j.tcf;
+        const int nc = nc_for_dev(cout);
+        for (long long i = t0; i < j.tcf_elems; i += stride)
+            o[i] = __float2bfloat16_rn(pack_tc_elem(w, i, cin, cout, cout, 0, nc, cin == 8));
+    }
+    if (j.tcd != nullptr) {
+        bf16* o = (bf16*)j.tcd;
+        const int nc = nc_for_dev(cin);
+        for (long long i = t0; i < j.tcd_elems; i += stride)
+            o[i] = __float2bfloat16_rn(pack_tc_elem(w, i, cin, cpad, cout, 1, nc, cpad == 8));
+    }
 }
 
 // y[n,d,h,w,gout] = conv3(x[n,d,h,w,gin], wtc) on the tensor cores; bf16 NDHWC in and out.
@@ -480,4 +518,12 @@ extern "C" int vs_conv3x3x3_tc(const void* x, const void* wtc, void* y, double* 
     if (nc == 16) return launch_tc<16, false, 4>(map, p, st);
     if (nc == 32) return launch_tc<32, false, 3>(map, p, st);
     return launch_tc<64, false, 2>(map, p, st);
+}
+
+extern "C" int vs_pack_conv3_batched(const void* jobs_dev, int njobs, void* stream) {
+    VS_REQUIRE(jobs_dev && njobs > 0, VS_ERR_SHAPE, "pack_conv3_batched: bad arguments");
+    dim3 grid(32, (unsigned)njobs);
+    pack_batched_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const vs_pack_job*)jobs_dev);
+    VS_CHECK_LAUNCH("pack_batched_kernel");
+    return VS_OK;
 }

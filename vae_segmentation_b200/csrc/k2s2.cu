@@ -133,50 +133,153 @@ __global__ void __launch_bounds__(256) k2s2_scatter_kernel(const T* __restrict__
     }
 }
 
-// dwt[a][b][k] += sum_o coarse[o,a] * fine[2o+k,b]; CTA = 8 a x BCH b pairs, persistent over
-// blocks of 32 coarse voxels staged in shared memory.
-template <typename T, int BCH>
-__global__ void __launch_bounds__(8 * BCH) k2s2_wgrad_kernel(const T* __restrict__ coarse, const T* __restrict__ fine,
-                                                             float* __restrict__ dwt, K2Dims p, long long total) {
-    constexpr int NTH = 8 * BCH;
-    constexpr int VB = 32;
-    __shared__ float cs[VB][8];
-    __shared__ float fs[VB][8][BCH];
-    const int t = threadIdx.x;
-    const int a_l = t / BCH, b_l = t % BCH;
-    const int a0 = blockIdx.y * 8, b0 = blockIdx.z * BCH;
-    float acc[8];
+// ---- k-split variants: thread = (coarse voxel, filter position k) --------------------------------------------
+// The per-voxel kernels above serialise the whole 8*B (or A) reduction in one thread and re-stage the weights every
+// 8 channels; on the deep levels (<= 24^3, C >= 32) that is a ~20-70 us latency chain for microseconds of work.  Here
+// the CTA stages ALL weights of its 8-channel output chunk once ([k][in][8 out] fp32, +4 words of row padding so the
+// eight k-lanes of a voxel read conflict-free) and eight lanes share a voxel.
+template <typename T>
+__global__ void __launch_bounds__(128) k2s2_gather_ksplit_kernel(const T* __restrict__ fine, const float* __restrict__ wt,
+                                                                 const float* __restrict__ bias, T* __restrict__ coarse,
+                                                                 K2Dims p, long long total) {
+    extern __shared__ float wsm[];                     // [8 k][B][8 a] (+4 pad per k)
+    const int t = threadIdx.x, k = t & 7;
+    const int a0 = blockIdx.y * 8;
+    const int kstride = p.b * 8 + 4;
+    for (int i = t; i < 8 * p.b * 8; i += 128) {       // global order [aa][b][k] (contiguous per aa)
+        const int kk = i & 7, bb = (i >> 3) % p.b, aa = i / (8 * p.b);
+        wsm[kk * kstride + bb * 8 + aa] = wt[((long long)(a0 + aa) * p.b + bb) * 8 + kk];
+    }
+    __syncthreads();
+    const long long o = (long long)blockIdx.x * 16 + (t >> 3);
+    const bool valid = o < total;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (valid) {
+        int n, od, oh, ow;
+        decode_coarse(o, p, n, od, oh, ow);
+        const T* px = fine + fine_index(p, n, od, oh, ow, k) * p.b;
+        const float* wk = wsm + k * kstride;
+        for (int b0 = 0; b0 < p.b; b0 += 8) {
+            float xv[8];
+            Store<T>::ld8(px + b0, xv);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-    for (long long base = (long long)blockIdx.x * VB; base < total; base += (long long)gridDim.x * VB) {
-        __syncthreads();
-        for (int i = t; i < VB * 8; i += NTH) {
-            int aa = i % 8, v = i / 8;
-            long long o = base + v;
-            cs[v][aa] = o < total ? Store<T>::ld(coarse + o * p.a + a0 + aa) : 0.f;
-        }
-        for (int i = t; i < VB * 8 * BCH; i += NTH) {
-            int bb = i % BCH, k = (i / BCH) % 8, v = i / (BCH * 8);
-            long long o = base + v;
-            float f = 0.f;
-            if (o < total) {
-                int n, od, oh, ow;
-                decode_coarse(o, p, n, od, oh, ow);
-                f = Store<T>::ld(fine + fine_index(p, n, od, oh, ow, k) * p.b + b0 + bb);
+            for (int bb = 0; bb < 8; ++bb) {
+                const float4 w0 = *reinterpret_cast<const float4*>(wk + (b0 + bb) * 8);
+                const float4 w1 = *reinterpret_cast<const float4*>(wk + (b0 + bb) * 8 + 4);
+                acc[0] = fmaf(xv[bb], w0.x, acc[0]); acc[1] = fmaf(xv[bb], w0.y, acc[1]);
+                acc[2] = fmaf(xv[bb], w0.z, acc[2]); acc[3] = fmaf(xv[bb], w0.w, acc[3]);
+                acc[4] = fmaf(xv[bb], w1.x, acc[4]); acc[5] = fmaf(xv[bb], w1.y, acc[5]);
+                acc[6] = fmaf(xv[bb], w1.z, acc[6]); acc[7] = fmaf(xv[bb], w1.w, acc[7]);
             }
-            fs[v][k][bb] = f;
-        }
-        __syncthreads();
-#pragma unroll 4
-        for (int v = 0; v < VB; ++v) {
-            const float c = cs[v][a_l];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) acc[k] = fmaf(c, fs[v][k][b_l], acc[k]);
         }
     }
-    float* pd = dwt + ((long long)(a0 + a_l) * p.b + b0 + b_l) * 8;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) atomicAdd(pd + k, acc[k]);
+    for (int q = 0; q < 8; ++q) {                      // sum over the eight k-lanes of the voxel
+        acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], 1);
+        acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], 2);
+        acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], 4);
+    }
+    if (valid && k == 0) {
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = acc[q] + (bias ? bias[a0 + q] : 0.f);
+        Store<T>::st8(coarse + o * p.a + a0, v);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) k2s2_scatter_ksplit_kernel(const T* __restrict__ coarse, const float* __restrict__ wt,
+                                                                  const float* __restrict__ bias, T* __restrict__ fine,
+                                                                  K2Dims p, long long total) {
+    extern __shared__ float wsm[];                     // [8 k][A][8 b] (+4 pad per k)
+    const int t = threadIdx.x, k = t & 7;
+    const int b0 = blockIdx.y * 8;
+    const int kstride = p.a * 8 + 4;
+    for (int i = t; i < p.a * 64; i += 128) {          // global order [a][bb][k] (64 contiguous floats per a)
+        const int kk = i & 7, bb = (i >> 3) & 7, aa = i >> 6;
+        wsm[kk * kstride + aa * 8 + bb] = wt[((long long)aa * p.b + b0 + bb) * 8 + kk];
+    }
+    __syncthreads();
+    const long long o = (long long)blockIdx.x * 16 + (t >> 3);
+    if (o >= total) return;
+    int n, od, oh, ow;
+    decode_coarse(o, p, n, od, oh, ow);
+    const T* px = coarse + o * p.a;
+    const float* wk = wsm + k * kstride;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int a0 = 0; a0 < p.a; a0 += 8) {
+        float xv[8];
+        Store<T>::ld8(px + a0, xv);
+#pragma unroll
+        for (int aa = 0; aa < 8; ++aa) {
+            const float4 w0 = *reinterpret_cast<const float4*>(wk + (a0 + aa) * 8);
+            const float4 w1 = *reinterpret_cast<const float4*>(wk + (a0 + aa) * 8 + 4);
+            acc[0] = fmaf(xv[aa], w0.x, acc[0]); acc[1] = fmaf(xv[aa], w0.y, acc[1]);
+            acc[2] = fmaf(xv[aa], w0.z, acc[2]); acc[3] = fmaf(xv[aa], w0.w, acc[3]);
+            acc[4] = fmaf(xv[aa], w1.x, acc[4]); acc[5] = fmaf(xv[aa], w1.y, acc[5]);
+            acc[6] = fmaf(xv[aa], w1.z, acc[6]); acc[7] = fmaf(xv[aa], w1.w, acc[7]);
+        }
+    }
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = acc[q] + (bias ? bias[b0 + q] : 0.f);
+    Store<T>::st8(fine + fine_index(p, n, od, oh, ow, k) * p.b + b0, v);
+}
+
+// dwt[a][b][k] += sum_o coarse[o,a] * fine[2o+k,b].
+// CTA = one 8x8 (a, b) block of the weight and a contiguous range of coarse voxels.  Warp w = filter position k,
+// lane = voxel lane: per voxel a thread issues two 16-byte loads (8 coarse channels, 8 channels of fine voxel 2o+k)
+// and 64 FMAs into an 8x8 register block -- no shared-memory staging, FMA-bound.  One shuffle reduction over the 32
+// voxel lanes and 64 atomics per warp at the end.
+template <typename T>
+__global__ void __launch_bounds__(256, 2) k2s2_wgrad_kernel(const T* __restrict__ coarse, const T* __restrict__ fine,
+                                                         float* __restrict__ dwt, K2Dims p, long long total,
+                                                         long long per_cta) {
+    const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
+    const int a0 = blockIdx.y * 8, b0 = blockIdx.z * 8;
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) acc[i][jj] = 0.f;
+    const long long begin = (long long)blockIdx.x * per_cta;
+    const long long end = min(total, begin + per_cta);
+    // two voxels per thread per iteration: four independent 16-byte loads in flight before the FMAs; two CTAs
+    // per SM (<= 128 registers) so that 16 warps hide the DRAM latency
+    for (long long o = begin + lane; o < end; o += 64) {
+        float c[2][8], f[2][8];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const long long ou = o + 32 * u;
+            if (ou < end) {
+                int n, od, oh, ow;
+                decode_coarse(ou, p, n, od, oh, ow);
+                Store<T>::ld8(coarse + ou * p.a + a0, c[u]);
+                Store<T>::ld8(fine + fine_index(p, n, od, oh, ow, k) * p.b + b0, f[u]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { c[u][q] = 0.f; f[u][q] = 0.f; }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) acc[i][jj] = fmaf(c[u][i], f[u][jj], acc[i][jj]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            const float v = warp_sum(acc[i][jj]);
+            if (lane == ((i * 8 + jj) & 31)) acc[i][jj] = v;        // spread the 64 results over the lanes
+        }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj)
+            if (lane == ((i * 8 + jj) & 31)) atomicAdd(dwt + ((long long)(a0 + i) * p.b + b0 + jj) * 8 + k, acc[i][jj]);
 }
 
 // out[c] += sum_rows t[row][c]   (C % 8 == 0)
@@ -218,6 +321,11 @@ int channel_sum(const T* x, float* out, long long rows, int c, cudaStream_t st) 
     return VS_OK;
 }
 
+int g_k2_ksplit_max = 8000;      // coarse voxels up to which the k-split kernels are used (tools/kbench.py sweeps it)
+bool use_ksplit(long long total, int reduce_channels) {
+    return total <= g_k2_ksplit_max && reduce_channels <= 256;
+}
+
 int check_k2(const void* p0, const void* p1, const void* p2, int n, int dc, int hc, int wc, int a, int b, const char* who) {
     VS_REQUIRE(n > 0 && dc > 0 && hc > 0 && wc > 0, VS_ERR_SHAPE, "%s: bad shape", who);
     VS_REQUIRE(a % 8 == 0 && b % 8 == 0 && a >= 8 && b >= 8, VS_ERR_UNSUPPORTED, "%s: channels must be multiples of 8 (A=%d B=%d)", who, a, b);
@@ -228,6 +336,8 @@ int check_k2(const void* p0, const void* p1, const void* p2, int n, int dc, int 
 
 }  // namespace
 
+extern "C" void vs_debug_set_k2_ksplit_max(int v) { g_k2_ksplit_max = v; }
+
 extern "C" int vs_k2s2_gather(int dtype, const void* fine, const float* wt, const float* bias, void* coarse,
                               int n, int dc, int hc, int wc, int a, int b, void* stream) {
     int rc = check_k2(fine, wt, coarse, n, dc, hc, wc, a, b, "k2s2_gather");
@@ -236,7 +346,13 @@ extern "C" int vs_k2s2_gather(int dtype, const void* fine, const float* wt, cons
     const long long total = (long long)n * dc * hc * wc;
     cudaStream_t st = (cudaStream_t)stream;
     VS_DISPATCH_DTYPE(dtype, T, {
-        if (a % 16 == 0) {
+        if (use_ksplit(total, b)) {
+            const size_t sm = (size_t)(8 * (b * 8 + 4)) * sizeof(float);
+            auto kern = k2s2_gather_ksplit_kernel<T>;
+            if (sm > 48 * 1024) VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm), "k2s2 smem attribute");
+            dim3 grid(vs_ceil_div(total, 16), a / 8);
+            kern<<<grid, 128, sm, st>>>((const T*)fine, wt, bias, (T*)coarse, p, total);
+        } else if (a % 16 == 0) {
             dim3 grid(vs_ceil_div(total, 128), a / 16);
             k2s2_gather_kernel<T, 16><<<grid, 128, 0, st>>>((const T*)fine, wt, bias, (T*)coarse, p, total);
         } else {
@@ -256,7 +372,13 @@ extern "C" int vs_k2s2_scatter(int dtype, const void* coarse, const float* wt, c
     const long long total = (long long)n * dc * hc * wc;
     cudaStream_t st = (cudaStream_t)stream;
     VS_DISPATCH_DTYPE(dtype, T, {
-        if (b % 16 == 0) {
+        if (use_ksplit(total, a)) {
+            const size_t sm = (size_t)(8 * (a * 8 + 4)) * sizeof(float);
+            auto kern = k2s2_scatter_ksplit_kernel<T>;
+            if (sm > 48 * 1024) VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm), "k2s2 smem attribute");
+            dim3 grid(vs_ceil_div(total, 16), b / 8);
+            kern<<<grid, 128, sm, st>>>((const T*)coarse, wt, bias, (T*)fine, p, total);
+        } else if (b % 16 == 0) {
             dim3 grid(vs_ceil_div(total, 64), b / 16);
             k2s2_scatter_kernel<T, 16><<<grid, 256, 0, st>>>((const T*)coarse, wt, bias, (T*)fine, p, total);
         } else {
@@ -282,12 +404,13 @@ extern "C" int vs_k2s2_wgrad(int dtype, const void* coarse, const void* fine, fl
         if (dbias_fine) VS_CUDA(cudaMemsetAsync(dbias_fine, 0, sizeof(float) * b, st), "k2s2 wgrad memset");
     }
     VS_DISPATCH_DTYPE(dtype, T, {
-        const int bch = (b % 16 == 0) ? 16 : 8;
-        dim3 grid(1, a / 8, b / bch);
-        long long slots = max(1LL, (long long)vs_sm_count() * 8 / ((long long)grid.y * grid.z));
-        grid.x = (unsigned)max(1LL, min(slots, (total + 31) / 32));
-        if (bch == 16) k2s2_wgrad_kernel<T, 16><<<grid, 128, 0, st>>>((const T*)coarse, (const T*)fine, dwt, p, total);
-        else k2s2_wgrad_kernel<T, 8><<<grid, 64, 0, st>>>((const T*)coarse, (const T*)fine, dwt, p, total);
+        dim3 grid(1, a / 8, b / 8);
+        const long long blocks = (long long)grid.y * grid.z;
+        long long parts = max(1LL, (long long)vs_sm_count() * 4 / blocks);        // ~2 waves of 2 CTAs per SM
+        parts = min(parts, (total + 63) / 64);                                      // >= 64 voxels per CTA
+        const long long per_cta = (total + parts - 1) / parts;
+        grid.x = (unsigned)((total + per_cta - 1) / per_cta);
+        k2s2_wgrad_kernel<T><<<grid, 256, 0, st>>>((const T*)coarse, (const T*)fine, dwt, p, total, per_cta);
         VS_CHECK_LAUNCH("k2s2_wgrad_kernel");
         if (dbias_coarse) { rc = channel_sum<T>((const T*)coarse, dbias_coarse, total, a, st); if (rc) return rc; }
         if (dbias_fine) { rc = channel_sum<T>((const T*)fine, dbias_fine, total * 8, b, st); if (rc) return rc; }

@@ -13,6 +13,7 @@ the softmax head writes planar probabilities, so no layout-conversion kernels ru
 Reference semantics implemented here: joint_model.py:35-52,101-136 (blocks), :369-390
 (Segmentation.forward incl. the two additive skips), :227-272 (VAE.forward).
 """
+import ctypes
 import os
 
 import torch
@@ -46,52 +47,133 @@ class Layer(object):
         self.save_as, self.skip_from, self.in_planar = save_as, skip_from, in_planar
 
 
+class _PackJob(ctypes.Structure):
+    # mirrors vs_pack_job (include/vaeseg_b200.h)
+    _fields_ = [("w", ctypes.c_void_p), ("wf", ctypes.c_void_p), ("wd", ctypes.c_void_p), ("tcf", ctypes.c_void_p),
+                ("tcd", ctypes.c_void_p), ("tcf_elems", ctypes.c_longlong), ("tcd_elems", ctypes.c_longlong),
+                ("cin", ctypes.c_int), ("cout", ctypes.c_int), ("cout_pad", ctypes.c_int), ("reserved", ctypes.c_int)]
+
+
 class PackCache(object):
-    """Derived caches of the fp32 master weights ([27][Cin][Cout] fprop / dgrad packs).
-    Keyed by storage pointer + tensor version + an explicit epoch that the fused optimiser
-    bumps (its raw-pointer updates do not touch torch's version counters)."""
+    """Derived caches of the fp32 master weights: fp32 [27][Cin][Cout] fprop / dgrad packs and the bf16 tensor-core
+    (UMMA B operand) packs.  Buffers are allocated once per weight and re-packed IN PLACE, so CUDA graphs that captured
+    their addresses stay valid.  An entry is current while (storage pointer, tensor version, epoch) match; the fused
+    optimiser / EMA update (raw-pointer writes that torch's version counters do not see) call `repack_all()`, which
+    refreshes every known entry with ONE batched launch, or `invalidate()` (lazy per-layer re-pack on next use)."""
 
     def __init__(self):
         self.epoch = 0
-        self._store = {}
+        self._store = {}          # (kind, data_ptr) -> entry dict
+        self._jobs = None         # (device table, n) of the batched re-pack, rebuilt when the entry set changes
 
     def invalidate(self):
         self.epoch += 1
+
+    def drop(self):
+        """Forget everything (the parameters moved: .to(device), load into new storage)."""
+        self.epoch += 1
         self._store.clear()
+        self._jobs = None
+
+    def _entry(self, kind, w, tc):
+        key = (w.data_ptr(), w._version, self.epoch)
+        ent = self._store.get((kind, w.data_ptr()))
+        fresh = ent is None or ent["shape"] != tuple(w.shape) or (tc and not ent["tc"])
+        if fresh:
+            ent = {"w": w, "shape": tuple(w.shape), "tc": False, "key": None, "wf": None, "wd": None, "tcf": None,
+                   "tcd": None, "kind": kind}
+            self._store[(kind, w.data_ptr())] = ent
+            self._jobs = None
+        return ent, key
 
     def conv3(self, w, tc=False):
         """Returns (wf, wd, wtc_fprop, wtc_dgrad); the tensor-core packs are None unless tc=True (bf16
         mode) and the tcgen05 path takes the shape."""
-        key = (w.data_ptr(), w._version, self.epoch, tc)
-        hit = self._store.get(w.data_ptr())
-        if hit is not None and hit[0] == key:
-            return hit[1]
-        wdet = w.detach()
-        wf, wd = ops.pack_conv3_weight(wdet, want_dgrad=True)
-        tf = td = None
-        if tc and USE_TENSOR_CORES:
-            tf = ops.pack_conv3_weight_tc(wdet, dgrad=False)
-            td = ops.pack_conv3_weight_tc(wdet, dgrad=True)
-        packs = (wf, wd, tf, td)
-        self._store[w.data_ptr()] = (key, packs)
-        return packs
-
+        tc = bool(tc and USE_TENSOR_CORES)
+        ent, key = self._entry("conv3", w, tc)
+        if ent["key"] != key or (tc and not ent["tc"]):
+            wdet = w.detach()
+            cout, cin = wdet.shape[0], wdet.shape[1]
+            if ent["wf"] is None:
+                ent["wf"] = torch.empty(27, cin, cout, device=wdet.device, dtype=torch.float32)
+                ent["wd"] = torch.empty(27, cout, cin, device=wdet.device, dtype=torch.float32)
+            ops.pack_conv3_weight(wdet, out=(ent["wf"], ent["wd"]))
+            if tc:
+                ent["tcf"] = ops.pack_conv3_weight_tc(wdet, dgrad=False, out=ent["tcf"])
+                ent["tcd"] = ops.pack_conv3_weight_tc(wdet, dgrad=True, out=ent["tcd"])
+                if not ent["tc"]:
+                    self._jobs = None
+                ent["tc"] = True
+            ent["key"] = key
+        return ent["wf"], ent["wd"], ent["tcf"], ent["tcd"]
 
     def head_dgrad_tc(self, w):
         """bf16 tensor-core dgrad pack of the head weight [n_class,Cin,3,3,3] zero-padded to 8 output channels (the
         head's logit gradient is produced as an 8-channel tensor, ops.softmax2_bwd_pad8), or None."""
         if not USE_TENSOR_CORES:
             return None
-        key = (w.data_ptr(), w._version, self.epoch, "head8")
-        hit = self._store.get(("head8", w.data_ptr()))
-        if hit is not None and hit[0] == key:
-            return hit[1]
-        wdet = w.detach()
-        w8 = torch.zeros(8, wdet.shape[1], 3, 3, 3, device=wdet.device, dtype=torch.float32)
-        w8[:wdet.shape[0]].copy_(wdet)
-        pack = ops.pack_conv3_weight_tc(w8, dgrad=True)
-        self._store[("head8", w.data_ptr())] = (key, pack)
-        return pack
+        ent, key = self._entry("head8", w, True)
+        if ent["key"] != key:
+            wdet = w.detach()
+            w8 = torch.zeros(8, wdet.shape[1], 3, 3, 3, device=wdet.device, dtype=torch.float32)
+            w8[:wdet.shape[0]].copy_(wdet)
+            ent["tcd"] = ops.pack_conv3_weight_tc(w8, dgrad=True, out=ent["tcd"])
+            ent["tc"] = True
+            ent["key"] = key
+        return ent["tcd"]
+
+    def repack_all(self):
+        """Re-packs every known entry in place with one launch; entries become current for the present weights."""
+        ents = [e for e in self._store.values() if e["key"] is not None]
+        if not ents:
+            self.invalidate()
+            return
+        if self._jobs is None or self._jobs[1] != len(ents):
+            arr = (_PackJob * len(ents))()
+            for j, e in zip(arr, ents):
+                w = e["w"].detach()
+                j.w = w.data_ptr()
+                j.cout, j.cin = w.shape[0], w.shape[1]
+                j.cout_pad = 8 if e["kind"] == "head8" else w.shape[0]
+                j.wf = e["wf"].data_ptr() if e["wf"] is not None else None
+                j.wd = e["wd"].data_ptr() if e["wd"] is not None else None
+                j.tcf = e["tcf"].data_ptr() if e["tcf"] is not None else None
+                j.tcd = e["tcd"].data_ptr() if e["tcd"] is not None else None
+                j.tcf_elems = e["tcf"].numel() if e["tcf"] is not None else 0
+                j.tcd_elems = e["tcd"].numel() if e["tcd"] is not None else 0
+            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+            self._jobs = (host.to(ents[0]["w"].device), len(ents), ents)
+        ops.pack_conv3_batched(self._jobs[0], self._jobs[1])
+        self.epoch += 1
+        for e in self._jobs[2]:
+            e["key"] = (e["w"].data_ptr(), e["w"]._version, self.epoch)
+
+
+# Optional side stream for the weight-gradient kernels (set by the trainers): wgrad(L) only needs dy(L) and the saved
+# input of L, while the backward chain continues with dgrad(L) -> norm-backward(L-1) -> ...; on a second stream (a
+# parallel branch of the captured CUDA graph) the wgrads fill the SMs that the small deep-level kernels leave idle.
+# Only used when the gradient is accumulated in place into an existing .grad (the trainers' flat arenas): the
+# consumer (optimiser) then waits on the side stream once per step (`join_wgrad_stream`).
+WGRAD_STREAM = None
+
+
+def _wgrad_async(fn, inplace, *inputs):
+    ws = WGRAD_STREAM
+    if ws is None or not inplace:
+        return fn()
+    cur = torch.cuda.current_stream()
+    ws.wait_stream(cur)
+    with torch.cuda.stream(ws):
+        out = fn()
+    for t in inputs:
+        if t is not None:
+            t.record_stream(ws)
+    return out
+
+
+def join_wgrad_stream():
+    if WGRAD_STREAM is not None:
+        torch.cuda.current_stream().wait_stream(WGRAD_STREAM)
 
 
 def _tc_channels(c):
@@ -196,17 +278,17 @@ def program_backward(tape, g, dtype, need, grads, param_refs, need_input_grad):
             dy = _sim(ops.inorm_relu_bwd(g, y, stats), "dy")
             if need[L.wi]:
                 tgt, acc = _grad_target(param_refs[L.wi], True)
-                if L.in_planar and dtype == torch.bfloat16 and USE_TENSOR_CORES and L.cin < 8 and L.cout % 8 == 0:
-                    # in-block (Cin 1 or 2, planar fp32 input): pad the input to 8 bf16 channels and take the
-                    # tensor-core wgrad; the padded input channels give zero rows that are dropped
-                    dw8, _ = ops.conv3_wgrad(ops.planar_to_ndhwc8(x_in), dy, dims, 8, L.cout)
-                    if acc:
-                        tgt.add_(dw8[:, :L.cin])
-                        dw = tgt
-                    else:
-                        dw = dw8[:, :L.cin].contiguous()
-                else:
-                    dw, _ = ops.conv3_wgrad(x_in, dy, dims, L.cin, L.cout, dw=tgt, in_planar=L.in_planar, accumulate=acc)
+                def run_wgrad(L=L, x_in=x_in, dy=dy, dims=dims, tgt=tgt, acc=acc):
+                    if L.in_planar and dtype == torch.bfloat16 and USE_TENSOR_CORES and L.cin < 8 and L.cout % 8 == 0:
+                        # in-block (Cin 1 or 2, planar fp32 input): pad the input to 8 bf16 channels and take the
+                        # tensor-core wgrad; the padded input channels give zero rows that are dropped
+                        dw8, _ = ops.conv3_wgrad(ops.planar_to_ndhwc8(x_in), dy, dims, 8, L.cout)
+                        if acc:
+                            tgt.add_(dw8[:, :L.cin])
+                            return tgt
+                        return dw8[:, :L.cin].contiguous()
+                    return ops.conv3_wgrad(x_in, dy, dims, L.cin, L.cout, dw=tgt, in_planar=L.in_planar, accumulate=acc)[0]
+                dw = _wgrad_async(run_wgrad, acc, x_in, dy)
                 grads[L.wi] = None if acc else dw
             if need[L.bi]:
                 # exactly zero: the bias cancels in InstanceNorm
@@ -218,14 +300,16 @@ def program_backward(tape, g, dtype, need, grads, param_refs, need_input_grad):
             # dims are the coarse (output) dims; g is the coarse gradient
             if need[L.wi] or need[L.bi]:
                 tw, tb, acc = _pair_targets(param_refs, need, L.wi, L.bi, (L.cout, L.cin, 2, 2, 2), (L.cout,), g.device)
-                ops.k2s2_wgrad(g, x_in, dims, L.cout, L.cin, dwt=tw, dbias_coarse=tb, accumulate=acc)
+                _wgrad_async(lambda: ops.k2s2_wgrad(g, x_in, dims, L.cout, L.cin, dwt=tw, dbias_coarse=tb, accumulate=acc),
+                             acc, g, x_in)
                 _hand_back(grads, need, L.wi, L.bi, tw, tb, acc)
             g = _sim(ops.k2s2_scatter(g, wt, None, dims, L.cout, L.cin), "g") if want_dx else None
         elif L.kind == K2UP:
             # dims are the coarse (input) dims; g is the fine gradient
             if need[L.wi] or need[L.bi]:
                 tw, tb, acc = _pair_targets(param_refs, need, L.wi, L.bi, (L.cin, L.cout, 2, 2, 2), (L.cout,), g.device)
-                ops.k2s2_wgrad(x_in, g, dims, L.cin, L.cout, dwt=tw, dbias_fine=tb, accumulate=acc)
+                _wgrad_async(lambda: ops.k2s2_wgrad(x_in, g, dims, L.cin, L.cout, dwt=tw, dbias_fine=tb, accumulate=acc),
+                             acc, g, x_in)
                 _hand_back(grads, need, L.wi, L.bi, tw, tb, acc)
             g = _sim(ops.k2s2_gather(g, wt, None, dims, L.cin, L.cout), "g") if want_dx else None
         elif L.kind == HEAD:
@@ -240,11 +324,13 @@ def program_backward(tape, g, dtype, need, grads, param_refs, need_input_grad):
                         tb.zero_()
                 dl8 = ops.softmax2_bwd_pad8(g, probs, dims, db=tb)
                 if need[L.wi]:
-                    dw8, _ = ops.conv3_wgrad(x_in, dl8, dims, L.cin, 8)
-                    if acc:
-                        tw.add_(dw8[:L.cout])
-                    else:
-                        tw.copy_(dw8[:L.cout])
+                    def run_head_wgrad(x_in=x_in, dl8=dl8, dims=dims, tw=tw, acc=acc, L=L):
+                        dw8, _ = ops.conv3_wgrad(x_in, dl8, dims, L.cin, 8)
+                        if acc:
+                            tw.add_(dw8[:L.cout])
+                        else:
+                            tw.copy_(dw8[:L.cout])
+                    _wgrad_async(run_head_wgrad, acc, x_in, dl8)
                 if need[L.wi] or need[L.bi]:
                     _hand_back(grads, need, L.wi, L.bi, tw, tb, acc)
                 g = ops.conv3_dgrad(dl8, None, dims, L.cin, 8, dtype, wdtc=wd[1]) if want_dx else None

@@ -146,14 +146,22 @@ class _Engineered(nn.Module):
         return _PRECISIONS[self._precision]
 
     def invalidate_packs(self):
-        """Call after updating parameters through raw pointers (fused optimiser, EMA)."""
+        """Call after updating parameters through raw pointers (fused optimiser, EMA): the derived weight packs are
+        re-made lazily, layer by layer, on next use."""
         for m in self.modules():
             if isinstance(m, _Engineered):
                 m._cache.invalidate()
 
+    def repack_packs(self):
+        """Same contract as invalidate_packs(), but refreshes every pack now, in place, with one launch per
+        network -- what the fused optimiser calls every step (and what keeps captured CUDA graphs valid)."""
+        for m in self.modules():
+            if isinstance(m, _Engineered):
+                m._cache.repack_all()
+
     def _apply(self, fn, *a, **k):
         out = super()._apply(fn, *a, **k)
-        self._cache.invalidate()
+        self._cache.drop()
         self._program = None
         return out
 

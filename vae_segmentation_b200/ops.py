@@ -43,26 +43,35 @@ def has_tcgen05():
 
 
 # ---- 3x3x3 convolution ---------------------------------------------------------------
-def pack_conv3_weight(w, want_dgrad=True):
-    """[Cout,Cin,3,3,3] fp32 -> (wf [27,Cin,Cout], wd [27,Cout,Cin] or None)."""
+def pack_conv3_weight(w, want_dgrad=True, out=None):
+    """[Cout,Cin,3,3,3] fp32 -> (wf [27,Cin,Cout], wd [27,Cout,Cin] or None); `out=(wf, wd)` re-packs in place."""
     cout, cin = w.shape[0], w.shape[1]
     _f32(w, "weight")
-    wf = torch.empty(27, cin, cout, device=w.device, dtype=torch.float32)
-    wd = torch.empty(27, cout, cin, device=w.device, dtype=torch.float32) if want_dgrad else None
+    if out is not None:
+        wf, wd = out
+    else:
+        wf = torch.empty(27, cin, cout, device=w.device, dtype=torch.float32)
+        wd = torch.empty(27, cout, cin, device=w.device, dtype=torch.float32) if want_dgrad else None
     _cabi.call("vs_pack_conv3_weight", _p(w), _p(wf), _p(wd), cin, cout, _stream())
     return wf, wd
 
 
-def pack_conv3_weight_tc(w, dgrad=False):
+def pack_conv3_weight_tc(w, dgrad=False, out=None):
     """bf16 tensor-core (UMMA B operand) pack of a [Cout,Cin,3,3,3] weight, or None if the tcgen05
-    path does not take this shape / the library was built without it."""
+    path does not take this shape / the library was built without it.  `out` re-packs in place."""
     cout, cin = w.shape[0], w.shape[1]
     nbytes = _cabi.lib().vs_conv3_tc_pack_bytes(cin, cout, int(dgrad))
     if nbytes == 0:
         return None
-    out = torch.empty(nbytes // 2, device=w.device, dtype=torch.bfloat16)
+    if out is None:
+        out = torch.empty(nbytes // 2, device=w.device, dtype=torch.bfloat16)
     _cabi.call("vs_pack_conv3_weight_tc", _p(_f32(w, "weight")), _p(out), cin, cout, int(dgrad), _stream())
     return out
+
+
+def pack_conv3_batched(jobs_dev, njobs):
+    """One launch re-packing every layer described by the device job table (engine.PackCache.repack_all)."""
+    _cabi.call("vs_pack_conv3_batched", _p(jobs_dev), int(njobs), _stream())
 
 
 def conv3_fprop(x, wf, bias, dims, cin, cout, out_dtype, in_planar=False, out_planar=False, want_stats=True,

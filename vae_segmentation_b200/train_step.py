@@ -43,8 +43,9 @@ class FlatArena(object):
                 p.grad = self.grad[off:off + k].view(p.shape)
             off += k
         self.numel = n
-        if hasattr(module, "invalidate_packs"):
-            module.invalidate_packs()
+        for m in module.modules():                       # parameters were re-homed: forget every derived pack
+            if hasattr(m, "_cache"):
+                m._cache.drop()
 
     def zero_grad(self):
         if self.grad is not None:
@@ -63,7 +64,7 @@ class FusedSGD(object):
         ops.sgd_step(self.arena.data, self.arena.grad, self.buf, self.lr, self.momentum, first=(self.steps == 0),
                      gscale=gscale)
         self.steps += 1
-        self.arena.module.invalidate_packs()
+        self.arena.module.repack_packs()
 
 
 class FusedAdam(object):
@@ -77,7 +78,7 @@ class FusedAdam(object):
         self.steps += 1
         ops.adam_step(self.arena.data, self.arena.grad, self.m, self.v, self.lr, self.betas[0], self.betas[1],
                       self.eps, self.steps, gscale=gscale)
-        self.arena.module.invalidate_packs()
+        self.arena.module.repack_packs()
 
 
 def _world():
@@ -152,7 +153,7 @@ class JointTrainer(object):
     the frozen VAE architecture; only student.Seg trains (main_target.py:396-433)."""
 
     def __init__(self, student, teacher, lr=1e-2, momentum=0.9, lambda_vae=1.0, loss_type=0, kl=False,
-                 confident=False, only_pseudo=False, alpha=0.995, adam=False, faithful_teacher=True):
+                 confident=False, only_pseudo=False, alpha=0.995, adam=False, faithful_teacher=True, overlap=True):
         self.student, self.teacher = student, teacher
         for p in student.Vae.parameters():
             p.requires_grad = False
@@ -165,23 +166,44 @@ class JointTrainer(object):
         self.confident, self.only_pseudo, self.alpha = confident, only_pseudo, alpha
         self.faithful_teacher = faithful_teacher
         self.stream = torch.cuda.Stream()        # see capture()
+        # Concurrency inside the step (parallel branches of the captured graph): the frozen teacher's forward is
+        # independent of the student's until the losses, and the weight-gradient kernels are leaves of the backward
+        # chain.  Both are dominated by deep-level kernels that occupy 8-48 of the 148 SMs, so they overlap well.
+        self.overlap = overlap
+        self.teacher_stream = torch.cuda.Stream() if overlap else None
+        self.wgrad_stream = torch.cuda.Stream() if overlap else None
 
     def ema_teacher(self):
         # main_target.py:512-516 on the Seg state_dict
         ops.ema_update(self.teacher_arena.data, self.arena.data, self.alpha)
-        self.teacher.invalidate_packs()
+        self.teacher.repack_packs()
 
     def losses(self, img, label, student=None):
         """Forward of one step; returns (final_loss, dict of monitored terms)."""
         student = student or self.student
+        cur = torch.cuda.current_stream()
+
+        def run_teacher():
+            with torch.no_grad():                                                     # :532 (frozen teacher)
+                if self.faithful_teacher or self.kl:
+                    return self.teacher({"img": img}, "img", "only_fake", "unused_recon")
+                out = self.teacher.Seg({"img": img}, "img", "only_fake")
+                out["mean"] = out["std"] = None
+                return out
+
+        if self.overlap:
+            self.teacher_stream.wait_stream(cur)
+            with torch.cuda.stream(self.teacher_stream):
+                tb = run_teacher()
         batch = {"img": img}
         batch = student(batch, "img", "pred", "recon_pred", dropout=True)            # main_target.py:531
-        with torch.no_grad():                                                         # :532 (frozen teacher)
-            if self.faithful_teacher or self.kl:
-                tb = self.teacher({"img": img}, "img", "only_fake", "unused_recon")
-            else:
-                tb = self.teacher.Seg({"img": img}, "img", "only_fake")
-                tb["mean"] = tb["std"] = None
+        if self.overlap:
+            cur.wait_stream(self.teacher_stream)
+            for v in tb.values():
+                if torch.is_tensor(v) and v.is_cuda:
+                    v.record_stream(cur)
+        else:
+            tb = run_teacher()
         pred = batch["pred"]
         recon_loss = 1 - ev.avg_dsc_fused(pred, batch["recon_pred"], "tensor", botindex=1, topindex=2)      # :543
         dsc_loss = 1 - ev.avg_dsc_fused(pred.detach(), label, "label", botindex=1, topindex=2)             # :545 (monitor)
@@ -205,9 +227,18 @@ class JointTrainer(object):
             self.ema_teacher()
         self.arena.zero_grad()
         final, mon, _ = self.losses(img, label)
-        final.backward()
+        self._backward(final)
         self.opt.step(allreduce_mean_(self.arena.grad))
         return mon
+
+    def _backward(self, final):
+        from . import engine
+        engine.WGRAD_STREAM = self.wgrad_stream
+        try:
+            final.backward()
+            engine.join_wgrad_stream()
+        finally:
+            engine.WGRAD_STREAM = None
 
     def capture(self, img_static, label_static, warmup=2):
         """CUDA-graph capture of zero_grad + forward (student, teacher, losses) + backward on the given static
@@ -227,7 +258,7 @@ class JointTrainer(object):
         with torch.cuda.graph(self._graph, stream=side):
             self.arena.zero_grad()
             final, mon, _ = self.losses(img_static, label_static)
-            final.backward()
+            self._backward(final)
         self._graph_mon = mon
         return self
 
@@ -249,13 +280,13 @@ class JointTrainer(object):
                 p.requires_grad = False
             ft = self._ft_arena = FlatArena(finetune.Seg)
         ft.data.copy_(self.arena.data)                                                # :810 load_state_dict
-        finetune.invalidate_packs()
+        finetune.repack_packs()
         for _ in range(iters):
             ft.zero_grad()
             final, _, _ = self.losses(img, label, student=finetune)
             final.backward()
             ops.sgd_step(ft.data, ft.grad, None, lr_finetune, 0.0, first=True)       # :886 SGD(lr_finetune, momentum 0)
-            finetune.invalidate_packs()
+            finetune.repack_packs()
         with torch.no_grad():                                                         # :902-914
             p0 = self.student.Seg.predict(img)
             p1 = finetune.Seg.predict(img)
