@@ -384,7 +384,13 @@ __global__ void pack_tc_kernel(const float* __restrict__ w, bf16* __restrict__ o
         out[i] = __float2bfloat16_rn(pack_tc_elem(w, i, cin_l, cout_l, cout_l, dgrad, nc, cin8));
 }
 
-__host__ __device__ constexpr int nc_for_dev(int gout) { return gout >= 64 ? 64 : (gout >= 32 ? 32 : 16); }
+// Output channels per CTA (MMA N).  An MMA costs ~(128 + N)/4 cycles (operand delivery from shared memory), so a
+// small N wastes tensor-pipe time in aggregate but shortens each CTA: layers with >= 64 output channels only occur at
+// the deep levels (<= 12^3), whose grids leave most SMs idle, so they are split into more, shorter CTAs.
+#ifndef VS_NC_WIDE
+#define VS_NC_WIDE 16
+#endif
+__host__ __device__ constexpr int nc_for_dev(int gout) { return gout >= 64 ? VS_NC_WIDE : (gout >= 32 ? 32 : 16); }
 int nc_for(int gout) { return nc_for_dev(gout); }
 
 template <int NC, bool CIN8, int NSTAGE>
