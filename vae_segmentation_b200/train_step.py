@@ -170,8 +170,8 @@ class JointTrainer(object):
         # independent of the student's until the losses, and the weight-gradient kernels are leaves of the backward
         # chain.  Both are dominated by deep-level kernels that occupy 8-48 of the 148 SMs, so they overlap well.
         self.overlap = overlap
-        self.teacher_stream = torch.cuda.Stream() if overlap else None
-        self.wgrad_stream = torch.cuda.Stream() if overlap else None
+        self.teacher_stream = torch.cuda.Stream()
+        self.wgrad_stream = torch.cuda.Stream()
 
     def ema_teacher(self):
         # main_target.py:512-516 on the Seg state_dict
@@ -233,7 +233,7 @@ class JointTrainer(object):
 
     def _backward(self, final):
         from . import engine
-        engine.WGRAD_STREAM = self.wgrad_stream
+        engine.WGRAD_STREAM = self.wgrad_stream if self.overlap else None
         try:
             final.backward()
             engine.join_wgrad_stream()
