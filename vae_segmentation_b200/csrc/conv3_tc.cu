@@ -38,6 +38,9 @@ constexpr int NTHREADS = 288;                          // 1 producer + 4 MMA + 4
 struct TcParams {
     int n, d, h, w, cin, cout;
     int tiles_d, tiles_h, tiles_w, tiles_per_n;
+    int bw, bh, bd;         // TMA box = staged halo extents (<= 10 x 18 x 6): clipped to the volume so that small
+                            // volumes do not pay for rows that are pure zero fill (TMA cost is per 16-byte row)
+    int td;                 // d-planes per work item (1, 2 or 4): deep levels use fewer so that the grid fills the SMs
     int nchunks;            // cout chunks of NC
     int kslices;            // cin / 16 (1 for cin == 8)
     long long work_items;   // n * tiles_per_n * nchunks
@@ -72,7 +75,7 @@ __device__ __forceinline__ void decode_work(long long item, const TcParams& p, i
     int r = (int)(t % p.tiles_per_n);
     w0 = (r % p.tiles_w) * TW; r /= p.tiles_w;
     h0 = (r % p.tiles_h) * TH; r /= p.tiles_h;
-    d0 = r * TD;
+    d0 = r * p.td;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -108,10 +111,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
         fence_barrier_init();
     }
     if (CIN8) {
-        // zero the pad behind each stage's plane once (read only under zero weights, but must not be NaN)
-        for (int i = threadIdx.x; i < NSTAGE * (PLANE_PAD / 4); i += NTHREADS) {
-            int s = i / (PLANE_PAD / 4), k = i % (PLANE_PAD / 4);
-            reinterpret_cast<uint32_t*>(smem + s * STAGE_BYTES + PLANE_BYTES)[k] = 0u;
+        // The zero-weighted third tap of the Cin=8 tap pairs reads one voxel past the row it belongs to: past the
+        // end of the staged box that is memory TMA never writes, which must not hold NaN patterns.  Zero the pad
+        // behind the full-size plane, or the whole A region when the box is clipped.
+        const bool clipped = p.bw < HW || p.bh < HH || p.bd < HD;
+        const int words = clipped ? A_BYTES / 4 : PLANE_PAD / 4, off = clipped ? 0 : PLANE_BYTES;
+        for (int i = threadIdx.x; i < NSTAGE * words; i += NTHREADS) {
+            int s = i / words, k = i % words;
+            reinterpret_cast<uint32_t*>(smem + s * STAGE_BYTES + off)[k] = 0u;
         }
         fence_proxy_async();
     }
@@ -131,7 +138,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
                 for (int ks = 0; ks < p.kslices; ++ks) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * STAGE_BYTES;
-                    mbar_expect_tx(&full_bar[stage], (CIN8 ? PLANE_BYTES : 2 * PLANE_BYTES) + B_BYTES);
+                    mbar_expect_tx(&full_bar[stage], (uint32_t)((CIN8 ? 1 : 2) * p.bd * p.bh * p.bw * 16 + B_BYTES));
                     if (CIN8) tma_load_4d(sa, &xmap, &full_bar[stage], (w0 - 1) * 8, h0 - 1, d0 - 1, n);   // (w,c) merged: 160 B rows
                     else tma_load_5d(sa, &xmap, &full_bar[stage], ks * 16, w0 - 1, h0 - 1, d0 - 1, n);
                     if (!CIN8) tma_load_5d(sa + PLANE_BYTES, &xmap, &full_bar[stage], ks * 16 + 8, w0 - 1, h0 - 1, d0 - 1, n);
@@ -150,7 +157,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
         for (long long item = blockIdx.x; item < p.work_items; item += gridDim.x) {
             int n, d0, h0, w0, chunk;
             decode_work(item, p, n, d0, h0, w0, chunk);
-            const bool active = j < min(TD, p.d - d0);
+            const bool active = j < min(p.td, p.d - d0);
             mbar_wait(&tempty_bar[buf], bphase ^ 1);
             tc_fence_after();
             const uint32_t dcol = tmem_base + (buf * TD + j) * NC;
@@ -158,18 +165,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
                 if (active) {
-                    const uint32_t a_base = smem_u32(smem + stage * STAGE_BYTES) + (uint32_t)(j * HH * HW) * 16u;
+                    const uint32_t a_base = smem_u32(smem + stage * STAGE_BYTES) + (uint32_t)(j * p.bh * p.bw) * 16u;
                     const uint32_t b_base = smem_u32(smem + stage * STAGE_BYTES) + A_BYTES;
                     int m = 0;
 #pragma unroll 1
                     for (int kd = 0; kd < 3; ++kd) {
 #pragma unroll
                         for (int kh = 0; kh < 3; ++kh) {
-                            const uint32_t row = a_base + (uint32_t)((kd * HH + kh) * HW) * 16u;
+                            const uint32_t row = a_base + (uint32_t)((kd * p.bh + kh) * p.bw) * 16u;
 #pragma unroll
                             for (int kx = 0; kx < (CIN8 ? 2 : 3); ++kx, ++m) {
-                                const uint64_t ad = CIN8 ? make_desc(row + kx * 32u, 16u, HW * 16u)
-                                                         : make_desc(row + kx * 16u, PLANE_BYTES, HW * 16u);
+                                const uint64_t ad = CIN8 ? make_desc(row + kx * 32u, 16u, (uint32_t)p.bw * 16u)
+                                                         : make_desc(row + kx * 16u, PLANE_BYTES, (uint32_t)p.bw * 16u);
                                 const uint64_t bd = make_desc(b_base + m * (NC * 32), NC * 16, 128u);
                                 tc_mma_elect(dcol, ad, bd, idesc, (ks | m) != 0);
                             }
@@ -228,6 +235,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
         const bool has_stats = p.stats != nullptr;
         const uint32_t sshift_addr = smem_u32(sshift);
         const int ref_row = rh * TW + rw;
+        const int ref_d0 = (rd / p.td) * p.td;                   // first plane of the work item that owns the reference voxel
         for (long long item = blockIdx.x; item < p.work_items; item += gridDim.x) {
             int n, d0, h0, w0, chunk;
             decode_work(item, p, n, d0, h0, w0, chunk);
@@ -237,14 +245,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
                 stat_n = n; stat_chunk = chunk;
                 if (p.shift != nullptr) {
                     asm volatile("bar.sync 1, 128;" ::: "memory");       // everyone is done with the previous group's sshift
-                    if (d0 == 0 && h0 == 0 && w0 == 0) {
+                    if (d0 == ref_d0 && h0 == 0 && w0 == 0) {
                         mbar_wait(&tfull_bar[buf], bphase);
                         tc_fence_after();
                         if (q == (ref_row >> 5)) {
 #pragma unroll
                             for (int c16 = 0; c16 < NC / 16; ++c16) {
                                 uint32_t r[16];
-                                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (buf * TD + rd) * NC + c16 * 16, r);
+                                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (buf * TD + (rd - ref_d0)) * NC + c16 * 16, r);
                                 tmem_ld_wait();
                                 if (lane == (ref_row & 31)) {
 #pragma unroll
@@ -275,7 +283,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
             }
             mbar_wait(&tfull_bar[buf], bphase);
             tc_fence_after();
-            const int jmax = min(TD, p.d - d0);
+            const int jmax = min(p.td, p.d - d0);
             const int gh = h0 + lh, gw = w0 + lw;
             const bool rc_ok = gh < p.h && gw < p.w;
             for (int j = 0; j < jmax; ++j) {
@@ -480,7 +488,18 @@ extern "C" int vs_conv3x3x3_tc(const void* x, const void* wtc, void* y, double* 
     const cuuint64_t gdim[5] = {(cuuint64_t)gin, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)d, (cuuint64_t)n};
     const cuuint64_t gstr[4] = {(cuuint64_t)gin * 2, (cuuint64_t)w * gin * 2, (cuuint64_t)h * w * gin * 2,
                                 (cuuint64_t)d * h * w * gin * 2};
-    const cuuint32_t box[5] = {8, HW, HH, HD, 1};
+    // d-planes per work item and the staged box, both fitted to the volume (see TcParams)
+    const int tiles_h = (h + TH - 1) / TH, tiles_w = (w + TW - 1) / TW;
+    const int nc = nc_for(gout);
+    const int nchunks = (gout + nc - 1) / nc;
+    // 4 planes per item unless fewer still fit one wave of CTAs -- the deep levels are latency-bound on a handful of
+    // CTAs that each serialise 4 planes x all k-slices on one tensor pipe.  (One item per CTA also keeps the shift
+    // hand-off trivially deadlock-free: the producing item is never queued behind a waiting one.)
+    int td = TD;
+    while (td > 1 && (long long)n * ((d + td / 2 - 1) / (td / 2)) * tiles_h * tiles_w * nchunks <= (long long)vs_sm_count())
+        td >>= 1;                                                   // stays a single wave: every CTA has one item
+    const int bw = min(HW, w + 2), bh = min(HH, h + 2), bd = min(HD, min(td, d) + 2);
+    const cuuint32_t box[5] = {8, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd, 1};
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult cr;
     if (gin == 8) {
@@ -488,7 +507,7 @@ extern "C" int vs_conv3x3x3_tc(const void* x, const void* wtc, void* y, double* 
         // dimension makes it ONE 160 B TMA row instead of ten 16 B rows (TMA cost is per row)
         const cuuint64_t gdim4[4] = {(cuuint64_t)w * 8, (cuuint64_t)h, (cuuint64_t)d, (cuuint64_t)n};
         const cuuint64_t gstr4[3] = {(cuuint64_t)w * 16, (cuuint64_t)h * w * 16, (cuuint64_t)d * h * w * 16};
-        const cuuint32_t box4[4] = {HW * 8, HH, HD, 1};
+        const cuuint32_t box4[4] = {(cuuint32_t)bw * 8, (cuuint32_t)bh, (cuuint32_t)bd, 1};
         cr = encode(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), gdim4, gstr4, box4, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -500,10 +519,11 @@ extern "C" int vs_conv3x3x3_tc(const void* x, const void* wtc, void* y, double* 
 
     TcParams p;
     p.n = n; p.d = d; p.h = h; p.w = w; p.cin = gin; p.cout = gout;
-    p.tiles_d = (d + TD - 1) / TD; p.tiles_h = (h + TH - 1) / TH; p.tiles_w = (w + TW - 1) / TW;
+    p.tiles_h = tiles_h; p.tiles_w = tiles_w;
+    p.nchunks = nchunks;
+    p.td = td; p.bw = bw; p.bh = bh; p.bd = bd;
+    p.tiles_d = (d + p.td - 1) / p.td;
     p.tiles_per_n = p.tiles_d * p.tiles_h * p.tiles_w;
-    const int nc = nc_for(gout);
-    p.nchunks = (gout + nc - 1) / nc;
     p.kslices = gin == 8 ? 1 : gin / 16;
     p.work_items = (long long)n * p.tiles_per_n * p.nchunks;
     p.wpack = (const bf16*)wtc; p.y = (bf16*)y; p.stats = stats; p.shift = shift;
