@@ -40,6 +40,7 @@ struct TcParams {
     int tiles_d, tiles_h, tiles_w, tiles_per_n;
     int bw, bh, bd;         // TMA box = staged halo extents (<= 10 x 18 x 6): clipped to the volume so that small
                             // volumes do not pay for rows that are pure zero fill (TMA cost is per 16-byte row)
+    int ref_tile;           // tile (within a sample) that holds the shift's reference voxel
     int td;                 // d-planes per work item (1, 2 or 4): deep levels use fewer so that the grid fills the SMs
     int nchunks;            // cout chunks of NC
     int kslices;            // cin / 16 (1 for cin == 8)
@@ -68,11 +69,25 @@ __device__ __forceinline__ float transpose_reduce16(float (&v)[16], int lane) {
     return v[0];
 }
 
+// Work item -> (sample, tile origin, cout chunk).  The first n * nchunks items are the tiles that hold the reference
+// voxel of the shift (tile index p.ref_tile of every sample): they are the first items of the lowest-numbered CTAs,
+// which the hardware dispatches first and which never wait, so a CTA spinning on a shift value always waits on a CTA
+// that is already running -- whatever else shares the GPU.  The remaining items follow in (n, tile, chunk) order.
 __device__ __forceinline__ void decode_work(long long item, const TcParams& p, int& n, int& d0, int& h0, int& w0, int& chunk) {
-    chunk = (int)(item % p.nchunks);
-    long long t = item / p.nchunks;
-    n = (int)(t / p.tiles_per_n);
-    int r = (int)(t % p.tiles_per_n);
+    const long long nprod = (long long)p.n * p.nchunks;
+    int r;
+    if (item < nprod) {
+        chunk = (int)(item % p.nchunks);
+        n = (int)(item / p.nchunks);
+        r = p.ref_tile;
+    } else {
+        const long long idx = item - nprod;
+        chunk = (int)(idx % p.nchunks);
+        const long long t = idx / p.nchunks;
+        n = (int)(t / (p.tiles_per_n - 1));
+        r = (int)(t % (p.tiles_per_n - 1));
+        r += (r >= p.ref_tile);
+    }
     w0 = (r % p.tiles_w) * TW; r /= p.tiles_w;
     h0 = (r % p.tiles_h) * TH; r /= p.tiles_h;
     d0 = r * p.td;
@@ -228,8 +243,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
         // fp32 accumulator of a reference voxel of the sample.  It is produced by the CTA that owns the tile holding
         // that voxel (tile 0 of the sample = the lowest work item of its (n, chunk) group), published through global
         // memory as (bits | 1) into the host-zeroed `shift` array, and every other CTA spins on "non-zero" before its
-        // first tile of the group.  Progress: a waiter only ever waits on a strictly lower work item and each CTA
-        // walks its items in increasing order; the grid is <= #SMs with one CTA per SM, so all CTAs are resident.
+        // first tile of the group.  Progress: the producing tiles are the FIRST items of CTAs 0 .. n*nchunks-1
+        // (decode_work), a producing item never waits, and the hardware dispatches CTAs in index order -- so whenever
+        // a waiter is resident, the CTA it waits on already is, independent of what else occupies the GPU.
         const int rd = min(1, p.d - 1), rh = min(1, p.h - 1), rw = min(1, p.w - 1);
         const bool has_shift = p.shift != nullptr;
         const bool has_stats = p.stats != nullptr;
@@ -524,6 +540,7 @@ extern "C" int vs_conv3x3x3_tc(const void* x, const void* wtc, void* y, double* 
     p.td = td; p.bw = bw; p.bh = bh; p.bd = bd;
     p.tiles_d = (d + p.td - 1) / p.td;
     p.tiles_per_n = p.tiles_d * p.tiles_h * p.tiles_w;
+    p.ref_tile = (min(1, d - 1) / td) * tiles_h * tiles_w;        // voxel (1,1,1): h- and w-tile 0, d-tile 1/td
     p.kslices = gin == 8 ? 1 : gin / 16;
     p.work_items = (long long)n * p.tiles_per_n * p.nchunks;
     p.wpack = (const bf16*)wtc; p.y = (bf16*)y; p.stats = stats; p.shift = shift;
