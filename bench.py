@@ -145,7 +145,7 @@ def kernel_cost(name, key):
     """ALGORITHMIC (flops, bytes) of one launch, from its shape signature."""
     size = {0: 4, 1: 2}
     if name == "vs_conv3x3x3_fprop":
-        idt, odt, _, _, n, d, h, w, cin, cout = key
+        idt, odt, _, _, _, n, d, h, w, cin, cout = key
         vox = n * d * h * w
         return 2.0 * 27 * cin * cout * vox, vox * (cin * size[idt] + cout * size[odt])
     if name == "vs_conv3x3x3_dgrad":
@@ -165,7 +165,7 @@ def kernel_cost(name, key):
         dt, n, s, c = key
         return 0.0, 2.0 * n * s * c * size[dt]
     if name in ("vs_inorm_relu_bwd_reduce",):
-        dt, n, s, c = key
+        dt, n, s, c, _ = key
         return 0.0, 2.0 * n * s * c * size[dt]
     if name == "vs_inorm_relu_bwd_apply":
         dt, n, s, c = key

@@ -30,6 +30,9 @@ extern "C" {
 
 typedef enum { VS_OK = 0, VS_ERR_SHAPE = -1, VS_ERR_UNSUPPORTED = -2, VS_ERR_ALIGN = -3, VS_ERR_CUDA = -4 } vs_status;
 typedef enum { VS_F32 = 0, VS_BF16 = 1 } vs_dtype;
+/* flags: VS_FLAG_PREZEROED = the caller already zeroed the statistics / shift (or sums) words the call would
+ * otherwise memset -- the host side zeroes ONE arena per network pass instead of one memset per layer. */
+enum { VS_FLAG_PREZEROED = 1 };
 
 const char* vs_last_error_string(void);
 int vs_version(void);
@@ -72,13 +75,19 @@ int vs_pack_conv3_batched(const void* jobs_dev, int njobs, void* stream);
  * at voxel (1,1,1) of every (n, co) and subtracts that constant from the whole output channel
  * before statistics and storage: InstanceNorm is invariant to a per-(n,c) shift, and storing
  * deviations keeps bf16 precision on channels with |mean| >> sigma (VAE layers on masks).     */
-int vs_conv3x3x3_fprop(int in_dtype, int out_dtype, int in_planar, int out_planar,
+int vs_conv3x3x3_fprop(int in_dtype, int out_dtype, int in_planar, int out_planar, int flags,
                        const void* x, const float* wpk, const void* wtc, const float* bias, void* y, double* stats,
                        float* shift, int n, int d, int h, int w, int cin, int cout, void* stream);
 /* dgrad is the same contraction with the flipped/transposed pack (wd of vs_pack_conv3_weight):
- * dx = conv3(dy, wd), Cin/Cout swapped.  Provided as its own symbol for the binding's clarity. */
+ * dx = conv3(dy, wd), Cin/Cout swapped.  Provided as its own symbol for the binding's clarity.
+ * Fused epilogue (tensor-core path only, else VS_ERR_UNSUPPORTED): when sums_prev != NULL, dx is the gradient w.r.t.
+ * the activation of the PREVIOUS Conv3d+InstanceNorm+ReLU layer whose raw output is y_prev (NDHWC bf16, dx's shape)
+ * with statistics stats_prev; the call then also accumulates that layer's InstanceNorm-backward sums
+ * sums_prev[N][Cin][2] += (sum dx*mask, sum dx*mask*xhat) -- what vs_inorm_relu_bwd_reduce would compute in a
+ * separate pass over dx and y_prev.  sums_prev must be zeroed by the caller.                                   */
 int vs_conv3x3x3_dgrad(int in_dtype, int out_dtype, int out_planar,
                        const void* dy, const float* wdpk, const void* wdtc, void* dx,
+                       const void* y_prev, const double* stats_prev, double* sums_prev,
                        int n, int d, int h, int w, int cin, int cout, void* stream);
 /* dw[Cout,Cin,27] (+)= sum_v dy[v,co] * x[v+tap,ci]; db[Cout] (+)= sum_v dy (db may be NULL).
  * x may be planar fp32 (in_planar=1).  accumulate=0 overwrites.  workspace: fp32
@@ -108,9 +117,10 @@ int vs_k2s2_wgrad(int dtype, const void* coarse, const void* fine, float* dwt,
 /* a = relu((y-mean)*rstd) [+ skip]; mean/rstd derived from the fp64 stats[N][C][2] over `s` voxels.  */
 int vs_inorm_relu_apply(int dtype, const void* y, const double* stats, const void* skip, void* a,
                         int n, long long s, int c, void* stream);
-/* sums[N][C][2] (fp64) = (sum g*mask, sum g*mask*xhat) with mask = [y > mean]; zeroed by the call. */
+/* sums[N][C][2] (fp64) = (sum g*mask, sum g*mask*xhat) with mask = [y > mean]; zeroed by the call unless
+ * flags & VS_FLAG_PREZEROED. */
 int vs_inorm_relu_bwd_reduce(int dtype, const void* g, const void* y, const double* stats, double* sums,
-                             int n, long long s, int c, void* stream);
+                             int n, long long s, int c, int flags, void* stream);
 /* dy = rstd * (g*mask - sums0/s - xhat * sums1/s)                                         */
 int vs_inorm_relu_bwd_apply(int dtype, const void* g, const void* y, const double* stats, const double* sums,
                             void* dy, int n, long long s, int c, void* stream);

@@ -85,3 +85,46 @@ def test_tc_wgrad(case):
     assert err < 2e-3 * scale, "tc wgrad max err %.3e (scale %.3e)" % (err, scale)
     dw2, _ = ops.conv3_wgrad(xd, gyd, dims, cin, cout, dw=dw.clone(), accumulate=True)
     assert (dw2.cpu() - 2 * want).abs().max().item() < 4e-3 * scale
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_tc_dgrad_fused_norm_backward_reduction(case):
+    """dgrad epilogue that also accumulates the previous layer's InstanceNorm+ReLU backward sums
+    (sum g*mask, sum g*mask*xhat) against the standalone reduction kernel run on the dgrad's own output,
+    and the resulting dy against torch autograd of relu(instance_norm(y_prev))."""
+    n, d, h, w, cin, cout = case
+    torch.manual_seed(sum(case) + 2)
+    dims = (n, d, h, w)
+    wt = torch.randn(cout, cin, 3, 3, 3) * 0.1
+    wd = wt.to(DEV)
+    _, wdg = ops.pack_conv3_weight(wd)
+    wdtc = ops.pack_conv3_weight_tc(wd, dgrad=True)
+    gy = torch.randn(n, cout, d, h, w).bfloat16().float()
+    yprev = (torch.randn(n, cin, d, h, w) * 1.5 + 0.3).bfloat16().float()       # previous layer's raw output
+    stats = torch.stack([yprev.double().sum((2, 3, 4)), (yprev.double() ** 2).sum((2, 3, 4))], -1).to(DEV)
+    ypd, gyd = to_ndhwc(yprev), to_ndhwc(gy)
+    assert ops.dgrad_can_fuse_reduce(gyd, cin, cout, torch.bfloat16, False, wdtc)
+    arena = ops.StatsArena(n * cin * 2, DEV)
+    sums = arena.take(n * cin * 2).view(n, cin, 2)
+    dx = ops.conv3_dgrad(gyd, wdg, dims, cin, cout, torch.bfloat16, wdtc=wdtc, prev=(ypd, stats, sums))
+    dx_plain = ops.conv3_dgrad(gyd, wdg, dims, cin, cout, torch.bfloat16, wdtc=wdtc)
+    torch.cuda.synchronize()
+    assert torch.equal(dx, dx_plain), "the fused epilogue must not change the dgrad output"
+    # reference sums from the standalone kernel on the same dx
+    import vae_segmentation_b200._cabi as cabi
+    sums_ref = torch.empty(n, cin, 2, device=DEV, dtype=torch.float64)
+    cabi.call("vs_inorm_relu_bwd_reduce", cabi.VS_BF16, dx.data_ptr(), ypd.data_ptr(), stats.data_ptr(), sums_ref.data_ptr(),
+              n, d * h * w, cin, 0, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    scale = sums_ref.abs().max().item() + 1e-6
+    # fp32 per-thread partial sums (a few hundred terms) vs the standalone kernel's fp64 accumulation
+    assert (sums - sums_ref).abs().max().item() < 2e-5 * scale + 1e-4, \
+        "fused sums differ: %.3e (scale %.3e)" % ((sums - sums_ref).abs().max().item(), scale)
+    dy_fused = ops.inorm_relu_bwd(dx, ypd, stats, sums=sums, reduced=True)
+    dy_split = ops.inorm_relu_bwd(dx, ypd, stats)
+    yr = yprev.clone().requires_grad_()
+    F.relu(F.instance_norm(yr, eps=1e-5)).backward(from_ndhwc(dx))
+    ref = yr.grad
+    gscale = ref.abs().max().item()
+    assert (from_ndhwc(dy_fused) - ref).abs().max().item() < 2e-2 * gscale
+    assert (dy_fused.float() - dy_split.float()).abs().max().item() < 1e-2 * gscale

@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libvaeseg_b200.so")
 
 VS_F32, VS_BF16 = 0, 1
+VS_FLAG_PREZEROED = 1
 TGT_TENSOR, TGT_BINARIZE, TGT_CONFIDENT, TGT_LABEL, TGT_ARGMAX = 0, 1, 2, 3, 4
 
 _P, _I, _L, _F, _Z = c_void_p, c_int, c_longlong, c_float, c_size_t
@@ -24,15 +25,15 @@ _SIGNATURES = {
     "vs_conv3_tc_pack_bytes": [_I, _I, _I],
     "vs_pack_conv3_weight_tc": [_P, _P, _I, _I, _I, _P],
     "vs_pack_conv3_batched": [_P, _I, _P],
-    "vs_conv3x3x3_fprop": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
-    "vs_conv3x3x3_dgrad": [_I, _I, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "vs_conv3x3x3_fprop": [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "vs_conv3x3x3_dgrad": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "vs_conv3_wgrad_workspace_bytes": [_I, _I, _I, _I, _I, _I],
     "vs_conv3x3x3_wgrad": [_I, _I, _P, _P, _P, _P, _P, _Z, _I, _I, _I, _I, _I, _I, _I, _P],
     "vs_k2s2_gather": [_I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "vs_k2s2_scatter": [_I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "vs_k2s2_wgrad": [_I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "vs_inorm_relu_apply": [_I, _P, _P, _P, _P, _I, _L, _I, _P],
-    "vs_inorm_relu_bwd_reduce": [_I, _P, _P, _P, _P, _I, _L, _I, _P],
+    "vs_inorm_relu_bwd_reduce": [_I, _P, _P, _P, _P, _I, _L, _I, _I, _P],
     "vs_inorm_relu_bwd_apply": [_I, _P, _P, _P, _P, _P, _I, _L, _I, _P],
     "vs_add_inplace": [_I, _P, _P, _L, _P],
     "vs_softmax2_fwd": [_P, _P, _I, _L, _P],

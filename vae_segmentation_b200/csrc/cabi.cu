@@ -32,7 +32,8 @@ extern "C" int vs_conv3x3x3_fprop_direct(int in_dtype, int out_dtype, int in_pla
 extern "C" int vs_conv3_shift_internal(int in_dtype, int in_planar, const void* x, const float* wpk, float* shift, int n,
                                        int d, int h, int w, int cin, int cout, void* stream);
 #ifdef VS_WITH_TCGEN05
-extern "C" int vs_conv3x3x3_tc(const void* x, const void* wtc, void* y, double* stats, float* shift, int n, int d,
+extern "C" int vs_conv3x3x3_tc(const void* x, const void* wtc, void* y, double* stats, float* shift, int prezeroed,
+                               const void* yprev, const double* pstats, double* psums, int n, int d,
                                int h, int w, int gin, int gout, void* stream);
 extern "C" size_t vs_conv3_tc_pack_bytes(int cin, int cout, int dgrad);
 #endif
@@ -51,31 +52,36 @@ extern "C" int vs_has_tcgen05(void) {
 #endif
 }
 
-extern "C" int vs_conv3x3x3_fprop(int in_dtype, int out_dtype, int in_planar, int out_planar, const void* x,
+extern "C" int vs_conv3x3x3_fprop(int in_dtype, int out_dtype, int in_planar, int out_planar, int flags, const void* x,
                                   const float* wpk, const void* wtc, const float* bias, void* y, double* stats,
                                   float* shift, int n, int d, int h, int w, int cin, int cout, void* stream) {
+    const int prezeroed = (flags & VS_FLAG_PREZEROED) != 0;
 #ifdef VS_WITH_TCGEN05
     if (wtc != nullptr && in_dtype == VS_BF16 && out_dtype == VS_BF16 && !in_planar && !out_planar && bias == nullptr &&
         tc_eligible(cin, cout)) {
         // the tensor-core kernel derives and publishes the shift itself (no separate launch)
-        return vs_conv3x3x3_tc(x, wtc, y, stats, shift, n, d, h, w, cin, cout, stream);
+        return vs_conv3x3x3_tc(x, wtc, y, stats, shift, prezeroed, nullptr, nullptr, nullptr, n, d, h, w, cin, cout, stream);
     }
 #else
     (void)wtc;
 #endif
-    return vs_conv3x3x3_fprop_direct(in_dtype, out_dtype, in_planar, out_planar, x, wpk, bias, y, stats, shift, n, d, h,
-                                     w, cin, cout, stream);
+    return vs_conv3x3x3_fprop_direct(in_dtype, out_dtype, in_planar, out_planar | (prezeroed ? 2 : 0), x, wpk, bias, y, stats,
+                                     shift, n, d, h, w, cin, cout, stream);
 }
 
 extern "C" int vs_conv3x3x3_dgrad(int in_dtype, int out_dtype, int out_planar, const void* dy, const float* wdpk,
-                                  const void* wdtc, void* dx, int n, int d, int h, int w, int cin, int cout, void* stream) {
+                                  const void* wdtc, void* dx, const void* y_prev, const double* stats_prev,
+                                  double* sums_prev, int n, int d, int h, int w, int cin, int cout, void* stream) {
     // dx[.., cin] = conv3(dy[.., cout], wd[27][cout][cin]): the fprop contraction with channels swapped
 #ifdef VS_WITH_TCGEN05
     if (wdtc != nullptr && in_dtype == VS_BF16 && out_dtype == VS_BF16 && !out_planar && tc_eligible(cout, cin))
-        return vs_conv3x3x3_tc(dy, wdtc, dx, nullptr, nullptr, n, d, h, w, cout, cin, stream);
+        return vs_conv3x3x3_tc(dy, wdtc, dx, nullptr, nullptr, 0, y_prev, stats_prev, sums_prev, n, d, h, w, cout, cin, stream);
 #else
     (void)wdtc;
 #endif
+    VS_REQUIRE(sums_prev == nullptr, VS_ERR_UNSUPPORTED,
+               "conv3 dgrad: the fused norm-backward reduction exists on the tensor-core path only (bf16 NDHWC, Cout in "
+               "{8, 16k}, Cin %% 8 == 0); call vs_inorm_relu_bwd_reduce instead");
     return vs_conv3x3x3_fprop_direct(in_dtype, out_dtype, 0, out_planar, dy, wdpk, nullptr, dx, nullptr, nullptr, n, d, h, w,
                                      cout, cin, stream);
 }

@@ -369,6 +369,8 @@ int launch_conv3(const void* x, const float* wpk, const float* bias, void* y, do
 int conv3_common(int in_dtype, int out_dtype, int in_planar, int out_planar, const void* x, const float* wpk,
                  const float* bias, void* y, double* stats, float* shift, int n, int d, int h, int w, int cin, int cout,
                  void* stream) {
+    const bool prezeroed = (out_planar & 2) != 0;       // internal: bit 1 of out_planar = statistics already zeroed
+    out_planar &= 1;
     VS_REQUIRE(n > 0 && d > 0 && h > 0 && w > 0 && cin > 0 && cout > 0, VS_ERR_SHAPE, "conv3: bad shape");
     VS_REQUIRE(x && wpk && y, VS_ERR_SHAPE, "conv3: null pointer");
     VS_REQUIRE(vs_aligned16(x) && vs_aligned16(y) && vs_aligned16(wpk), VS_ERR_ALIGN, "conv3: pointers must be 16B aligned");
@@ -377,7 +379,7 @@ int conv3_common(int in_dtype, int out_dtype, int in_planar, int out_planar, con
     if (out_planar) VS_REQUIRE(out_dtype == VS_F32, VS_ERR_UNSUPPORTED, "conv3: planar output is fp32 only");
     cudaStream_t st = (cudaStream_t)stream;
     ConvDims p = make_dims(n, d, h, w, cin, cout);
-    if (stats) VS_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * n * cout, st), "conv3 stats memset");
+    if (stats && !prezeroed) VS_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * n * cout, st), "conv3 stats memset");
     if (in_planar) {
         VS_REQUIRE(!out_planar, VS_ERR_UNSUPPORTED, "conv3: planar->planar unsupported");
         if (out_dtype == VS_F32) return launch_conv3<float, float, true, false>(x, wpk, bias, y, stats, shift, p, st);

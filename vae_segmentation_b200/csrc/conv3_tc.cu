@@ -49,6 +49,12 @@ struct TcParams {
     bf16* y;
     double* stats;          // [n][cout][2] or null
     float* shift;           // [n][cout] or null; zeroed by the host, published in-kernel (see epilogue)
+    // dgrad only -- fused InstanceNorm+ReLU backward reduction of the PREVIOUS layer (whose output gradient this
+    // launch produces): psums[n][cout][2] += (sum g*mask, sum g*mask*xhat) with xhat from yprev / pstats.
+    const bf16* yprev;      // raw conv output of the previous layer, same shape as y, or null
+    const double* pstats;   // its (sum, sumsq) statistics [n][cout][2]
+    double* psums;          // zeroed by the caller
+    double inv_s;           // 1 / (d*h*w)
 };
 
 // Column sums of a 32-lane x 16-value register tile in 31 shuffles: afterwards v[0] of lane L holds the
@@ -115,7 +121,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
     uint64_t* tempty_bar = tfull_bar + NBUF;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + NBUF);
     float* sshift = reinterpret_cast<float*>(tmem_slot + 4);          // [NC]
-    double* sstat = reinterpret_cast<double*>(sshift + NC);           // [NC][2]
+    float* smean = sshift + NC;                                       // [NC]  (fused norm-backward reduction)
+    float* srstd = smean + NC;                                        // [NC]
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);      // warp-uniform for the compiler
     const int lane = threadIdx.x & 31;
@@ -221,16 +228,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
         for (int c = 0; c < NC / 16; ++c)
 #pragma unroll
             for (int k = 0; k < 16; ++k) { rs[c][k] = 0.f; rq[c][k] = 0.f; }
+        const bool fused = p.psums != nullptr;
+        double* const sout = fused ? p.psums : p.stats;
         auto flush_stats = [&]() {
-            if (p.stats != nullptr && stat_n >= 0) {
+            if (sout != nullptr && stat_n >= 0) {
 #pragma unroll
                 for (int c = 0; c < NC / 16; ++c) {
                     const float s1 = transpose_reduce16(rs[c], lane);
                     const float s2 = transpose_reduce16(rq[c], lane);
                     const int co = stat_chunk * NC + c * 16 + lane;
                     if (lane < 16 && co < p.cout) {
-                        atomicAdd(&p.stats[((long long)stat_n * p.cout + co) * 2], (double)s1);
-                        atomicAdd(&p.stats[((long long)stat_n * p.cout + co) * 2 + 1], (double)s2);
+                        atomicAdd(&sout[((long long)stat_n * p.cout + co) * 2], (double)s1);
+                        atomicAdd(&sout[((long long)stat_n * p.cout + co) * 2 + 1], (double)s2);
                     }
 #pragma unroll
                     for (int k = 0; k < 16; ++k) { rs[c][k] = 0.f; rq[c][k] = 0.f; }
@@ -250,6 +259,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
         const bool has_shift = p.shift != nullptr;
         const bool has_stats = p.stats != nullptr;
         const uint32_t sshift_addr = smem_u32(sshift);
+        const uint32_t smean_addr = smem_u32(smean), srstd_addr = smem_u32(srstd);
         const int ref_row = rh * TW + rw;
         const int ref_d0 = (rd / p.td) * p.td;                   // first plane of the work item that owns the reference voxel
         for (long long item = blockIdx.x; item < p.work_items; item += gridDim.x) {
@@ -259,6 +269,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
             if (n != stat_n || chunk != stat_chunk) {
                 flush_stats();
                 stat_n = n; stat_chunk = chunk;
+                if (fused) {
+                    asm volatile("bar.sync 1, 128;" ::: "memory");       // everyone is done with the previous group's constants
+                    if (et < NC) {
+                        float mu = 0.f, rs_ = 0.f;
+                        if (co0 + et < p.cout) in_mean_rstd(p.pstats + ((long long)n * p.cout + co0 + et) * 2, p.inv_s, mu, rs_);
+                        smean[et] = mu; srstd[et] = rs_;
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
                 if (p.shift != nullptr) {
                     asm volatile("bar.sync 1, 128;" ::: "memory");       // everyone is done with the previous group's sshift
                     if (d0 == ref_d0 && h0 == 0 && w0 == 0) {
@@ -304,7 +323,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
             const bool rc_ok = gh < p.h && gw < p.w;
             for (int j = 0; j < jmax; ++j) {
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (buf * TD + j) * NC;
-                bf16* py = p.y + (((long long)n * p.d + d0 + j) * p.h + gh) * (long long)p.w * p.cout + (long long)gw * p.cout + co0;
+                const long long yoff = (((long long)n * p.d + d0 + j) * p.h + gh) * (long long)p.w * p.cout + (long long)gw * p.cout + co0;
+                bf16* py = p.y + yoff;
 #pragma unroll
                 for (int c16 = 0; c16 < NC / 16; ++c16) {
                     uint32_t r[16];
@@ -344,6 +364,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
                     if (has_stats) {
 #pragma unroll
                         for (int k = 0; k < 16; ++k) { rs[c16][k] += v[k]; rq[c16][k] = fmaf(v[k], v[k], rq[c16][k]); }
+                    }
+                    if (fused) {
+                        // g = this launch's output (as stored, i.e. rounded to bf16); mask / xhat from the previous
+                        // layer's raw output at the same voxel -- exactly what inorm_relu_bwd_reduce_kernel computes
+#pragma unroll
+                        for (int h8 = 0; h8 < 2; ++h8) {
+                            float yv[8];
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) yv[k] = 0.f;
+                            if (rc_ok && co0 + c16 * 16 + h8 * 8 < p.cout) Store<bf16>::ld8(p.yprev + yoff + c16 * 16 + h8 * 8, yv);
+#pragma unroll
+                            for (int k4 = 0; k4 < 2; ++k4) {
+                                const float4 mu = lds128(smean_addr + (c16 * 16 + h8 * 8 + k4 * 4) * 4);
+                                const float4 rr = lds128(srstd_addr + (c16 * 16 + h8 * 8 + k4 * 4) * 4);
+                                const float mus[4] = {mu.x, mu.y, mu.z, mu.w}, rrs[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const int kk = h8 * 8 + k4 * 4 + k;
+                                    const float xh = (yv[k4 * 4 + k] - mus[k]) * rrs[k];
+                                    const float gq = __bfloat162float(__float2bfloat16_rn(v[kk]));
+                                    const float gm = xh > 0.f ? gq : 0.f;
+                                    rs[c16][kk] += gm;
+                                    rq[c16][kk] = fmaf(gm, xh, rq[c16][kk]);
+                                }
+                            }
+                        }
                     }
                 }
             }
@@ -490,7 +536,8 @@ __global__ void __launch_bounds__(256) pack_batched_kernel(const vs_pack_job* __
 }
 
 // y[n,d,h,w,gout] = conv3(x[n,d,h,w,gin], wtc) on the tensor cores; bf16 NDHWC in and out.
-extern "C" int vs_conv3x3x3_tc(const void* x, const void* wtc, void* y, double* stats, float* shift, int n, int d,
+extern "C" int vs_conv3x3x3_tc(const void* x, const void* wtc, void* y, double* stats, float* shift, int prezeroed,
+                               const void* yprev, const double* pstats, double* psums, int n, int d,
                                int h, int w, int gin, int gout, void* stream) {
     VS_REQUIRE(x && wtc && y, VS_ERR_SHAPE, "conv3_tc: null pointer");
     VS_REQUIRE((gin == 8 || (gin % 16 == 0 && gin >= 16)) && gout % 8 == 0 && gout >= 8, VS_ERR_UNSUPPORTED,
@@ -544,9 +591,17 @@ extern "C" int vs_conv3x3x3_tc(const void* x, const void* wtc, void* y, double* 
     p.kslices = gin == 8 ? 1 : gin / 16;
     p.work_items = (long long)n * p.tiles_per_n * p.nchunks;
     p.wpack = (const bf16*)wtc; p.y = (bf16*)y; p.stats = stats; p.shift = shift;
+    p.yprev = (const bf16*)yprev; p.pstats = pstats; p.psums = psums; p.inv_s = 1.0 / ((double)d * h * w);
+    if (psums != nullptr) {
+        VS_REQUIRE(yprev && pstats && stats == nullptr && shift == nullptr, VS_ERR_SHAPE,
+                   "conv3_tc: the fused norm-backward reduction needs y_prev + stats_prev and no forward statistics");
+        VS_REQUIRE(vs_aligned16(yprev), VS_ERR_ALIGN, "conv3_tc: y_prev must be 16B aligned");
+    }
     // zero the statistics and the shift/flag words (one memset when the caller laid them out back to back)
     const size_t stat_bytes = sizeof(double) * 2 * (size_t)n * gout, shift_bytes = sizeof(float) * (size_t)n * gout;
-    if (stats && shift && reinterpret_cast<char*>(shift) == reinterpret_cast<char*>(stats) + stat_bytes) {
+    if (prezeroed) {
+        // the caller zeroed statistics and shift words (one arena memset per network pass instead of one per layer)
+    } else if (stats && shift && reinterpret_cast<char*>(shift) == reinterpret_cast<char*>(stats) + stat_bytes) {
         VS_CUDA(cudaMemsetAsync(stats, 0, stat_bytes + shift_bytes, st), "conv3_tc stats+shift memset");
     } else {
         if (stats) VS_CUDA(cudaMemsetAsync(stats, 0, stat_bytes, st), "conv3_tc stats memset");

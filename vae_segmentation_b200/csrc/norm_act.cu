@@ -225,11 +225,11 @@ extern "C" int vs_inorm_relu_apply(int dtype, const void* y, const double* stats
 }
 
 extern "C" int vs_inorm_relu_bwd_reduce(int dtype, const void* g, const void* y, const double* stats, double* sums,
-                                        int n, long long s, int c, void* stream) {
+                                        int n, long long s, int c, int flags, void* stream) {
     int rc = check_norm(g, y, n, s, c, "inorm_relu_bwd_reduce");
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    VS_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * n * c, st), "inorm bwd memset");
+    if (!(flags & VS_FLAG_PREZEROED)) VS_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * n * c, st), "inorm bwd memset");
     const int lanes = NT / (c / 8);
     long long blocks = (s + (long long)lanes * 8 - 1) / ((long long)lanes * 8);
     dim3 grid((unsigned)max(1LL, min(blocks, (long long)vs_sm_count() * 4)), n);

@@ -26,6 +26,8 @@ C3IN, K2DOWN, K2UP, HEAD = "c3in", "k2down", "k2up", "head"
 # direct kernel remains for the fp32 check mode and the Cin in {1,2} / Cout = 2 layers.  VAESEG_NO_TC=1 forces
 # the direct kernel everywhere (A/B measurements).
 USE_TENSOR_CORES = os.environ.get("VAESEG_NO_TC", "0") != "1"
+# VAESEG_NO_FUSE_REDUCE=1 keeps the InstanceNorm-backward reduction a separate pass (A/B measurements, parity tests)
+FUSE_BWD_REDUCE = os.environ.get("VAESEG_NO_FUSE_REDUCE", "0") != "1"
 
 # tools/precision_probe*.py only: names of tensor classes to round through bf16 while running the fp32
 # check mode ("y", "a", "g", "dy", "k2"), to attribute bf16-mode error to a storage point.  Empty in production.
@@ -219,12 +221,14 @@ def program_forward(layers, tensors, x, dims, dtype, cache, record=True):
     tape = []
     slots = {}
     cur = x
+    # statistics + shift words of every Conv+InstanceNorm layer, zeroed by ONE launch (not one memset per layer)
+    arena = ops.StatsArena(sum(ops.stats_words(n, L.cout) for L in layers if L.kind == C3IN), x.device)
     for L in layers:
         if L.kind == C3IN:
             wf, wd, wtc, wdtc = cache.conv3(tensors[L.wi], tc=(dtype == torch.bfloat16))
             # the conv bias is a no-op ahead of InstanceNorm(affine=False): skipped
             y, stats = ops.conv3_fprop(cur, wf, None, (n, d, h, w), L.cin, L.cout, dtype, in_planar=L.in_planar,
-                                       wtc=None if L.in_planar else wtc)
+                                       wtc=None if L.in_planar else wtc, arena=arena)
             skip = slots[L.skip_from] if L.skip_from is not None else None
             y = _sim(y, "y")
             a = _sim(ops.inorm_relu_apply(y, stats, skip), "a")
@@ -266,6 +270,28 @@ def program_backward(tape, g, dtype, need, grads, param_refs, need_input_grad):
     the tensor handed back to autograd (None when accumulated in place into .grad).
     Returns the gradient w.r.t. the program input (or None)."""
     pending = {}                     # slot name -> gradient arriving through an additive skip
+    # InstanceNorm-backward sums of every Conv+InstanceNorm layer: one zero-filled arena; where the gradient of a
+    # layer's activation is produced by a tensor-core dgrad (and no skip gradient is added to it afterwards) the
+    # reduction is fused into that dgrad's epilogue and only the apply pass remains.
+    arena = ops.StatsArena(sum(e[4][0] * e[0].cout * 2 for e in tape if e[0].kind == C3IN), g.device)
+    sums_of = {}
+    fused = set()
+
+    def fuse_prev(idx, dy_like, cin, cout, wdtc):
+        """(y_prev, stats_prev, sums_prev) if the dgrad of tape[idx] may also reduce for tape[idx-1], else None."""
+        if idx == 0 or SIMULATE_BF16 or not FUSE_BWD_REDUCE:
+            return None
+        Lp = tape[idx - 1][0]
+        if Lp.kind != C3IN or (Lp.save_as is not None and Lp.save_as in pending):
+            return None
+        if not ops.dgrad_can_fuse_reduce(dy_like, cin, cout, dtype, False, wdtc):
+            return None
+        fused.add(idx - 1)
+        return tape[idx - 1][2], tape[idx - 1][3], sums_of[idx - 1]
+
+    for idx, e in enumerate(tape):
+        if e[0].kind == C3IN:
+            sums_of[idx] = arena.take(e[4][0] * e[0].cout * 2).view(e[4][0], e[0].cout, 2)
     for idx in range(len(tape) - 1, -1, -1):
         L, x_in, y, stats, dims, wd, wt = tape[idx]
         first = idx == 0
@@ -275,7 +301,7 @@ def program_backward(tape, g, dtype, need, grads, param_refs, need_input_grad):
         if L.kind == C3IN:
             if L.skip_from is not None:
                 pending[L.skip_from] = g
-            dy = _sim(ops.inorm_relu_bwd(g, y, stats), "dy")
+            dy = _sim(ops.inorm_relu_bwd(g, y, stats, sums=sums_of[idx], reduced=idx in fused), "dy")
             if need[L.wi]:
                 tgt, acc = _grad_target(param_refs[L.wi], True)
                 def run_wgrad(L=L, x_in=x_in, dy=dy, dims=dims, tgt=tgt, acc=acc):
@@ -294,7 +320,8 @@ def program_backward(tape, g, dtype, need, grads, param_refs, need_input_grad):
                 # exactly zero: the bias cancels in InstanceNorm
                 tgt, acc = _grad_target(param_refs[L.bi], True)
                 grads[L.bi] = None if acc else torch.zeros(L.cout, device=dy.device, dtype=torch.float32)
-            g = _sim(ops.conv3_dgrad(dy, wd[0], dims, L.cin, L.cout, dtype, out_planar=L.in_planar, wdtc=wd[1]), "g") \
+            g = _sim(ops.conv3_dgrad(dy, wd[0], dims, L.cin, L.cout, dtype, out_planar=L.in_planar, wdtc=wd[1],
+                                     prev=None if L.in_planar else fuse_prev(idx, dy, L.cin, L.cout, wd[1])), "g") \
                 if want_dx else None
         elif L.kind == K2DOWN:
             # dims are the coarse (output) dims; g is the coarse gradient
@@ -333,7 +360,8 @@ def program_backward(tape, g, dtype, need, grads, param_refs, need_input_grad):
                     _wgrad_async(run_head_wgrad, acc, x_in, dl8)
                 if need[L.wi] or need[L.bi]:
                     _hand_back(grads, need, L.wi, L.bi, tw, tb, acc)
-                g = ops.conv3_dgrad(dl8, None, dims, L.cin, 8, dtype, wdtc=wd[1]) if want_dx else None
+                g = ops.conv3_dgrad(dl8, None, dims, L.cin, 8, dtype, wdtc=wd[1],
+                                    prev=fuse_prev(idx, dl8, L.cin, 8, wd[1])) if want_dx else None
                 continue
             dlogits = _sim(ops.softmax2_bwd(g, probs, dims, dtype), "dy")
             if need[L.wi] or need[L.bi]:

@@ -6,7 +6,7 @@ kernels from libvaeseg_b200.so.  CPU tensors are rejected: there is no fallback 
 import torch
 
 from . import _cabi
-from ._cabi import VS_BF16, VS_F32
+from ._cabi import VS_BF16, VS_F32, VS_FLAG_PREZEROED
 
 _DT = {torch.float32: VS_F32, torch.bfloat16: VS_BF16}
 
@@ -74,10 +74,32 @@ def pack_conv3_batched(jobs_dev, njobs):
     _cabi.call("vs_pack_conv3_batched", _p(jobs_dev), int(njobs), _stream())
 
 
+def stats_words(n, cout):
+    """fp64 words of one layer's statistics + shift block (see conv3_fprop / StatsArena)."""
+    return n * cout * 2 + (n * cout + 1) // 2
+
+
+class StatsArena(object):
+    """One zero-filled fp64 buffer carved into per-layer (statistics, shift) or (sums) blocks: a network pass zeroes
+    it with ONE launch instead of one memset node per layer on the critical path."""
+
+    def __init__(self, words, device):
+        self.buf = torch.zeros(max(int(words), 1), device=device, dtype=torch.float64)
+        self.off = 0
+
+    def take(self, words):
+        if self.off + words > self.buf.numel():
+            raise RuntimeError("vaeseg_b200: StatsArena exhausted")
+        out = self.buf[self.off:self.off + words]
+        self.off += words
+        return out
+
+
 def conv3_fprop(x, wf, bias, dims, cin, cout, out_dtype, in_planar=False, out_planar=False, want_stats=True,
-                shifted=None, wtc=None):
+                shifted=None, wtc=None, arena=None):
     """dims = (N, D, H, W).  Returns (y, stats).  `shifted` (default: same as want_stats) subtracts the
-    per-(n,co) reference-voxel value from the output (InstanceNorm-invariant, see the header)."""
+    per-(n,co) reference-voxel value from the output (InstanceNorm-invariant, see the header).  `arena`: a
+    zero-filled StatsArena that supplies the statistics / shift words (the call then skips its memset)."""
     n, d, h, w = dims
     dev = x.device
     if out_planar:
@@ -87,30 +109,45 @@ def conv3_fprop(x, wf, bias, dims, cin, cout, out_dtype, in_planar=False, out_pl
     if shifted is None:
         shifted = want_stats
     stats = shift = None
+    flags = 0
     if want_stats and shifted:
         # one allocation, statistics first and the shift words right behind them: the library zeroes both with a
         # single memset (the tensor-core kernel publishes the shift through those words, see conv3_tc.cu)
-        buf = torch.empty(n * cout * 2 + (n * cout + 1) // 2, device=dev, dtype=torch.float64)
+        if arena is not None:
+            buf = arena.take(stats_words(n, cout))
+            flags = VS_FLAG_PREZEROED
+        else:
+            buf = torch.empty(stats_words(n, cout), device=dev, dtype=torch.float64)
         stats = buf[:n * cout * 2].view(n, cout, 2)
         shift = buf[n * cout * 2:].view(torch.float32)[:n * cout].view(n, cout)
     elif want_stats:
         stats = torch.empty(n, cout, 2, device=dev, dtype=torch.float64)
     elif shifted:
         shift = torch.empty(n, cout, device=dev, dtype=torch.float32)
-    _cabi.call("vs_conv3x3x3_fprop", _dt(x), _dt(y), int(in_planar), int(out_planar), _p(x), _p(_f32(wf, "wf")), _p(wtc),
+    _cabi.call("vs_conv3x3x3_fprop", _dt(x), _dt(y), int(in_planar), int(out_planar), flags, _p(x), _p(_f32(wf, "wf")), _p(wtc),
                _p(_f32(bias, "bias")), _p(y), _p(stats), _p(shift), n, d, h, w, cin, cout, _stream())
     return y, stats
 
 
-def conv3_dgrad(dy, wd, dims, cin, cout, out_dtype, out_planar=False, wdtc=None):
-    """dy: [N,D,H,W,Cout] -> dx [N,D,H,W,Cin] (or planar fp32 [N,Cin,D,H,W])."""
+def dgrad_can_fuse_reduce(dy, cin, cout, out_dtype, out_planar, wdtc):
+    """Whether conv3_dgrad takes the tensor-core path for this call, i.e. may fuse the previous layer's
+    InstanceNorm-backward reduction into its epilogue."""
+    gin, gout = cout, cin
+    return (wdtc is not None and dy.dtype == torch.bfloat16 and out_dtype == torch.bfloat16 and not out_planar
+            and (gin == 8 or (gin >= 16 and gin % 16 == 0)) and gout >= 8 and gout % 8 == 0)
+
+
+def conv3_dgrad(dy, wd, dims, cin, cout, out_dtype, out_planar=False, wdtc=None, prev=None):
+    """dy: [N,D,H,W,Cout] -> dx [N,D,H,W,Cin] (or planar fp32 [N,Cin,D,H,W]).  prev = (y_prev, stats_prev,
+    sums_prev): also accumulate the previous layer's norm-backward sums (tensor-core path only; sums pre-zeroed)."""
     n, d, h, w = dims
+    yp, sp, sums = prev if prev is not None else (None, None, None)
     if out_planar:
         dx = torch.empty(n, cin, d, h, w, device=dy.device, dtype=torch.float32)
     else:
         dx = torch.empty(n, d, h, w, cin, device=dy.device, dtype=out_dtype)
     _cabi.call("vs_conv3x3x3_dgrad", _dt(dy), _dt(dx), int(out_planar), _p(dy), _p(_f32(wd, "wd")), _p(wdtc), _p(dx),
-               n, d, h, w, cin, cout, _stream())
+               _p(yp), _p(sp), _p(sums), n, d, h, w, cin, cout, _stream())
     return dx
 
 
@@ -162,12 +199,16 @@ def inorm_relu_apply(y, stats, skip=None):
     return a
 
 
-def inorm_relu_bwd(g, y, stats):
-    """Returns dy (gradient w.r.t. the raw conv output)."""
+def inorm_relu_bwd(g, y, stats, sums=None, reduced=False):
+    """Returns dy (gradient w.r.t. the raw conv output).  `sums`: pre-zeroed fp64 [N,C,2] block (StatsArena);
+    reduced=True: `sums` already holds the reduction (fused into the producing dgrad), only the apply pass runs."""
     n, c = y.shape[0], y.shape[-1]
     s = y.numel() // (n * c)
-    sums = torch.empty(n, c, 2, device=y.device, dtype=torch.float64)
-    _cabi.call("vs_inorm_relu_bwd_reduce", _dt(y), _p(g), _p(y), _p(stats), _p(sums), n, s, c, _stream())
+    if not reduced:
+        flags = VS_FLAG_PREZEROED if sums is not None else 0
+        if sums is None:
+            sums = torch.empty(n, c, 2, device=y.device, dtype=torch.float64)
+        _cabi.call("vs_inorm_relu_bwd_reduce", _dt(y), _p(g), _p(y), _p(stats), _p(sums), n, s, c, flags, _stream())
     dy = torch.empty_like(y)
     _cabi.call("vs_inorm_relu_bwd_apply", _dt(y), _p(g), _p(y), _p(stats), _p(sums), _p(dy), n, s, c, _stream())
     return dy
