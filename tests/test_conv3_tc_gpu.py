@@ -64,7 +64,9 @@ def test_tc_fprop_and_dgrad(case):
     assert (y2.float() - y.float()).abs().max().item() < 1e-2 * scale
 
 
-@pytest.mark.parametrize("case", CASES + [(2, 8, 32, 16, 8, 8), (1, 4, 16, 8, 16, 128), (1, 5, 6, 7, 128, 256)])
+@pytest.mark.parametrize("case", CASES + [(2, 8, 32, 16, 8, 8), (1, 4, 16, 8, 16, 128), (1, 5, 6, 7, 128, 256),
+                                          (1, 1, 5, 5, 8, 8), (1, 3, 3, 3, 8, 8), (2, 2, 17, 9, 32, 8), (1, 13, 33, 17, 16, 8),
+                                          (1, 24, 24, 24, 8, 8)])
 def test_tc_wgrad(case):
     """tcgen05 backward-filter (voxel = K, MN-major operands) against torch autograd on the same bf16 operands;
     ragged extents exercise the TMA zero fill of BOTH operands, Cout > 64 the 64-row chunks, accumulate=True the

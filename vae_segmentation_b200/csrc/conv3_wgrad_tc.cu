@@ -220,6 +220,177 @@ int launch_wg(const CUtensorMap& xmap, const CUtensorMap& dymap, const WgParams&
     return VS_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Cout = 8 variant ("d-shift"): with one real 8-channel plane of dy, seven of the eight M groups of the M = 64
+// operand above are wasted.  Here the M groups are THREE D-SHIFTED COPIES of the dy tile instead (M-group stride =
+// one staged d-plane):   D[(m, co), (kw, ci)] += sum_v dy[v + m*e_d][co] * x[v + (1, kh-1, kw-1)][ci]
+// which, with u = v + m*e_d, is the filter tap kd = 2 - m.  One MMA therefore produces the three kd taps at once:
+// 3 MMAs per 16-voxel K-step (per 8-channel group of ci) instead of 9.  The reduction domain of v is extended to
+// d in [-2, D) so that u covers the whole volume for every m; TMA's out-of-bounds zero fill supplies both the
+// convolution padding of x and the zeros of dy outside the volume.  Staged per tile: dy planes d0 .. d0+5 (6 planes),
+// x halo planes d0+1 .. d0+4 (4 planes; the kd halo moved into dy).
+// Issue balance: 12 accumulators, three per issuing warp.  Cin = 8: warp j takes every fourth K-step (the four
+// partial accumulators of a tap are summed by the atomics of the read-back); Cin = 16-slice: warp j takes ci group
+// j >> 1 on every second K-step.
+// ---------------------------------------------------------------------------------------------
+constexpr int DSH_DY_BYTES = (TD + 2) * TH * TW * 16;    // 12288
+constexpr int DSH_XPLANE_BYTES = TD * HH * HW * 16;      // 11520
+
+template <bool CIN8, int NSTAGE>
+__global__ void __launch_bounds__(NTHREADS, 1) conv3_wgrad_dsh_kernel(const __grid_constant__ CUtensorMap xmap,
+                                                                      const __grid_constant__ CUtensorMap dymap, WgParams p) {
+    constexpr int XP = CIN8 ? 1 : 2;
+    constexpr int STAGE_BYTES = DSH_DY_BYTES + XP * DSH_XPLANE_BYTES;
+    constexpr int NACC = 12;
+    constexpr int TMEM_COLS = 512;                            // 12 x 24 columns
+    static_assert(STAGE_BYTES % 128 == 0, "stage alignment");
+    // the M = 64 operand spans eight plane-strided groups from its start address: the furthest read (K-step jd = 3,
+    // h2 = 7, group 7) ends inside the stage, so no tail padding is needed
+    static_assert(((TD - 1) * TH * TW + (TH - 2) * TW) * 16 + 7 * TH * TW * 16 + 2 * TW * 16 <= STAGE_BYTES, "A over-read");
+
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + NSTAGE;
+    uint64_t* done_bar = empty_bar + NSTAGE;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    const int ks = blockIdx.y;                                // 16-channel slice of ci (0 for Cin = 8)
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 4); }
+        mbar_init(done_bar, 4);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    const bool has_work = (int)blockIdx.x < p.tiles;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+                const int n = tile / p.tiles_per_n;
+                int r = tile % p.tiles_per_n;
+                const int w0 = (r % p.tiles_w) * TW; r /= p.tiles_w;
+                const int h0 = (r % p.tiles_h) * TH; r /= p.tiles_h;
+                const int d0 = r * TD - 2;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sdy = smem + stage * STAGE_BYTES;
+                uint8_t* sx = sdy + DSH_DY_BYTES;
+                mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+                tma_load_4d(sdy, &dymap, &full_bar[stage], w0 * 8, h0, d0, n);
+                if (CIN8) {
+                    tma_load_4d(sx, &xmap, &full_bar[stage], (w0 - 1) * 8, h0 - 1, d0 + 1, n);
+                } else {
+                    tma_load_5d(sx, &xmap, &full_bar[stage], ks * 16, w0 - 1, h0 - 1, d0 + 1, n);
+                    tma_load_5d(sx + DSH_XPLANE_BYTES, &xmap, &full_bar[stage], ks * 16 + 8, w0 - 1, h0 - 1, d0 + 1, n);
+                }
+                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        const int j = warp - 1;
+        constexpr uint32_t idesc = make_idesc_mn(24);
+        const int kmod = CIN8 ? 4 : 2, kres = CIN8 ? j : (j & 1);        // this warp's K-steps: kcount % kmod == kres
+        const int cg = CIN8 ? 0 : (j >> 1);
+        const uint32_t col0 = tmem_base + (uint32_t)(j * 3) * 24;
+        uint32_t stage = 0, phase = 0;
+        uint32_t acc = 0u;                                               // first K-step of this warp overwrites
+        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+            int r = tile % p.tiles_per_n;
+            r /= p.tiles_w;
+            const int h0 = (r % p.tiles_h) * TH;
+            const int h2_end = min(TH / 2, (p.h - h0 + 1) / 2);          // rows past the volume are zero
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sdy = smem_u32(smem + stage * STAGE_BYTES);
+            const uint64_t ad0 = make_desc(sdy, TW * 16u, TH * TW * 16u);
+            const uint64_t bd0 = make_desc(sdy + DSH_DY_BYTES + cg * DSH_XPLANE_BYTES, HW * 16u, 16u);
+            int kcount = 0;
+#pragma unroll 1
+            for (int jd = 0; jd < TD; ++jd) {
+#pragma unroll 1
+                for (int h2 = 0; h2 < h2_end; ++h2, ++kcount) {          // 16 voxels = two h-rows of one d-plane
+                    if (kcount % kmod != kres) continue;
+                    const uint64_t ad = ad0 + (uint64_t)((jd * TH * TW + h2 * 2 * TW));           // 16-byte units
+                    const uint64_t bdk = bd0 + (uint64_t)((jd * HH + h2 * 2) * HW);
+#pragma unroll
+                    for (int kh = 0; kh < 3; ++kh) tc_mma_elect(col0 + kh * 24, ad, bdk + (uint64_t)(kh * HW), idesc, acc);
+                    acc = 1u;
+                }
+            }
+            tc_commit_elect(&empty_bar[stage]);
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        }
+        tc_commit_elect(done_bar);
+        if (has_work) {
+            mbar_wait(done_bar, 0);
+            tc_fence_after();
+            // M = 64 accumulator rows live in lanes (row & 15) + 32 * (row >> 4); row = m * 8 + co, m = 0..2 valid
+            const int q = warp & 3;
+            const int row = q * 16 + lane;
+            const int m = row >> 3, co = row & 7;
+            const bool valid = lane < 16 && m <= 2;
+            if (q < 2) {
+#pragma unroll 1
+                for (int g = 0; g < NACC; ++g) {
+                    const int gw = g / 3, kh = g % 3;
+                    const int gcg = CIN8 ? 0 : (gw >> 1);
+                    uint32_t r0[8], r1[8], r2[8];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + g * 24;
+                    tmem_ld8(taddr, r0);
+                    tmem_ld8(taddr + 8, r1);
+                    tmem_ld8(taddr + 16, r2);
+                    tmem_ld_wait();
+                    if (valid) {
+                        float* base = p.dw + ((long long)co * p.cin + ks * 16 + gcg * 8) * 27 + (2 - m) * 9 + kh * 3;
+#pragma unroll
+                        for (int c8 = 0; c8 < 8; ++c8) {
+                            atomicAdd(base + c8 * 27 + 0, __uint_as_float(r0[c8]));
+                            atomicAdd(base + c8 * 27 + 1, __uint_as_float(r1[c8]));
+                            atomicAdd(base + c8 * 27 + 2, __uint_as_float(r2[c8]));
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+template <bool CIN8, int NSTAGE>
+int launch_wg_dsh(const CUtensorMap& xmap, const CUtensorMap& dymap, const WgParams& p, int slices, cudaStream_t st) {
+    constexpr int XP = CIN8 ? 1 : 2;
+    constexpr int STAGE_BYTES = DSH_DY_BYTES + XP * DSH_XPLANE_BYTES;
+    constexpr int SMEM = NSTAGE * STAGE_BYTES + 128 + 8 * (2 * NSTAGE + 1) + 16 + 64;
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
+    auto kern = conv3_wgrad_dsh_kernel<CIN8, NSTAGE>;
+    static bool configured = false;
+    if (!configured) {
+        VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM), "conv3_wgrad_dsh smem attribute");
+        configured = true;
+    }
+    int parts = vs_sm_count() / slices;
+    if (parts < 1) parts = 1;
+    if (parts > p.tiles) parts = p.tiles;
+    dim3 grid((unsigned)parts, (unsigned)slices);
+    kern<<<grid, NTHREADS, SMEM, st>>>(xmap, dymap, p);
+    VS_CHECK_LAUNCH("conv3_wgrad_dsh_kernel");
+    return VS_OK;
+}
+
 template <bool CIN8>
 int dispatch_wg(int ncog, const CUtensorMap& xmap, const CUtensorMap& dymap, const WgParams& p, int slices, cudaStream_t st) {
     if (ncog <= 1) return launch_wg<CIN8, 1, 4>(xmap, dymap, p, slices, st);
@@ -229,6 +400,10 @@ int dispatch_wg(int ncog, const CUtensorMap& xmap, const CUtensorMap& dymap, con
 }
 
 }  // namespace
+
+static int g_wgrad_dsh = 1;
+// development switch (A/B runs, tests): 0 disables the d-shift variant for Cout = 8
+extern "C" void vs_debug_set_wgrad_dsh(int on) { g_wgrad_dsh = on; }
 
 extern "C" int vs_conv3_wgrad_tc_eligible(int cin, int cout) {
     return (cin == 8 || (cin % 16 == 0 && cin >= 16)) && cout % 8 == 0 && cout >= 8;
@@ -245,12 +420,14 @@ extern "C" int vs_conv3x3x3_wgrad_tc(const void* x, const void* dy, float* dw, i
     VS_REQUIRE(encode != nullptr, VS_ERR_CUDA, "conv3_wgrad_tc: cuTensorMapEncodeTiled unavailable");
     cudaStream_t st = (cudaStream_t)stream;
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const bool dsh = cout == 8 && g_wgrad_dsh;                 // d-shift variant (see conv3_wgrad_dsh_kernel)
+    const cuuint32_t xbd = dsh ? TD : HD, dybd = dsh ? TD + 2 : TD;
     CUtensorMap xmap, dymap;
     CUresult cr;
     if (cin == 8) {
         const cuuint64_t gdim[4] = {(cuuint64_t)w * 8, (cuuint64_t)h, (cuuint64_t)d, (cuuint64_t)n};
         const cuuint64_t gstr[3] = {(cuuint64_t)w * 16, (cuuint64_t)h * w * 16, (cuuint64_t)d * h * w * 16};
-        const cuuint32_t box[4] = {HW * 8, HH, HD, 1};
+        const cuuint32_t box[4] = {HW * 8, HH, xbd, 1};
         cr = encode(&xmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), gdim, gstr, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -258,7 +435,7 @@ extern "C" int vs_conv3x3x3_wgrad_tc(const void* x, const void* dy, float* dw, i
         const cuuint64_t gdim[5] = {(cuuint64_t)cin, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)d, (cuuint64_t)n};
         const cuuint64_t gstr[4] = {(cuuint64_t)cin * 2, (cuuint64_t)w * cin * 2, (cuuint64_t)h * w * cin * 2,
                                     (cuuint64_t)d * h * w * cin * 2};
-        const cuuint32_t box[5] = {8, HW, HH, HD, 1};
+        const cuuint32_t box[5] = {8, HW, HH, xbd, 1};
         cr = encode(&xmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), gdim, gstr, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -267,7 +444,7 @@ extern "C" int vs_conv3x3x3_wgrad_tc(const void* x, const void* dy, float* dw, i
     if (cout == 8) {
         const cuuint64_t gdim[4] = {(cuuint64_t)w * 8, (cuuint64_t)h, (cuuint64_t)d, (cuuint64_t)n};
         const cuuint64_t gstr[3] = {(cuuint64_t)w * 16, (cuuint64_t)h * w * 16, (cuuint64_t)d * h * w * 16};
-        const cuuint32_t box[4] = {TW * 8, TH, TD, 1};
+        const cuuint32_t box[4] = {TW * 8, TH, dybd, 1};
         cr = encode(&dymap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dy), gdim, gstr, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -284,7 +461,7 @@ extern "C" int vs_conv3x3x3_wgrad_tc(const void* x, const void* dy, float* dw, i
 
     WgParams p;
     p.n = n; p.d = d; p.h = h; p.w = w; p.cin = cin; p.cout = cout;
-    p.tiles_d = (d + TD - 1) / TD; p.tiles_h = (h + TH - 1) / TH; p.tiles_w = (w + TW - 1) / TW;
+    p.tiles_d = ((dsh ? d + 2 : d) + TD - 1) / TD; p.tiles_h = (h + TH - 1) / TH; p.tiles_w = (w + TW - 1) / TW;
     p.tiles_per_n = p.tiles_d * p.tiles_h * p.tiles_w;
     const long long tiles = (long long)n * p.tiles_per_n;
     VS_REQUIRE(tiles < 2147483647LL, VS_ERR_SHAPE, "conv3_wgrad_tc: too many tiles");
@@ -295,6 +472,10 @@ extern "C" int vs_conv3x3x3_wgrad_tc(const void* x, const void* dy, float* dw, i
     const int mchunks = (cout + MROWS - 1) / MROWS;
     const int slices = p.kslices * mchunks;
     const int ncog = cout >= MROWS ? 8 : cout / 8;            // planes of the (possibly only) 64-channel chunk
+    if (dsh) {
+        if (cin == 8) return launch_wg_dsh<true, 4>(xmap, dymap, p, slices, st);
+        return launch_wg_dsh<false, 4>(xmap, dymap, p, slices, st);
+    }
     if (cin == 8) return dispatch_wg<true>(ncog, xmap, dymap, p, slices, st);
     return dispatch_wg<false>(ncog, xmap, dymap, p, slices, st);
 }

@@ -268,18 +268,30 @@ __global__ void __launch_bounds__(256, 2) k2s2_wgrad_kernel(const T* __restrict_
 #pragma unroll
                 for (int jj = 0; jj < 8; ++jj) acc[i][jj] = fmaf(c[u][i], f[u][jj], acc[i][jj]);
     }
+    // Epilogue: the 8 warps (= the 8 filter positions k) hold one 8x8 block each; dwt is [a][b][k] with k innermost,
+    // so the CTA's 512 results are 128 aligned groups of four consecutive floats.  Transpose through shared memory
+    // and issue 128 float4 atomics instead of 512 scalar ones: with hundreds of CTAs adding onto the same few
+    // cache lines the L2 atomic unit, not the FMAs, bounds this kernel.
+    __shared__ float red[8][64];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
             const float v = warp_sum(acc[i][jj]);
-            if (lane == ((i * 8 + jj) & 31)) acc[i][jj] = v;        // spread the 64 results over the lanes
+            if (lane == ((i * 8 + jj) & 31)) red[k][i * 8 + jj] = v;
         }
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj)
-            if (lane == ((i * 8 + jj) & 31)) atomicAdd(dwt + ((long long)(a0 + i) * p.b + b0 + jj) * 8 + k, acc[i][jj]);
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        const int idx = threadIdx.x >> 1, half = threadIdx.x & 1;
+        const int i = idx >> 3, jj = idx & 7;
+        float* dst = dwt + ((long long)(a0 + i) * p.b + b0 + jj) * 8 + half * 4;
+        const float4 v = make_float4(red[half * 4 + 0][idx], red[half * 4 + 1][idx], red[half * 4 + 2][idx], red[half * 4 + 3][idx]);
+        if (vs_aligned16_dev(dst)) {
+            atomicAdd(reinterpret_cast<float4*>(dst), v);
+        } else {
+            atomicAdd(dst + 0, v.x); atomicAdd(dst + 1, v.y); atomicAdd(dst + 2, v.z); atomicAdd(dst + 3, v.w);
+        }
+    }
 }
 
 // out[c] += sum_rows t[row][c]   (C % 8 == 0)

@@ -156,13 +156,23 @@ class PackCache(object):
 # parallel branch of the captured CUDA graph) the wgrads fill the SMs that the small deep-level kernels leave idle.
 # Only used when the gradient is accumulated in place into an existing .grad (the trainers' flat arenas): the
 # consumer (optimiser) then waits on the side stream once per step (`join_wgrad_stream`).
-WGRAD_STREAM = None
+WGRAD_STREAM = None            # a stream, or a list of streams used round-robin (independent layers overlap)
+_wgrad_rr = [0]
+
+
+def _wgrad_streams():
+    ws = WGRAD_STREAM
+    if ws is None:
+        return []
+    return list(ws) if isinstance(ws, (list, tuple)) else [ws]
 
 
 def _wgrad_async(fn, inplace, *inputs):
-    ws = WGRAD_STREAM
-    if ws is None or not inplace:
+    streams = _wgrad_streams()
+    if not streams or not inplace:
         return fn()
+    ws = streams[_wgrad_rr[0] % len(streams)]
+    _wgrad_rr[0] += 1
     cur = torch.cuda.current_stream()
     ws.wait_stream(cur)
     with torch.cuda.stream(ws):
@@ -174,8 +184,9 @@ def _wgrad_async(fn, inplace, *inputs):
 
 
 def join_wgrad_stream():
-    if WGRAD_STREAM is not None:
-        torch.cuda.current_stream().wait_stream(WGRAD_STREAM)
+    for ws in _wgrad_streams():
+        torch.cuda.current_stream().wait_stream(ws)
+    _wgrad_rr[0] = 0
 
 
 def _tc_channels(c):

@@ -15,6 +15,8 @@ evaluated on the device (no .item() sync).  Data parallelism = one p
 GPU (torch.distributed, NCCL): per-rank batch shards, one gradient all-reduce per step and,
 for type 8, a 1-float all-reduce of the recon Dice so every rank takes the same branch.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -171,7 +173,7 @@ class JointTrainer(object):
         # chain.  Both are dominated by deep-level kernels that occupy 8-48 of the 148 SMs, so they overlap well.
         self.overlap = overlap
         self.teacher_stream = torch.cuda.Stream()
-        self.wgrad_stream = torch.cuda.Stream()
+        self.wgrad_stream = [torch.cuda.Stream() for _ in range(max(1, int(os.environ.get("VAESEG_WGRAD_STREAMS", "1"))))]
 
     def ema_teacher(self):
         # main_target.py:512-516 on the Seg state_dict
