@@ -59,9 +59,13 @@ typedef struct {
     void* tcf;            /* bf16 tensor-core fprop pack or NULL                        */
     void* tcd;            /* bf16 tensor-core dgrad pack (of [cout_pad][Cin][27]) or NULL */
     long long tcf_elems, tcd_elems;
-    int cin, cout, cout_pad, reserved;
+    int cin, cout, cout_pad, cin_pad;   /* cin_pad > cin zero-pads the input channels of the dgrad pack (0 = none) */
 } vs_pack_job;
 int vs_pack_conv3_batched(const void* jobs_dev, int njobs, void* stream);
+/* One padded pack: master weight [cout][cin][27], pack built for cin_pad >= cin / cout_pad >= cout channels (zeros);
+ * out holds vs_conv3_tc_pack_bytes(cin_pad, cout_pad, dgrad) bytes.                                             */
+int vs_pack_conv3_weight_tc_padded(const float* w, void* out, int cin, int cout, int cin_pad, int cout_pad, int dgrad,
+                                   void* stream);
 
 /* ---- 3x3x3 convolution, padding 1 (Conv3d at joint_model.py:40-46,106,224,366) ------- */
 /* x: NDHWC `in_dtype` (or planar fp32 when in_planar=1, used by the in_blocks whose input is
@@ -84,11 +88,18 @@ int vs_conv3x3x3_fprop(int in_dtype, int out_dtype, int in_planar, int out_plana
  * the activation of the PREVIOUS Conv3d+InstanceNorm+ReLU layer whose raw output is y_prev (NDHWC bf16, dx's shape)
  * with statistics stats_prev; the call then also accumulates that layer's InstanceNorm-backward sums
  * sums_prev[N][Cin][2] += (sum dx*mask, sum dx*mask*xhat) -- what vs_inorm_relu_bwd_reduce would compute in a
- * separate pass over dx and y_prev.  sums_prev must be zeroed by the caller.                                   */
+ * separate pass over dx and y_prev.  sums_prev must be zeroed by the caller.
+ * out_planar=1 with Cin == 2 and wdtc = vs_pack_conv3_weight_tc_padded(w, 2, cout, 8, cout, dgrad=1): tensor-core
+ * path storing the two real input-gradient channels as planar fp32 (the VAE in-block).                          */
 int vs_conv3x3x3_dgrad(int in_dtype, int out_dtype, int out_planar,
                        const void* dy, const float* wdpk, const void* wdtc, void* dx,
                        const void* y_prev, const double* stats_prev, double* sums_prev,
                        int n, int d, int h, int w, int cin, int cout, void* stream);
+/* 2-class head in one launch: probs[N][2][D][H][W] (planar fp32) = softmax_c(conv3(x, w) + bias).  x: NDHWC bf16,
+ * Cin == 8 or Cin %% 16 == 0; wtc8: vs_pack_conv3_weight_tc_padded(w, cin, 2, cin, 8, dgrad=0) (output channels
+ * zero-padded to 8); bias fp32 [2] or NULL.  Replaces Conv3d + nn.Softmax(dim=1) at joint_model.py:224-225,366-367. */
+int vs_head_conv_softmax2_fwd(const void* x, const void* wtc8, const float* bias, float* probs,
+                              int n, int d, int h, int w, int cin, void* stream);
 /* dw[Cout,Cin,27] (+)= sum_v dy[v,co] * x[v+tap,ci]; db[Cout] (+)= sum_v dy (db may be NULL).
  * x may be planar fp32 (in_planar=1).  accumulate=0 overwrites.  workspace: fp32
  * vs_conv3_wgrad_workspace_bytes() bytes (partial sums).                                 */

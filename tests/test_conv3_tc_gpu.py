@@ -130,3 +130,38 @@ def test_tc_dgrad_fused_norm_backward_reduction(case):
     gscale = ref.abs().max().item()
     assert (from_ndhwc(dy_fused) - ref).abs().max().item() < 2e-2 * gscale
     assert (dy_fused.float() - dy_split.float()).abs().max().item() < 1e-2 * gscale
+
+
+@pytest.mark.parametrize("case", [(2, 5, 17, 9, 8), (1, 8, 16, 8, 16), (1, 7, 20, 19, 8), (2, 3, 3, 3, 32)])
+def test_tc_head_conv_bias_softmax(case):
+    """The 2-class head in one tensor-core launch (output channels padded to 8, bias + softmax + planar fp32 store in
+    the epilogue) against softmax(conv3d + bias) of torch on the same bf16 operands."""
+    n, d, h, w, cin = case
+    torch.manual_seed(sum(case) + 3)
+    x = torch.randn(n, cin, d, h, w).bfloat16().float()
+    wt = torch.randn(2, cin, 3, 3, 3) * 0.2
+    b = torch.randn(2)
+    ref = F.softmax(F.conv3d(x, wt.bfloat16().float(), b, padding=1), dim=1)
+    wtc8 = ops.pack_conv3_weight_tc_padded(wt.to(DEV), cin, 8, dgrad=False)
+    probs = ops.head_conv_softmax2(to_ndhwc(x), wtc8, b.to(DEV), (n, d, h, w), cin)
+    torch.cuda.synchronize()
+    assert probs.shape == ref.shape and probs.dtype == torch.float32
+    assert (probs.cpu() - ref).abs().max().item() < 2e-3
+    assert (probs.cpu().argmax(1) == ref.argmax(1)).float().mean().item() > 0.999
+
+
+@pytest.mark.parametrize("case", [(2, 5, 17, 9), (1, 8, 16, 8), (1, 3, 3, 3)])
+def test_tc_inblock2_planar_dgrad(case):
+    """Planar fp32 2-channel input gradient of an in-block (2 -> 8) on the tensor cores: the dgrad pack has its input
+    channels zero-padded to 8, the epilogue stores channels 0..1 as planar fp32."""
+    n, d, h, w = case
+    torch.manual_seed(sum(case) + 4)
+    wt = torch.randn(8, 2, 3, 3, 3) * 0.2
+    gy = torch.randn(n, 8, d, h, w).bfloat16().float()
+    ref = F.conv_transpose3d(gy, wt.bfloat16().float(), None, padding=1)
+    wdtc = ops.pack_conv3_weight_tc_padded(wt.to(DEV), 8, 8, dgrad=True)
+    _, wdg = ops.pack_conv3_weight(wt.to(DEV))
+    dx = ops.conv3_dgrad(to_ndhwc(gy), wdg, (n, d, h, w), 2, 8, torch.bfloat16, out_planar=True, wdtc=wdtc)
+    torch.cuda.synchronize()
+    assert dx.shape == ref.shape and dx.dtype == torch.float32
+    assert (dx.cpu() - ref).abs().max().item() < 2e-3 * ref.abs().max().item()

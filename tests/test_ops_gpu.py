@@ -40,7 +40,8 @@ def q(x, dtype):
 
 CONV_CASES = [  # (n, d, h, w, cin, cout, planar_in)
     (2, 5, 9, 10, 1, 8, True), (1, 4, 8, 8, 2, 8, True), (2, 6, 7, 9, 8, 16, False), (1, 9, 8, 17, 16, 8, False),
-    (1, 4, 4, 4, 32, 32, False), (1, 3, 3, 3, 64, 16, False), (2, 4, 5, 6, 8, 2, False)]
+    (1, 4, 4, 4, 32, 32, False), (1, 3, 3, 3, 64, 16, False), (2, 4, 5, 6, 8, 2, False),
+    (2, 9, 19, 70, 1, 8, True), (2, 6, 17, 33, 2, 8, True), (1, 3, 3, 3, 2, 8, True)]
 
 
 @pytest.mark.parametrize("dtype", DTYPES)

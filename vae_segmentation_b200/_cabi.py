@@ -25,6 +25,8 @@ _SIGNATURES = {
     "vs_conv3_tc_pack_bytes": [_I, _I, _I],
     "vs_pack_conv3_weight_tc": [_P, _P, _I, _I, _I, _P],
     "vs_pack_conv3_batched": [_P, _I, _P],
+    "vs_pack_conv3_weight_tc_padded": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "vs_head_conv_softmax2_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "vs_conv3x3x3_fprop": [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "vs_conv3x3x3_dgrad": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "vs_conv3_wgrad_workspace_bytes": [_I, _I, _I, _I, _I, _I],

@@ -33,7 +33,8 @@ extern "C" int vs_conv3_shift_internal(int in_dtype, int in_planar, const void* 
                                        int d, int h, int w, int cin, int cout, void* stream);
 #ifdef VS_WITH_TCGEN05
 extern "C" int vs_conv3x3x3_tc(const void* x, const void* wtc, void* y, double* stats, float* shift, int prezeroed,
-                               const void* yprev, const double* pstats, double* psums, int n, int d,
+                               const void* yprev, const double* pstats, double* psums, int planar_mode,
+                               float* yplanar, const float* bias, int n, int d,
                                int h, int w, int gin, int gout, void* stream);
 extern "C" size_t vs_conv3_tc_pack_bytes(int cin, int cout, int dgrad);
 #endif
@@ -60,7 +61,8 @@ extern "C" int vs_conv3x3x3_fprop(int in_dtype, int out_dtype, int in_planar, in
     if (wtc != nullptr && in_dtype == VS_BF16 && out_dtype == VS_BF16 && !in_planar && !out_planar && bias == nullptr &&
         tc_eligible(cin, cout)) {
         // the tensor-core kernel derives and publishes the shift itself (no separate launch)
-        return vs_conv3x3x3_tc(x, wtc, y, stats, shift, prezeroed, nullptr, nullptr, nullptr, n, d, h, w, cin, cout, stream);
+        return vs_conv3x3x3_tc(x, wtc, y, stats, shift, prezeroed, nullptr, nullptr, nullptr, 0, nullptr, nullptr, n, d, h, w,
+                               cin, cout, stream);
     }
 #else
     (void)wtc;
@@ -75,7 +77,14 @@ extern "C" int vs_conv3x3x3_dgrad(int in_dtype, int out_dtype, int out_planar, c
     // dx[.., cin] = conv3(dy[.., cout], wd[27][cout][cin]): the fprop contraction with channels swapped
 #ifdef VS_WITH_TCGEN05
     if (wdtc != nullptr && in_dtype == VS_BF16 && out_dtype == VS_BF16 && !out_planar && tc_eligible(cout, cin))
-        return vs_conv3x3x3_tc(dy, wdtc, dx, nullptr, nullptr, 0, y_prev, stats_prev, sums_prev, n, d, h, w, cout, cin, stream);
+        return vs_conv3x3x3_tc(dy, wdtc, dx, nullptr, nullptr, 0, y_prev, stats_prev, sums_prev, 0, nullptr, nullptr, n, d, h, w,
+                               cout, cin, stream);
+    // 2-channel planar fp32 input gradient (the VAE in-block, whose input is the module's NCDHW tensor): the pack is
+    // built with the input channels zero-padded to 8 (vs_pack_conv3_weight_tc_padded) and the epilogue stores
+    // channels 0..1 as planar fp32
+    if (wdtc != nullptr && in_dtype == VS_BF16 && out_planar && cin == 2 && sums_prev == nullptr && tc_eligible(cout, 8))
+        return vs_conv3x3x3_tc(dy, wdtc, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 2, (float*)dx, nullptr, n, d, h,
+                               w, cout, 8, stream);
 #else
     (void)wdtc;
 #endif
@@ -86,7 +95,24 @@ extern "C" int vs_conv3x3x3_dgrad(int in_dtype, int out_dtype, int out_planar, c
                                      cout, cin, stream);
 }
 
+// 2-class head: probs[N][2][D][H][W] = softmax(conv3(x, w) + bias) in one launch (tensor-core kernel with the output
+// channels padded to 8; bias + softmax + planar fp32 store fused into the epilogue).  joint_model.py:224-225,366-367
+extern "C" int vs_head_conv_softmax2_fwd(const void* x, const void* wtc8, const float* bias, float* probs, int n, int d,
+                                         int h, int w, int cin, void* stream) {
+#ifdef VS_WITH_TCGEN05
+    VS_REQUIRE(x && wtc8 && probs, VS_ERR_SHAPE, "head_conv_softmax2_fwd: null pointer");
+    VS_REQUIRE(tc_eligible(cin, 8), VS_ERR_UNSUPPORTED, "head_conv_softmax2_fwd: Cin must be 8 or a multiple of 16 (got %d)", cin);
+    return vs_conv3x3x3_tc(x, wtc8, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 1, probs, bias, n, d, h, w, cin, 8,
+                           stream);
+#else
+    VS_FAIL(VS_ERR_UNSUPPORTED, "library built without the tcgen05 kernels");
+#endif
+}
+
 #ifndef VS_WITH_TCGEN05
+extern "C" int vs_pack_conv3_weight_tc_padded(const float*, void*, int, int, int, int, int, void*) {
+    VS_FAIL(VS_ERR_UNSUPPORTED, "library built without the tcgen05 kernels");
+}
 extern "C" size_t vs_conv3_tc_pack_bytes(int, int, int) { return 0; }
 extern "C" int vs_pack_conv3_weight_tc(const float*, void*, int, int, int, void*) {
     VS_FAIL(VS_ERR_UNSUPPORTED, "library built without the tcgen05 kernels");

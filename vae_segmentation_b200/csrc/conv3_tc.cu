@@ -55,6 +55,12 @@ struct TcParams {
     const double* pstats;   // its (sum, sumsq) statistics [n][cout][2]
     double* psums;          // zeroed by the caller
     double inv_s;           // 1 / (d*h*w)
+    // planar fp32 output of the first two GEMM output channels instead of the bf16 NDHWC store (Cout padded to 8):
+    // 1 = the 2-class head: probs = softmax(acc + bias) -> yplanar[n][2][d][h][w]   (joint_model.py:224-225,366-367)
+    // 2 = plain values (gradient w.r.t. a 2-channel planar module input)
+    int planar_mode;
+    float* yplanar;
+    const float* bias;      // [2] or null (mode 1)
 };
 
 // Column sums of a 32-lane x 16-value register tile in 31 shuffles: afterwards v[0] of lane L holds the
@@ -255,6 +261,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
         // first tile of the group.  Progress: the producing tiles are the FIRST items of CTAs 0 .. n*nchunks-1
         // (decode_work), a producing item never waits, and the hardware dispatches CTAs in index order -- so whenever
         // a waiter is resident, the CTA it waits on already is, independent of what else occupies the GPU.
+        float hb0 = 0.f, hb1 = 0.f;
+        if (p.planar_mode == 1 && p.bias != nullptr) { hb0 = p.bias[0]; hb1 = p.bias[1]; }
+        const long long vol = (long long)p.d * p.h * p.w;
         const int rd = min(1, p.d - 1), rh = min(1, p.h - 1), rw = min(1, p.w - 1);
         const bool has_shift = p.shift != nullptr;
         const bool has_stats = p.stats != nullptr;
@@ -350,7 +359,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
 #pragma unroll
                         for (int k = 0; k < 16; ++k) v[k] = 0.f;
                     }
-                    if (rc_ok) {
+                    if (p.planar_mode != 0) {
+                        if (rc_ok && c16 == 0 && co0 == 0) {
+                            float o0 = v[0] + hb0, o1 = v[1] + hb1;
+                            if (p.planar_mode == 1) {
+                                const float mx = fmaxf(o0, o1);
+                                const float e0 = expf(o0 - mx), e1 = expf(o1 - mx);
+                                const float inv = 1.f / (e0 + e1);
+                                o0 = e0 * inv; o1 = e1 * inv;
+                            }
+                            float* pp = p.yplanar + (long long)n * 2 * vol + ((long long)(d0 + j) * p.h + gh) * p.w + gw;
+                            pp[0] = o0;
+                            pp[vol] = o1;
+                        }
+                    } else if (rc_ok) {
 #pragma unroll
                         for (int h8 = 0; h8 < 2; ++h8) {
                             if (co0 + c16 * 16 + h8 * 8 < p.cout) {
@@ -417,7 +439,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
 // One element of the bf16 UMMA B-operand pack.  cout_real < cout_l zero-pads the output channels (the head's
 // 2 -> 8 channel dgrad pack).
 __device__ __forceinline__ float pack_tc_elem(const float* __restrict__ w, long long i, int cin_l, int cout_l, int cout_real,
-                                              int dgrad, int nc, int cin8) {
+                                              int dgrad, int nc, int cin8, int cin_real = -1) {
+    if (cin_real < 0) cin_real = cin_l;         // cin_real < cin_l zero-pads the input channels (2-channel in-block dgrad)
     // GEMM-side channel counts
     const int gin = dgrad ? cout_l : cin_l, gout = dgrad ? cin_l : cout_l;
     const int kslices = cin8 ? 1 : gin / 16;
@@ -442,8 +465,8 @@ __device__ __forceinline__ float pack_tc_elem(const float* __restrict__ w, long 
     }
     float v = 0.f;
     if (go < gout && gi < gin && tap >= 0) {
-        if (dgrad) { if (gi < cout_real) v = w[((long long)gi * cin_l + go) * 27 + (26 - tap)]; }   // w[co=gi][ci=go][flipped tap]
-        else if (go < cout_real) v = w[((long long)go * cin_l + gi) * 27 + tap];
+        if (dgrad) { if (gi < cout_real && go < cin_real) v = w[((long long)gi * cin_real + go) * 27 + (26 - tap)]; }   // w[co=gi][ci=go][flipped tap]
+        else if (go < cout_real && gi < cin_real) v = w[((long long)go * cin_real + gi) * 27 + tap];
     }
     return v;
 }
@@ -493,6 +516,28 @@ extern "C" size_t vs_conv3_tc_pack_bytes(int cin, int cout, int dgrad) {
     return (size_t)nchunks * kslices * (gin == 8 ? 18 : 27) * nc * 32;
 }
 
+// Padded variants: the fp32 master weight is [cout][cin][27]; the pack is built for cout_pad >= cout output and
+// cin_pad >= cin input channels (zeros), e.g. the 2-class head as an 8-channel layer (fprop and dgrad) and the VAE
+// in-block's 2-channel input gradient as an 8-channel one.
+extern "C" size_t vs_conv3_tc_pack_bytes(int cin, int cout, int dgrad);
+__global__ void pack_tc_padded_kernel(const float* __restrict__ w, bf16* __restrict__ out, int cin, int cout, int cin_pad,
+                                      int cout_pad, int dgrad, int nc, int cin8, long long total) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+        out[i] = __float2bfloat16_rn(pack_tc_elem(w, i, cin_pad, cout_pad, cout, dgrad, nc, cin8, cin));
+}
+extern "C" int vs_pack_conv3_weight_tc_padded(const float* w, void* out, int cin, int cout, int cin_pad, int cout_pad, int dgrad,
+                                              void* stream) {
+    const size_t bytes = vs_conv3_tc_pack_bytes(cin_pad, cout_pad, dgrad);
+    VS_REQUIRE(w && out && bytes > 0 && cin_pad >= cin && cout_pad >= cout, VS_ERR_UNSUPPORTED,
+               "pack_conv3_weight_tc_padded: unsupported shape Cin=%d(%d) Cout=%d(%d)", cin, cin_pad, cout, cout_pad);
+    const int gin = dgrad ? cout_pad : cin_pad, gout = dgrad ? cin_pad : cout_pad;
+    const long long total = (long long)(bytes / 2);
+    pack_tc_padded_kernel<<<(unsigned)min(1024LL, (total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        w, (bf16*)out, cin, cout, cin_pad, cout_pad, dgrad, nc_for(gout), gin == 8, total);
+    VS_CHECK_LAUNCH("pack_tc_padded_kernel");
+    return VS_OK;
+}
+
 extern "C" int vs_pack_conv3_weight_tc(const float* w, void* out, int cin, int cout, int dgrad, void* stream) {
     const size_t bytes = vs_conv3_tc_pack_bytes(cin, cout, dgrad);
     VS_REQUIRE(w && out && bytes > 0, VS_ERR_UNSUPPORTED, "pack_conv3_weight_tc: unsupported shape Cin=%d Cout=%d", cin, cout);
@@ -510,6 +555,7 @@ __global__ void __launch_bounds__(256) pack_batched_kernel(const vs_pack_job* __
     const vs_pack_job j = jobs[blockIdx.y];
     const float* w = (const float*)j.w;
     const int cin = j.cin, cout = j.cout, cpad = j.cout_pad;
+    const int cinpad = j.cin_pad > cin ? j.cin_pad : cin;
     const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (j.wf != nullptr || j.wd != nullptr) {
         float* wf = (float*)j.wf; float* wd = (float*)j.wd;
@@ -523,23 +569,25 @@ __global__ void __launch_bounds__(256) pack_batched_kernel(const vs_pack_job* __
     }
     if (j.tcf != nullptr) {
         bf16* o = (bf16*)j.tcf;
-        const int nc = nc_for_dev(cout);
+        const int nc = nc_for_dev(cpad);
         for (long long i = t0; i < j.tcf_elems; i += stride)
-            o[i] = __float2bfloat16_rn(pack_tc_elem(w, i, cin, cout, cout, 0, nc, cin == 8));
+            o[i] = __float2bfloat16_rn(pack_tc_elem(w, i, cin, cpad, cout, 0, nc, cin == 8));
     }
     if (j.tcd != nullptr) {
         bf16* o = (bf16*)j.tcd;
-        const int nc = nc_for_dev(cin);
+        const int nc = nc_for_dev(cinpad);
         for (long long i = t0; i < j.tcd_elems; i += stride)
-            o[i] = __float2bfloat16_rn(pack_tc_elem(w, i, cin, cpad, cout, 1, nc, cpad == 8));
+            o[i] = __float2bfloat16_rn(pack_tc_elem(w, i, cinpad, cpad, cout, 1, nc, cpad == 8, cin));
     }
 }
 
 // y[n,d,h,w,gout] = conv3(x[n,d,h,w,gin], wtc) on the tensor cores; bf16 NDHWC in and out.
 extern "C" int vs_conv3x3x3_tc(const void* x, const void* wtc, void* y, double* stats, float* shift, int prezeroed,
-                               const void* yprev, const double* pstats, double* psums, int n, int d,
+                               const void* yprev, const double* pstats, double* psums, int planar_mode,
+                               float* yplanar, const float* bias, int n, int d,
                                int h, int w, int gin, int gout, void* stream) {
-    VS_REQUIRE(x && wtc && y, VS_ERR_SHAPE, "conv3_tc: null pointer");
+    VS_REQUIRE(x && wtc && (y || planar_mode), VS_ERR_SHAPE, "conv3_tc: null pointer");
+    if (planar_mode) VS_REQUIRE(yplanar && gout == 8 && !stats && !shift && !psums, VS_ERR_SHAPE, "conv3_tc: planar output needs Cout padded to 8 and no statistics");
     VS_REQUIRE((gin == 8 || (gin % 16 == 0 && gin >= 16)) && gout % 8 == 0 && gout >= 8, VS_ERR_UNSUPPORTED,
                "conv3_tc: unsupported channels Cin=%d Cout=%d", gin, gout);
     VS_REQUIRE(vs_aligned16(x) && vs_aligned16(y) && vs_aligned16(wtc), VS_ERR_ALIGN, "conv3_tc: pointers must be 16B aligned");
@@ -592,6 +640,7 @@ extern "C" int vs_conv3x3x3_tc(const void* x, const void* wtc, void* y, double* 
     p.work_items = (long long)n * p.tiles_per_n * p.nchunks;
     p.wpack = (const bf16*)wtc; p.y = (bf16*)y; p.stats = stats; p.shift = shift;
     p.yprev = (const bf16*)yprev; p.pstats = pstats; p.psums = psums; p.inv_s = 1.0 / ((double)d * h * w);
+    p.planar_mode = planar_mode; p.yplanar = yplanar; p.bias = bias;
     if (psums != nullptr) {
         VS_REQUIRE(yprev && pstats && stats == nullptr && shift == nullptr, VS_ERR_SHAPE,
                    "conv3_tc: the fused norm-backward reduction needs y_prev + stats_prev and no forward statistics");

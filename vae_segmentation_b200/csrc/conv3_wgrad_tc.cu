@@ -339,23 +339,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_wgrad_dsh_kernel(const __gr
             const int m = row >> 3, co = row & 7;
             const bool valid = lane < 16 && m <= 2;
             if (q < 2) {
+                // the K-split partial accumulators of one (ci group, kh) are summed in registers first: one atomic per
+                // CTA and weight element (the atomics onto the same few cache lines from 148 CTAs are not free)
+                constexpr int NSETS = CIN8 ? 4 : 2, NCG = CIN8 ? 1 : 2;
 #pragma unroll 1
-                for (int g = 0; g < NACC; ++g) {
-                    const int gw = g / 3, kh = g % 3;
-                    const int gcg = CIN8 ? 0 : (gw >> 1);
-                    uint32_t r0[8], r1[8], r2[8];
-                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + g * 24;
-                    tmem_ld8(taddr, r0);
-                    tmem_ld8(taddr + 8, r1);
-                    tmem_ld8(taddr + 16, r2);
-                    tmem_ld_wait();
-                    if (valid) {
-                        float* base = p.dw + ((long long)co * p.cin + ks * 16 + gcg * 8) * 27 + (2 - m) * 9 + kh * 3;
+                for (int gcg = 0; gcg < NCG; ++gcg) {
+#pragma unroll 1
+                    for (int kh = 0; kh < 3; ++kh) {
+                        float s0[8], s1[8], s2[8];
 #pragma unroll
-                        for (int c8 = 0; c8 < 8; ++c8) {
-                            atomicAdd(base + c8 * 27 + 0, __uint_as_float(r0[c8]));
-                            atomicAdd(base + c8 * 27 + 1, __uint_as_float(r1[c8]));
-                            atomicAdd(base + c8 * 27 + 2, __uint_as_float(r2[c8]));
+                        for (int c8 = 0; c8 < 8; ++c8) { s0[c8] = 0.f; s1[c8] = 0.f; s2[c8] = 0.f; }
+#pragma unroll
+                        for (int set = 0; set < NSETS; ++set) {
+                            const int jw = CIN8 ? set : (gcg * 2 + set);          // issuing warp that owns the partial
+                            uint32_t r0[8], r1[8], r2[8];
+                            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (jw * 3 + kh) * 24;
+                            tmem_ld8(taddr, r0);
+                            tmem_ld8(taddr + 8, r1);
+                            tmem_ld8(taddr + 16, r2);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int c8 = 0; c8 < 8; ++c8) {
+                                s0[c8] += __uint_as_float(r0[c8]); s1[c8] += __uint_as_float(r1[c8]); s2[c8] += __uint_as_float(r2[c8]);
+                            }
+                        }
+                        if (valid) {
+                            float* base = p.dw + ((long long)co * p.cin + ks * 16 + gcg * 8) * 27 + (2 - m) * 9 + kh * 3;
+#pragma unroll
+                            for (int c8 = 0; c8 < 8; ++c8) {
+                                atomicAdd(base + c8 * 27 + 0, s0[c8]);
+                                atomicAdd(base + c8 * 27 + 1, s1[c8]);
+                                atomicAdd(base + c8 * 27 + 2, s2[c8]);
+                            }
                         }
                     }
                 }

@@ -53,7 +53,7 @@ class _PackJob(ctypes.Structure):
     # mirrors vs_pack_job (include/vaeseg_b200.h)
     _fields_ = [("w", ctypes.c_void_p), ("wf", ctypes.c_void_p), ("wd", ctypes.c_void_p), ("tcf", ctypes.c_void_p),
                 ("tcd", ctypes.c_void_p), ("tcf_elems", ctypes.c_longlong), ("tcd_elems", ctypes.c_longlong),
-                ("cin", ctypes.c_int), ("cout", ctypes.c_int), ("cout_pad", ctypes.c_int), ("reserved", ctypes.c_int)]
+                ("cin", ctypes.c_int), ("cout", ctypes.c_int), ("cout_pad", ctypes.c_int), ("cin_pad", ctypes.c_int)]
 
 
 class PackCache(object):
@@ -109,17 +109,35 @@ class PackCache(object):
             ent["key"] = key
         return ent["wf"], ent["wd"], ent["tcf"], ent["tcd"]
 
-    def head_dgrad_tc(self, w):
-        """bf16 tensor-core dgrad pack of the head weight [n_class,Cin,3,3,3] zero-padded to 8 output channels (the
-        head's logit gradient is produced as an 8-channel tensor, ops.softmax2_bwd_pad8), or None."""
+    def head_tc(self, w):
+        """bf16 tensor-core (fprop, dgrad) packs of the head weight [n_class,Cin,3,3,3] zero-padded to 8 output
+        channels: the head runs as an 8-channel layer whose epilogue stores softmax probabilities (forward) and whose
+        logit gradient is produced as an 8-channel tensor (ops.softmax2_bwd_pad8).  (None, None) without tcgen05."""
         if not USE_TENSOR_CORES:
-            return None
+            return None, None
         ent, key = self._entry("head8", w, True)
         if ent["key"] != key:
             wdet = w.detach()
-            w8 = torch.zeros(8, wdet.shape[1], 3, 3, 3, device=wdet.device, dtype=torch.float32)
-            w8[:wdet.shape[0]].copy_(wdet)
-            ent["tcd"] = ops.pack_conv3_weight_tc(w8, dgrad=True, out=ent["tcd"])
+            cin = wdet.shape[1]
+            ent["tcf"] = ops.pack_conv3_weight_tc_padded(wdet, cin, 8, dgrad=False, out=ent["tcf"])
+            ent["tcd"] = ops.pack_conv3_weight_tc_padded(wdet, cin, 8, dgrad=True, out=ent["tcd"])
+            if not ent["tc"]:
+                self._jobs = None
+            ent["tc"] = True
+            ent["key"] = key
+        return ent["tcf"], ent["tcd"]
+
+    def inblock2_dgrad_tc(self, w):
+        """bf16 tensor-core dgrad pack of a 2-input-channel in-block weight [Cout,2,3,3,3] with the input channels
+        zero-padded to 8 (the planar 2-channel input gradient of the VAE, cabi vs_conv3x3x3_dgrad), or None."""
+        if not USE_TENSOR_CORES:
+            return None
+        ent, key = self._entry("inblk8", w, True)
+        if ent["key"] != key:
+            wdet = w.detach()
+            ent["tcd"] = ops.pack_conv3_weight_tc_padded(wdet, 8, wdet.shape[0], dgrad=True, out=ent["tcd"])
+            if not ent["tc"]:
+                self._jobs = None
             ent["tc"] = True
             ent["key"] = key
         return ent["tcd"]
@@ -137,6 +155,7 @@ class PackCache(object):
                 j.w = w.data_ptr()
                 j.cout, j.cin = w.shape[0], w.shape[1]
                 j.cout_pad = 8 if e["kind"] == "head8" else w.shape[0]
+                j.cin_pad = 8 if e["kind"] == "inblk8" else 0
                 j.wf = e["wf"].data_ptr() if e["wf"] is not None else None
                 j.wd = e["wd"].data_ptr() if e["wd"] is not None else None
                 j.tcf = e["tcf"].data_ptr() if e["tcf"] is not None else None
@@ -237,6 +256,8 @@ def program_forward(layers, tensors, x, dims, dtype, cache, record=True):
     for L in layers:
         if L.kind == C3IN:
             wf, wd, wtc, wdtc = cache.conv3(tensors[L.wi], tc=(dtype == torch.bfloat16))
+            if L.in_planar and L.cin == 2 and record and dtype == torch.bfloat16 and L.cout % 8 == 0:
+                wdtc = cache.inblock2_dgrad_tc(tensors[L.wi])      # planar 2-channel input gradient on the tensor cores
             # the conv bias is a no-op ahead of InstanceNorm(affine=False): skipped
             y, stats = ops.conv3_fprop(cur, wf, None, (n, d, h, w), L.cin, L.cout, dtype, in_planar=L.in_planar,
                                        wtc=None if L.in_planar else wtc, arena=arena)
@@ -259,13 +280,18 @@ def program_forward(layers, tensors, x, dims, dtype, cache, record=True):
             d, h, w = d * 2, h * 2, w * 2
             cur = out
         elif L.kind == HEAD:
-            wf, wd, _, _ = cache.conv3(tensors[L.wi], tc=(dtype == torch.bfloat16))
-            wdtc = None
-            if record and dtype == torch.bfloat16 and L.cout <= 8 and _tc_channels(L.cin) and not L.in_planar:
-                wdtc = cache.head_dgrad_tc(tensors[L.wi])
-            logits, _ = ops.conv3_fprop(cur, wf, tensors[L.bi].detach(), (n, d, h, w), L.cin, L.cout, torch.float32,
-                                        in_planar=L.in_planar, want_stats=False)
-            probs = ops.softmax2_fwd(logits, (n, d, h, w))
+            wtc8 = wdtc = None
+            if dtype == torch.bfloat16 and L.cout == 2 and _tc_channels(L.cin) and not L.in_planar:
+                wtc8, wdtc = cache.head_tc(tensors[L.wi])
+            if wtc8 is not None:
+                # conv + bias + softmax + planar store in ONE tensor-core launch
+                wd = None
+                probs = ops.head_conv_softmax2(cur, wtc8, tensors[L.bi].detach(), (n, d, h, w), L.cin)
+            else:
+                wf, wd, _, _ = cache.conv3(tensors[L.wi], tc=False)
+                logits, _ = ops.conv3_fprop(cur, wf, tensors[L.bi].detach(), (n, d, h, w), L.cin, L.cout, torch.float32,
+                                            in_planar=L.in_planar, want_stats=False)
+                probs = ops.softmax2_fwd(logits, (n, d, h, w))
             if record:
                 tape.append((L, cur, probs, None, (n, d, h, w), (wd, wdtc)))
             cur = probs

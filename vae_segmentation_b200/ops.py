@@ -69,6 +69,28 @@ def pack_conv3_weight_tc(w, dgrad=False, out=None):
     return out
 
 
+def pack_conv3_weight_tc_padded(w, cin_pad, cout_pad, dgrad=False, out=None):
+    """bf16 tensor-core pack of a [Cout,Cin,3,3,3] weight zero-padded to cin_pad / cout_pad channels."""
+    cout, cin = w.shape[0], w.shape[1]
+    nbytes = _cabi.lib().vs_conv3_tc_pack_bytes(cin_pad, cout_pad, int(dgrad))
+    if nbytes == 0:
+        return None
+    if out is None:
+        out = torch.empty(nbytes // 2, device=w.device, dtype=torch.bfloat16)
+    _cabi.call("vs_pack_conv3_weight_tc_padded", _p(_f32(w, "weight")), _p(out), cin, cout, cin_pad, cout_pad, int(dgrad), _stream())
+    return out
+
+
+def head_conv_softmax2(x, wtc8, bias, dims, cin):
+    """probs [N,2,D,H,W] fp32 = softmax(conv3(x, w) + bias): the 2-class head in one tensor-core launch."""
+    n, d, h, w = dims
+    if x.dtype != torch.bfloat16:
+        raise RuntimeError("vaeseg_b200: head_conv_softmax2 takes bf16 NDHWC activations")
+    probs = torch.empty(n, 2, d, h, w, device=x.device, dtype=torch.float32)
+    _cabi.call("vs_head_conv_softmax2_fwd", _p(x), _p(wtc8), _p(_f32(bias, "bias")), _p(probs), n, d, h, w, cin, _stream())
+    return probs
+
+
 def pack_conv3_batched(jobs_dev, njobs):
     """One launch re-packing every layer described by the device job table (engine.PackCache.repack_all)."""
     _cabi.call("vs_pack_conv3_batched", _p(jobs_dev), int(njobs), _stream())
