@@ -325,12 +325,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
                     asm volatile("bar.sync 1, 128;" ::: "memory");
                 }
             }
-            mbar_wait(&tfull_bar[buf], bphase);
-            tc_fence_after();
             const int jmax = min(p.td, p.d - d0);
             const int gh = h0 + lh, gw = w0 + lw;
             const bool rc_ok = gh < p.h && gw < p.w;
-            for (int j = 0; j < jmax; ++j) {
+            // fused norm-backward reduction: the previous layer's raw output at this thread's voxels is fetched BEFORE
+            // waiting for the accumulators, so the global latency hides behind the MMAs of the tile (NC = 16 only: at
+            // NC >= 32 the registers are needed for the running sums and the loads stay inline)
+            uint4 ypre[NC == 16 ? TD : 1][2];
+            if (NC == 16 && fused) {
+#pragma unroll
+                for (int j = 0; j < TD; ++j) {
+#pragma unroll
+                    for (int h8 = 0; h8 < 2; ++h8) {
+                        ypre[NC == 16 ? j : 0][h8] = make_uint4(0u, 0u, 0u, 0u);
+                        if (j < jmax && rc_ok && co0 + h8 * 8 < p.cout)
+                            ypre[NC == 16 ? j : 0][h8] = __ldg(reinterpret_cast<const uint4*>(
+                                p.yprev + (((long long)n * p.d + d0 + j) * p.h + gh) * (long long)p.w * p.cout + (long long)gw * p.cout + co0 + h8 * 8));
+                    }
+                }
+            }
+            mbar_wait(&tfull_bar[buf], bphase);
+            tc_fence_after();
+#pragma unroll
+            for (int j = 0; j < TD; ++j) {
+                if (j >= jmax) break;
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (buf * TD + j) * NC;
                 const long long yoff = (((long long)n * p.d + d0 + j) * p.h + gh) * (long long)p.w * p.cout + (long long)gw * p.cout + co0;
                 bf16* py = p.y + yoff;
@@ -393,9 +411,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
 #pragma unroll
                         for (int h8 = 0; h8 < 2; ++h8) {
                             float yv[8];
+                            if (NC == 16) {
+                                const uint4 raw = ypre[NC == 16 ? j : 0][h8];
+                                const uint32_t u[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-                            for (int k = 0; k < 8; ++k) yv[k] = 0.f;
-                            if (rc_ok && co0 + c16 * 16 + h8 * 8 < p.cout) Store<bf16>::ld8(p.yprev + yoff + c16 * 16 + h8 * 8, yv);
+                                for (int i2 = 0; i2 < 4; ++i2) { yv[2 * i2] = __uint_as_float(u[i2] << 16); yv[2 * i2 + 1] = __uint_as_float(u[i2] & 0xffff0000u); }
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) yv[k] = 0.f;
+                                if (rc_ok && co0 + c16 * 16 + h8 * 8 < p.cout) Store<bf16>::ld8(p.yprev + yoff + c16 * 16 + h8 * 8, yv);
+                            }
 #pragma unroll
                             for (int k4 = 0; k4 < 2; ++k4) {
                                 const float4 mu = lds128(smean_addr + (c16 * 16 + h8 * 8 + k4 * 4) * 4);

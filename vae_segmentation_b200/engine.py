@@ -321,7 +321,7 @@ def program_backward(tape, g, dtype, need, grads, param_refs, need_input_grad):
         Lp = tape[idx - 1][0]
         if Lp.kind != C3IN or (Lp.save_as is not None and Lp.save_as in pending):
             return None
-        if not ops.dgrad_can_fuse_reduce(dy_like, cin, cout, dtype, False, wdtc):
+        if not ops.dgrad_can_fuse_reduce(dy_like, cin, cout, dtype, False, wdtc, tape[idx][4]):
             return None
         fused.add(idx - 1)
         return tape[idx - 1][2], tape[idx - 1][3], sums_of[idx - 1]

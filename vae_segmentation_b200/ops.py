@@ -151,12 +151,17 @@ def conv3_fprop(x, wf, bias, dims, cin, cout, out_dtype, in_planar=False, out_pl
     return y, stats
 
 
-def dgrad_can_fuse_reduce(dy, cin, cout, out_dtype, out_planar, wdtc):
+def dgrad_can_fuse_reduce(dy, cin, cout, out_dtype, out_planar, wdtc, dims=None):
     """Whether conv3_dgrad takes the tensor-core path for this call, i.e. may fuse the previous layer's
-    InstanceNorm-backward reduction into its epilogue."""
+    InstanceNorm-backward reduction into its epilogue -- and whether that pays: the 16-column kernel variant prefetches
+    the previous layer's output behind the MMAs (fusion is free at every size); the 32-column variant (32 <= Cin < 64)
+    loads it inline, which only beats a separate reduction launch on small volumes (measured: <= 16^3 per sample)."""
     gin, gout = cout, cin
-    return (wdtc is not None and dy.dtype == torch.bfloat16 and out_dtype == torch.bfloat16 and not out_planar
-            and (gin == 8 or (gin >= 16 and gin % 16 == 0)) and gout >= 8 and gout % 8 == 0)
+    ok = (wdtc is not None and dy.dtype == torch.bfloat16 and out_dtype == torch.bfloat16 and not out_planar
+          and (gin == 8 or (gin >= 16 and gin % 16 == 0)) and gout >= 8 and gout % 8 == 0)
+    if ok and dims is not None and 32 <= gout < 64:
+        ok = dims[1] * dims[2] * dims[3] <= 4096
+    return ok
 
 
 def conv3_dgrad(dy, wd, dims, cin, cout, out_dtype, out_planar=False, wdtc=None, prev=None):
