@@ -694,7 +694,7 @@ extern "C" int vs_conv3x3x3_tc(const void* x, const void* wtc, void* y, double* 
 
 extern "C" int vs_pack_conv3_batched(const void* jobs_dev, int njobs, void* stream) {
     VS_REQUIRE(jobs_dev && njobs > 0, VS_ERR_SHAPE, "pack_conv3_batched: bad arguments");
-    dim3 grid(32, (unsigned)njobs);
+    dim3 grid((unsigned)vs_sm_count(), (unsigned)njobs);    // grid-stride per job: the 128/256-channel layers carry most elements
     pack_batched_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const vs_pack_job*)jobs_dev);
     VS_CHECK_LAUNCH("pack_batched_kernel");
     return VS_OK;

@@ -46,6 +46,17 @@ __host__ __device__ constexpr uint32_t make_idesc_mn(int n) {
            ((uint32_t)(MROWS >> 4) << 24);
 }
 
+// dst[0..3] += v as ONE 16-byte L2 atomic when dst is 16-byte aligned (sm_90+), else four scalar atomics.  The
+// read-back of the accumulators is bound by the L2 atomic unit (every CTA adds its partial dw onto the same lines).
+__device__ __forceinline__ void atomic_add4(float* dst, float4 v) {
+    if (vs_aligned16_dev(dst)) {
+        atomicAdd(reinterpret_cast<float4*>(dst), v);
+    } else {
+        atomicAdd(dst + 0, v.x); atomicAdd(dst + 1, v.y); atomicAdd(dst + 2, v.z); atomicAdd(dst + 3, v.w);
+    }
+}
+constexpr int WROW = 216 + 4;      // staged (co, 8-ci group) block: [c8][27] floats, padded row
+
 template <bool CIN8, int NCOG, int NSTAGE>
 __global__ void __launch_bounds__(NTHREADS, 1) conv3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap xmap,
                                                                      const __grid_constant__ CUtensorMap dymap, WgParams p) {
@@ -164,28 +175,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_wgrad_tc_kernel(const __gri
             // M = 64 accumulator rows live in lanes (row & 15) + 32 * (row >> 4): warp quadrant q holds rows 16q..16q+15
             const int q = warp & 3;
             const int co = mc * MROWS + q * 16 + lane;
-            const bool valid = lane < 16 && co < p.cout;
+            // dw[co][ci][27]: for one row and one 8-channel group of ci the 9 accumulators x 24 columns are 216
+            // CONTIGUOUS floats.  Stage them in that order in shared memory (the operand stages are free now: every
+            // MMA of the CTA has completed) and add them with 54 16-byte atomics per row instead of 216 scalar ones.
+            float* stage_f = reinterpret_cast<float*>(smem) + (size_t)q * 16 * WROW;
 #pragma unroll 1
-            for (int g = 0; g < NG; ++g) {
-                const int cg = g / 9, t9 = g % 9;
-                uint32_t r[24];
-                uint32_t r0[8], r1[8], r2[8];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + g * 24;
-                tmem_ld8(taddr, r0);
-                tmem_ld8(taddr + 8, r1);
-                tmem_ld8(taddr + 16, r2);
-                tmem_ld_wait();
+            for (int cg = 0; cg < XP; ++cg) {
+#pragma unroll 1
+                for (int t9 = 0; t9 < 9; ++t9) {
+                    uint32_t r0[8], r1[8], r2[8];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (cg * 9 + t9) * 24;
+                    tmem_ld8(taddr, r0);
+                    tmem_ld8(taddr + 8, r1);
+                    tmem_ld8(taddr + 16, r2);
+                    tmem_ld_wait();
+                    if (lane < 16) {
+                        float* dst = stage_f + lane * WROW + t9 * 3;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) { r[k] = r0[k]; r[8 + k] = r1[k]; r[16 + k] = r2[k]; }
-                if (valid) {
-                    float* base = p.dw + ((long long)co * p.cin + ks * 16 + cg * 8) * 27 + t9 * 3;
-#pragma unroll
-                    for (int kw = 0; kw < 3; ++kw)
-#pragma unroll
-                        for (int c8 = 0; c8 < 8; ++c8)
-                            atomicAdd(base + c8 * 27 + kw, __uint_as_float(r[kw * 8 + c8]));
+                        for (int c8 = 0; c8 < 8; ++c8) {
+                            dst[c8 * 27 + 0] = __uint_as_float(r0[c8]);
+                            dst[c8 * 27 + 1] = __uint_as_float(r1[c8]);
+                            dst[c8 * 27 + 2] = __uint_as_float(r2[c8]);
+                        }
+                    }
                 }
+                __syncwarp();
+                for (int i = lane; i < 16 * 54; i += 32) {
+                    const int row = i / 54, f4 = i - row * 54;
+                    const int cor = mc * MROWS + q * 16 + row;
+                    if (cor < p.cout) {
+                        const float4 v = *reinterpret_cast<const float4*>(stage_f + row * WROW + f4 * 4);
+                        atomic_add4(p.dw + ((long long)cor * p.cin + ks * 16 + cg * 8) * 27 + f4 * 4, v);
+                    }
+                }
+                __syncwarp();
             }
+            (void)co;
         }
     }
     tc_fence_before();
@@ -339,9 +364,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_wgrad_dsh_kernel(const __gr
             const int m = row >> 3, co = row & 7;
             const bool valid = lane < 16 && m <= 2;
             if (q < 2) {
-                // the K-split partial accumulators of one (ci group, kh) are summed in registers first: one atomic per
-                // CTA and weight element (the atomics onto the same few cache lines from 148 CTAs are not free)
+                // The K-split partial accumulators of one (ci group, kh) are summed in registers, staged in shared
+                // memory (free now) in dw's own order -- [co][ci group][c8][27] -- and added with 16-byte atomics:
+                // 54 per (co, ci group) instead of 216 scalar ones per partial (the L2 atomic unit bounds the tail).
                 constexpr int NSETS = CIN8 ? 4 : 2, NCG = CIN8 ? 1 : 2;
+                float* stage_f = reinterpret_cast<float*>(smem);                  // [8 co][NCG][WROW]
 #pragma unroll 1
                 for (int gcg = 0; gcg < NCG; ++gcg) {
 #pragma unroll 1
@@ -364,15 +391,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_wgrad_dsh_kernel(const __gr
                             }
                         }
                         if (valid) {
-                            float* base = p.dw + ((long long)co * p.cin + ks * 16 + gcg * 8) * 27 + (2 - m) * 9 + kh * 3;
+                            float* dst = stage_f + (co * NCG + gcg) * WROW + (2 - m) * 9 + kh * 3;
 #pragma unroll
                             for (int c8 = 0; c8 < 8; ++c8) {
-                                atomicAdd(base + c8 * 27 + 0, s0[c8]);
-                                atomicAdd(base + c8 * 27 + 1, s1[c8]);
-                                atomicAdd(base + c8 * 27 + 2, s2[c8]);
+                                dst[c8 * 27 + 0] = s0[c8];
+                                dst[c8 * 27 + 1] = s1[c8];
+                                dst[c8 * 27 + 2] = s2[c8];
                             }
                         }
                     }
+                }
+                asm volatile("bar.sync 2, 64;" ::: "memory");                     // the two read-back warps (q = 0, 1)
+                const int t64 = q * 32 + lane;
+                for (int i = t64; i < 8 * NCG * 54; i += 64) {
+                    const int blk = i / 54, f4 = i - blk * 54;
+                    const int cor = blk / NCG, gcg = blk % NCG;
+                    const float4 v = *reinterpret_cast<const float4*>(stage_f + blk * WROW + f4 * 4);
+                    atomic_add4(p.dw + ((long long)cor * p.cin + ks * 16 + gcg * 8) * 27 + f4 * 4, v);
                 }
             }
         }

@@ -93,19 +93,24 @@ class PackCache(object):
         mode) and the tcgen05 path takes the shape."""
         tc = bool(tc and USE_TENSOR_CORES)
         ent, key = self._entry("conv3", w, tc)
-        if ent["key"] != key or (tc and not ent["tc"]):
+        stale_fp32 = ent["wf"] is None and not (tc and ent["tcf"] is not None and ent["tcd"] is not None)
+        if ent["key"] != key or (tc and not ent["tc"]) or stale_fp32:
             wdet = w.detach()
             cout, cin = wdet.shape[0], wdet.shape[1]
-            if ent["wf"] is None:
-                ent["wf"] = torch.empty(27, cin, cout, device=wdet.device, dtype=torch.float32)
-                ent["wd"] = torch.empty(27, cout, cin, device=wdet.device, dtype=torch.float32)
-            ops.pack_conv3_weight(wdet, out=(ent["wf"], ent["wd"]))
             if tc:
                 ent["tcf"] = ops.pack_conv3_weight_tc(wdet, dgrad=False, out=ent["tcf"])
                 ent["tcd"] = ops.pack_conv3_weight_tc(wdet, dgrad=True, out=ent["tcd"])
                 if not ent["tc"]:
                     self._jobs = None
                 ent["tc"] = True
+            # the fp32 [27][Cin][Cout] packs feed the CUDA-core direct kernels only: skipped for layers whose fprop AND
+            # dgrad both run on the tensor cores (most of the re-pack traffic after every optimiser step)
+            if not (tc and ent["tcf"] is not None and ent["tcd"] is not None):
+                if ent["wf"] is None:
+                    ent["wf"] = torch.empty(27, cin, cout, device=wdet.device, dtype=torch.float32)
+                    ent["wd"] = torch.empty(27, cout, cin, device=wdet.device, dtype=torch.float32)
+                    self._jobs = None
+                ops.pack_conv3_weight(wdet, out=(ent["wf"], ent["wd"]))
             ent["key"] = key
         return ent["wf"], ent["wd"], ent["tcf"], ent["tcd"]
 
