@@ -210,6 +210,14 @@ int vs_ema_update(float* teacher, const float* student, long long count, float a
  * writes final loss and the two scalar weights (d final/d recon, d final/d fake, d final/d kl). */
 int vs_compose_target_loss(const float* terms, float lambda_vae, int loss_type, int use_kl,
                            float* final_loss, float* weights, void* stream);
+/* The scalar tail of a teacher-student step in ONE launch (main_target.py:543-546,550-560,588-590): from the three
+ * vs_dice_sums results (student vs reconstruction, vs ground truth [monitor, may be NULL], vs pseudo label) and the
+ * teacher KL value (may be NULL): out5 = (final, recon_loss, dice_loss, dice_loss_fake, kl) with
+ * loss = 1 - mean_{n, c in [bot,top)} Dice, and gper2[2][N][C] = d final / d Dice[n][c] of the reconstruction and the
+ * pseudo-label term (the gper arguments of the two vs_dice_bwd launches).  only_pseudo: final = dice_loss_fake.   */
+int vs_joint_target_finish(const float* sums_recon, const float* sums_gt, const float* sums_fake, const float* kl,
+                           int n, int c, int bot, int top, float eps, float lambda_vae, int loss_type, int use_kl,
+                           int only_pseudo, float* out5, float* gper2, void* stream);
 
 #ifdef __cplusplus
 }

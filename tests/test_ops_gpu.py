@@ -325,3 +325,48 @@ def test_sgd_adam_ema():
     td = t.to(DEV)
     ops.ema_update(td, s.to(DEV), 0.995)
     check(td, 0.995 * t + 0.005 * s, torch.float32, what="ema")
+
+
+@pytest.mark.parametrize("cfg", [(1.0, 0, False, False, False), (0.7, 8, True, False, True), (1.0, 0, False, True, False),
+                                 (2.0, 8, False, False, False)])
+def test_joint_target_loss_fused_vs_composed(cfg):
+    """ev.joint_target_loss (one autograd node, one scalar kernel) against the same loss composed from the
+    reference-named pieces (avg_dsc / KLloss + main_target.py:550-560,588-590 arithmetic in torch)."""
+    from vae_segmentation_b200 import evaluation as ev
+    lam, loss_type, use_kl, only_pseudo, confident = cfg
+    torch.manual_seed(5)
+    n, d = 2, 12
+    mk = lambda: torch.softmax(torch.randn(n, 2, d, d, d, device=DEV) * 2, 1)
+    pred0, recon0, tpred = mk(), mk(), mk()
+    label = (torch.rand(n, 1, d, d, d, device=DEV) > 0.7).float()
+    kl = torch.tensor(3.25, device=DEV)
+    outs = []
+    for fused in (True, False):
+        pred, recon = pred0.clone().requires_grad_(), recon0.clone().requires_grad_()
+        if fused:
+            final, mon = ev.joint_target_loss(pred, recon, label, tpred, kl=kl, lambda_vae=lam, loss_type=loss_type,
+                                              use_kl=use_kl, only_pseudo=only_pseudo, confident=confident)
+            mon = mon.cpu()
+        else:
+            r = 1 - ev.avg_dsc_fused(pred, recon, "tensor", botindex=1, topindex=2)
+            g = 1 - ev.avg_dsc_fused(pred.detach(), label, "label", botindex=1, topindex=2)
+            f = 1 - ev.avg_dsc_fused(pred, tpred, "confident" if confident else "binarize", botindex=1, topindex=2)
+            if only_pseudo:
+                final = f
+            elif loss_type == 8:
+                rv = r.item()
+                cur = lam * (0.6 if rv < 0.15 else 1.2 if rv < 0.225 else 2.0 if rv < 0.3 else 3.0)
+                final = (r + f / cur + (kl if use_kl else 0)) if cur > 1 else (cur * r + f + (cur * kl if use_kl else 0))
+            else:
+                final = lam * r + f + (0.00002 * lam * kl if use_kl else 0)
+            mon = torch.stack([final.detach(), r.detach(), g.detach(), f.detach(), kl]).cpu()
+        final.backward()
+        outs.append((final.detach().cpu(), mon, pred.grad.cpu(), recon.grad.cpu() if recon.grad is not None else None))
+    (fa, ma, ga, ra), (fb, mb, gb, rb) = outs
+    assert torch.allclose(fa, fb, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(ma, mb, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(ga, gb, rtol=1e-4, atol=1e-9)
+    if rb is None:
+        assert ra is None or ra.abs().max().item() == 0.0
+    else:
+        assert torch.allclose(ra, rb, rtol=1e-4, atol=1e-9)

@@ -162,6 +162,51 @@ __global__ void compose_target_loss_kernel(const float* __restrict__ terms, floa
     final_loss[0] = wr * recon + wf * fake + wk * kl;
 }
 
+// One thread: the three Dice evaluations of a teacher-student step -> scalar losses, the composed final loss and
+// the gradient of the final loss w.r.t. every per-(n,c) Dice value (what vs_dice_bwd takes as gper).
+//   loss_x = 1 - mean_{n, c in [bot,top)} 2 I/(S+T+eps)     main_target.py:543-546,588-590 (type 0), :550-560 (type 8)
+__global__ void joint_target_finish_kernel(const float* __restrict__ sums_r, const float* __restrict__ sums_g,
+                                           const float* __restrict__ sums_f, const float* __restrict__ kl, int n, int c,
+                                           int bot, int top, float eps, float lambda_vae, int loss_type, int use_kl,
+                                           int only_pseudo, float* __restrict__ out, float* __restrict__ gper) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const float inv = 1.f / (float)(n * (top - bot));
+    float loss[3];
+    const float* srcs[3] = {sums_r, sums_g, sums_f};
+    for (int k = 0; k < 3; ++k) {
+        float acc = 0.f;
+        if (srcs[k] != nullptr)
+            for (int i = 0; i < n; ++i)
+                for (int ch = bot; ch < top; ++ch) {
+                    const float* sm = srcs[k] + ((long long)i * c + ch) * 3;
+                    acc += 2.f * sm[0] / (sm[1] + sm[2] + eps);
+                }
+        loss[k] = 1.f - acc * inv;
+    }
+    const float recon = loss[0], fake = loss[2], klv = kl != nullptr ? kl[0] : 0.f;
+    float wr, wf, wk;
+    if (only_pseudo) { wr = 0.f; wf = 1.f; wk = 0.f; }
+    else if (loss_type == 8) {                  // main_target.py:550-560
+        float cur;
+        if (recon < 0.15f) cur = lambda_vae * 0.6f;
+        else if (recon < 0.225f) cur = lambda_vae * 1.2f;
+        else if (recon < 0.3f) cur = lambda_vae * 2.0f;
+        else cur = lambda_vae * 3.0f;
+        if (cur > 1.f) { wr = 1.f; wf = 1.f / cur; wk = use_kl ? 1.f : 0.f; }
+        else { wr = cur; wf = 1.f; wk = use_kl ? cur : 0.f; }
+    } else {                                    // main_target.py:588-590
+        wr = lambda_vae; wf = 1.f; wk = use_kl ? 0.00002f * lambda_vae : 0.f;
+    }
+    out[0] = wr * recon + wf * fake + wk * klv;
+    out[1] = recon; out[2] = loss[1]; out[3] = fake; out[4] = klv;
+    for (int i = 0; i < n; ++i)
+        for (int ch = 0; ch < c; ++ch) {
+            const float g = (ch >= bot && ch < top) ? -inv : 0.f;
+            gper[(long long)i * c + ch] = wr * g;
+            gper[(long long)(n + i) * c + ch] = wf * g;
+        }
+}
+
 int red_grid(long long s) { return (int)max(1LL, min((s / 4 + NT - 1) / NT, (long long)vs_sm_count() * 2)); }
 
 }  // namespace
@@ -219,6 +264,17 @@ extern "C" int vs_one_hot(const float* label, float* out, int n, int c, long lon
     dim3 grid((unsigned)max(1LL, min((s + NT - 1) / NT, (long long)vs_sm_count() * 8)), n);
     one_hot_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(label, out, c, s);
     VS_CHECK_LAUNCH("one_hot_kernel");
+    return VS_OK;
+}
+
+extern "C" int vs_joint_target_finish(const float* sums_recon, const float* sums_gt, const float* sums_fake, const float* kl,
+                                      int n, int c, int bot, int top, float eps, float lambda_vae, int loss_type,
+                                      int use_kl, int only_pseudo, float* out5, float* gper2, void* stream) {
+    VS_REQUIRE(sums_recon && sums_fake && out5 && gper2 && n > 0 && c > 0 && bot >= 0 && top > bot && top <= c, VS_ERR_SHAPE,
+               "joint_target_finish: bad arguments");
+    joint_target_finish_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sums_recon, sums_gt, sums_fake, kl, n, c, bot, top, eps,
+                                                                  lambda_vae, loss_type, use_kl, only_pseudo, out5, gper2);
+    VS_CHECK_LAUNCH("joint_target_finish_kernel");
     return VS_OK;
 }
 

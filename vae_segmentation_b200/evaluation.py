@@ -110,6 +110,50 @@ def KLloss(data_dict, mean_key='mean', std_key='std'):
     return _KLFn.apply(_prep(data_dict[mean_key], "KLloss"), _prep(data_dict[std_key], "KLloss"))
 
 
+class _JointTargetLossFn(torch.autograd.Function):
+    """The loss tail of a teacher-student step as ONE autograd node: three fused Dice reductions, one scalar kernel
+    (losses, dynamic-lambda composition, per-Dice gradients), and in backward two fused elementwise passes -- instead
+    of ~45 tiny ATen kernels.  main_target.py:543-546 (terms), :550-560 / :588-590 (composition)."""
+
+    @staticmethod
+    def forward(ctx, pred, recon, label, teacher_pred, kl, cfg):
+        lambda_vae, loss_type, use_kl, only_pseudo, fake_mode, eps = cfg
+        sums_r = ops.dice_sums(pred, recon, TGT_TENSOR)
+        sums_g = ops.dice_sums(pred, label, TGT_LABEL) if label is not None else None
+        sums_f = ops.dice_sums(pred, teacher_pred, fake_mode)
+        out5, gper2 = ops.joint_target_finish(sums_r, sums_g, sums_f, kl, 1, 2, eps, lambda_vae, loss_type, use_kl, only_pseudo)
+        ctx.save_for_backward(pred, recon, teacher_pred, sums_r, sums_f, gper2)
+        ctx.cfg = (fake_mode, eps)
+        mon = out5.detach()
+        ctx.mark_non_differentiable(mon)
+        return out5[0], mon
+
+    @staticmethod
+    def backward(ctx, g, _gmon):
+        pred, recon, teacher_pred, sums_r, sums_f, gper2 = ctx.saved_tensors
+        fake_mode, eps = ctx.cfg
+        gper = gper2 * g
+        want_pred, want_recon = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gpred, grecon = ops.dice_bwd(pred, recon, TGT_TENSOR, sums_r, gper[0], eps, want_src=want_pred, want_tgt=want_recon)
+        if want_pred:
+            ops.dice_bwd(pred, teacher_pred, fake_mode, sums_f, gper[1], eps, want_src=True, gsrc=gpred, accumulate=True)
+        return gpred, grecon, None, None, None, None
+
+
+def joint_target_loss(pred, recon, label, teacher_pred, kl=None, lambda_vae=1.0, loss_type=0, use_kl=False,
+                      only_pseudo=False, confident=False, eps=0.000001):
+    """(final, mon) with mon = [final, recon_loss, dice_loss, dice_loss_fake, kl] (detached).  Single-process form of
+    the loss tail of main_target.py:543-603; with loss_type 8 under data parallelism use the composed path of
+    train_step.JointTrainer (the recon term is all-reduced between the reductions and the composition)."""
+    pred = _prep(pred, "joint_target_loss")
+    recon = _prep(recon, "joint_target_loss")
+    teacher_pred = _prep(teacher_pred, "joint_target_loss").detach()
+    label = _prep(label, "joint_target_loss").detach() if label is not None else None
+    kl = kl.detach().reshape(1).float().contiguous() if kl is not None else None
+    cfg = (float(lambda_vae), int(loss_type), bool(use_kl), bool(only_pseudo), TGT_CONFIDENT if confident else TGT_BINARIZE, eps)
+    return _JointTargetLossFn.apply(pred, recon, label, teacher_pred, kl, cfg)
+
+
 def avg_ce(data_dict, source_key='align_lung', target_key='source_lung'):
     raise NotImplementedError("avg_ce (BCE) is not on the training hot path: no shipped preset calls it "
                               "(SURVEY.md section 2); not implemented in vaeseg_b200")

@@ -384,3 +384,13 @@ def compose_target_loss(terms, lambda_vae, loss_type, use_kl):
     _cabi.call("vs_compose_target_loss", _p(_f32(terms, "terms")), float(lambda_vae), int(loss_type), int(use_kl),
                _p(final), _p(weights), _stream())
     return final, weights
+
+
+def joint_target_finish(sums_r, sums_g, sums_f, kl, bot, top, eps, lambda_vae, loss_type, use_kl, only_pseudo):
+    """(out5, gper2): see vs_joint_target_finish."""
+    n, c = sums_r.shape[0], sums_r.shape[1]
+    out5 = torch.empty(5, device=sums_r.device, dtype=torch.float32)
+    gper2 = torch.empty(2, n, c, device=sums_r.device, dtype=torch.float32)
+    _cabi.call("vs_joint_target_finish", _p(sums_r), _p(sums_g), _p(sums_f), _p(_f32(kl, "kl")), n, c, int(bot), int(top),
+               float(eps), float(lambda_vae), int(loss_type), int(use_kl), int(only_pseudo), _p(out5), _p(gper2), _stream())
+    return out5, gper2

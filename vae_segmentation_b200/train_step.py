@@ -167,6 +167,7 @@ class JointTrainer(object):
         self.lambda_vae, self.loss_type, self.kl = lambda_vae, loss_type, kl
         self.confident, self.only_pseudo, self.alpha = confident, only_pseudo, alpha
         self.faithful_teacher = faithful_teacher
+        self.fused_loss = os.environ.get("VAESEG_NO_FUSED_LOSS", "0") != "1"     # ev.joint_target_loss (one autograd node)
         self.stream = torch.cuda.Stream()        # see capture()
         # Concurrency inside the step (parallel branches of the captured graph): the frozen teacher's forward is
         # independent of the student's until the losses, and the weight-gradient kernels are leaves of the backward
@@ -207,6 +208,13 @@ class JointTrainer(object):
         else:
             tb = run_teacher()
         pred = batch["pred"]
+        if self.fused_loss and not (self.loss_type == 8 and _world() > 1):
+            klv = ev.KLloss(tb) if tb.get("mean") is not None else None                                   # :544 (teacher's, F8)
+            final, m5 = ev.joint_target_loss(pred, batch["recon_pred"], label, tb["only_fake"], kl=klv,
+                                             lambda_vae=self.lambda_vae, loss_type=self.loss_type, use_kl=self.kl,
+                                             only_pseudo=self.only_pseudo, confident=self.confident)
+            mon = {"final_loss": m5[0], "recon_loss": m5[1], "dice_loss": m5[2], "dice_loss_fake": m5[3], "kl_loss": m5[4]}
+            return final, mon, batch
         recon_loss = 1 - ev.avg_dsc_fused(pred, batch["recon_pred"], "tensor", botindex=1, topindex=2)      # :543
         dsc_loss = 1 - ev.avg_dsc_fused(pred.detach(), label, "label", botindex=1, topindex=2)             # :545 (monitor)
         dsc_loss_fake = 1 - ev.avg_dsc_fused(pred, tb["only_fake"], "confident" if self.confident else "binarize",
