@@ -210,6 +210,9 @@ int vs_ema_update(float* teacher, const float* student, long long count, float a
  * writes final loss and the two scalar weights (d final/d recon, d final/d fake, d final/d kl). */
 int vs_compose_target_loss(const float* terms, float lambda_vae, int loss_type, int use_kl,
                            float* final_loss, float* weights, void* stream);
+/* dst[r][0..row_len) += src[r * src_row_stride + 0..row_len) with atomics (gradient fan-in from concurrent streams) */
+int vs_atomic_add_rows(float* dst, const float* src, long long rows, long long row_len, long long src_row_stride,
+                       void* stream);
 /* The scalar tail of a teacher-student step in ONE launch (main_target.py:543-546,550-560,588-590): from the three
  * vs_dice_sums results (student vs reconstruction, vs ground truth [monitor, may be NULL], vs pseudo label) and the
  * teacher KL value (may be NULL): out5 = (final, recon_loss, dice_loss, dice_loss_fake, kl) with

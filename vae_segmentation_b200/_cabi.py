@@ -56,6 +56,7 @@ _SIGNATURES = {
     "vs_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _P],
     "vs_ema_update": [_P, _P, _L, _F, _P],
     "vs_compose_target_loss": [_P, _F, _I, _I, _P, _P, _P],
+    "vs_atomic_add_rows": [_P, _P, _L, _L, _L, _P],
     "vs_joint_target_finish": [_P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _I, _I, _I, _P, _P, _P],
 }
 _RESTYPES = {"vs_last_error_string": c_char_p, "vs_conv3_wgrad_workspace_bytes": c_size_t,

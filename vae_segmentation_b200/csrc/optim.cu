@@ -40,6 +40,17 @@ __global__ void __launch_bounds__(NT) ema_kernel(float* __restrict__ teacher, co
         teacher[i] = alpha * teacher[i] + (1.f - alpha) * student[i];
 }
 
+// dst[r][i] += src[r * src_row_stride + i] with atomics: parameter-gradient fan-in from concurrent streams (per-sample
+// backward chains add their partial weight gradients onto the same .grad)
+__global__ void __launch_bounds__(NT) atomic_add_rows_kernel(float* __restrict__ dst, const float* __restrict__ src,
+                                                             long long rows, long long row_len, long long src_row_stride) {
+    const long long total = rows * row_len;
+    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+        const long long r = i / row_len, c = i - r * row_len;
+        atomicAdd(dst + i, src[r * src_row_stride + c]);
+    }
+}
+
 int ew_grid(long long count) { return (int)max(1LL, min((count + NT - 1) / NT, (long long)vs_sm_count() * 8)); }
 }  // namespace
 
@@ -64,5 +75,13 @@ extern "C" int vs_ema_update(float* teacher, const float* student, long long cou
     VS_REQUIRE(teacher && student && count > 0, VS_ERR_SHAPE, "ema_update: bad arguments");
     ema_kernel<<<ew_grid(count), NT, 0, (cudaStream_t)stream>>>(teacher, student, count, alpha);
     VS_CHECK_LAUNCH("ema_kernel");
+    return VS_OK;
+}
+
+extern "C" int vs_atomic_add_rows(float* dst, const float* src, long long rows, long long row_len, long long src_row_stride,
+                                  void* stream) {
+    VS_REQUIRE(dst && src && rows > 0 && row_len > 0 && src_row_stride >= row_len, VS_ERR_SHAPE, "atomic_add_rows: bad arguments");
+    atomic_add_rows_kernel<<<ew_grid(rows * row_len), NT, 0, (cudaStream_t)stream>>>(dst, src, rows, row_len, src_row_stride);
+    VS_CHECK_LAUNCH("atomic_add_rows_kernel");
     return VS_OK;
 }

@@ -22,7 +22,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "{\n\t"
         ".reg .pred p;\n\t"
         "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n\t"    // suspend-time hint: sleep in hardware, do not poll the shared-memory pipe the MMA operands use
         "@p bra DONE;\n\t"
         "bra WAIT_LOOP;\n\t"
         "DONE:\n\t"

@@ -352,7 +352,8 @@ def program_backward(tape, g, dtype, need, grads, param_refs, need_input_grad):
                         # tensor-core wgrad; the padded input channels give zero rows that are dropped
                         dw8, _ = ops.conv3_wgrad(ops.planar_to_ndhwc8(x_in), dy, dims, 8, L.cout)
                         if acc:
-                            tgt.add_(dw8[:, :L.cin])
+                            ops.atomic_add_rows(tgt, dw8, L.cout, L.cin * 27, 8 * 27)      # += dw8[:, :cin]; atomics:
+                            # other per-sample backward chains may be adding onto the same .grad concurrently
                             return tgt
                         return dw8[:, :L.cin].contiguous()
                     return ops.conv3_wgrad(x_in, dy, dims, L.cin, L.cout, dw=tgt, in_planar=L.in_planar, accumulate=acc)[0]
@@ -396,7 +397,7 @@ def program_backward(tape, g, dtype, need, grads, param_refs, need_input_grad):
                     def run_head_wgrad(x_in=x_in, dl8=dl8, dims=dims, tw=tw, acc=acc, L=L):
                         dw8, _ = ops.conv3_wgrad(x_in, dl8, dims, L.cin, 8)
                         if acc:
-                            tw.add_(dw8[:L.cout])
+                            ops.atomic_add_rows(tw, dw8, 1, L.cout * L.cin * 27, dw8.numel())  # += dw8[:cout] (atomics)
                         else:
                             tw.copy_(dw8[:L.cout])
                     _wgrad_async(run_head_wgrad, acc, x_in, dl8)

@@ -394,3 +394,8 @@ def joint_target_finish(sums_r, sums_g, sums_f, kl, bot, top, eps, lambda_vae, l
     _cabi.call("vs_joint_target_finish", _p(sums_r), _p(sums_g), _p(sums_f), _p(_f32(kl, "kl")), n, c, int(bot), int(top),
                float(eps), float(lambda_vae), int(loss_type), int(use_kl), int(only_pseudo), _p(out5), _p(gper2), _stream())
     return out5, gper2
+
+
+def atomic_add_rows(dst, src, rows, row_len, src_row_stride):
+    """dst[r, :row_len] += src[r*src_row_stride : +row_len] with atomics (dst contiguous fp32; src a base pointer)."""
+    _cabi.call("vs_atomic_add_rows", _p(_f32(dst, "dst")), src.data_ptr(), int(rows), int(row_len), int(src_row_stride), _stream())

@@ -168,7 +168,21 @@ class JointTrainer(object):
         self.confident, self.only_pseudo, self.alpha = confident, only_pseudo, alpha
         self.faithful_teacher = faithful_teacher
         self.fused_loss = os.environ.get("VAESEG_NO_FUSED_LOSS", "0") != "1"     # ev.joint_target_loss (one autograd node)
-        self.stream = torch.cuda.Stream()        # see capture()
+        # Per-sample chains: every op of the step is per-sample (InstanceNorm per (n,c), Dice per sample then batch
+        # mean), so the B samples of the per-GPU batch run as B independent forward/backward chains on their own
+        # streams (parallel branches of the captured graph).  Half of a chain's time is launch-latency-bound deep-level
+        # kernels on a handful of SMs: two chains overlap there, and serialise only on the full-resolution kernels
+        # that fill the GPU anyway.  Weight gradients of all chains accumulate onto the same .grad with atomics.
+        # Not used with the dynamic lambda (type 8 thresholds the BATCH reconstruction loss before composing).
+        # MEASURED (B200, 2 x 96^3): 279 vol/s with chains vs 313 without -- the full-resolution kernels are persistent
+        # 148-CTA grids that serialise across chains while their fixed cost doubles -- so it is opt-in
+        # (VAESEG_SAMPLE_PARALLEL=1); parity-tested (tests/test_models_gpu.py runs the joint step both ways).
+        self.sample_parallel = os.environ.get("VAESEG_SAMPLE_PARALLEL", "0") == "1"
+        self._chain_streams = {}
+        # the step's own (critical) chain runs at high priority; the teacher forward and the weight gradients, which
+        # only have to finish by the loss / the optimiser step, fill in behind it at the default priority
+        hp = -1 if os.environ.get("VAESEG_STREAM_PRIORITY", "1") == "1" else 0
+        self.stream = torch.cuda.Stream(priority=hp)        # see capture()
         # Concurrency inside the step (parallel branches of the captured graph): the frozen teacher's forward is
         # independent of the student's until the losses, and the weight-gradient kernels are leaves of the backward
         # chain.  Both are dominated by deep-level kernels that occupy 8-48 of the 148 SMs, so they overlap well.
@@ -232,12 +246,59 @@ class JointTrainer(object):
                "dice_loss_fake": dsc_loss_fake.detach(), "kl_loss": klloss.detach()}
         return final, mon, batch
 
+    def _use_chains(self, img):
+        return (self.sample_parallel and self.overlap and self.fused_loss and self.loss_type != 8 and img.shape[0] > 1
+                and self.student is not None)
+
+    def _chains(self, b):
+        st = self._chain_streams.get(b)
+        if st is None:
+            st = self._chain_streams[b] = (torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream())
+        return st            # (student chain, teacher, weight gradients) of sample b
+
+    def forward_backward(self, img, label):
+        """zero_grad + forward + backward of one step on the current stream; returns the monitored terms."""
+        from . import engine
+        self.arena.zero_grad()
+        if not self._use_chains(img):
+            final, mon, _ = self.losses(img, label)
+            self._backward(final)
+            return mon
+        cur = torch.cuda.current_stream()
+        B = img.shape[0]
+        mons = []
+        saved_teacher, saved_overlap = self.teacher_stream, self.overlap
+        try:
+            for b in range(B):
+                s_main, s_teacher, s_wgrad = self._chains(b)
+                s_main.wait_stream(cur)
+                self.teacher_stream = s_teacher
+                with torch.cuda.stream(s_main):
+                    final, mon, _ = self.losses(img[b:b + 1], label[b:b + 1])
+                    engine.WGRAD_STREAM = s_wgrad
+                    try:
+                        (final / B).backward()
+                        engine.join_wgrad_stream()
+                    finally:
+                        engine.WGRAD_STREAM = None
+                mons.append(mon)
+            for b in range(B):
+                cur.wait_stream(self._chains(b)[0])
+        finally:
+            self.teacher_stream, self.overlap = saved_teacher, saved_overlap
+        out = {}
+        for k in mons[0]:
+            vals = torch.stack([m[k].reshape(()) for m in mons])
+            for v in (m[k] for m in mons):
+                if torch.is_tensor(v) and v.is_cuda:
+                    v.record_stream(cur)
+            out[k] = vals.mean()
+        return out
+
     def step(self, img, label, update_teacher=False):
         if update_teacher:
             self.ema_teacher()
-        self.arena.zero_grad()
-        final, mon, _ = self.losses(img, label)
-        self._backward(final)
+        mon = self.forward_backward(img, label)
         self.opt.step(allreduce_mean_(self.arena.grad))
         return mon
 
@@ -266,9 +327,7 @@ class JointTrainer(object):
         torch.cuda.synchronize()
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph, stream=side):
-            self.arena.zero_grad()
-            final, mon, _ = self.losses(img_static, label_static)
-            self._backward(final)
+            mon = self.forward_backward(img_static, label_static)
         self._graph_mon = mon
         return self
 
