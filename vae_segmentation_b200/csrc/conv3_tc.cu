@@ -85,19 +85,22 @@ __device__ __forceinline__ float transpose_reduce16(float (&v)[16], int lane) {
 // voxel of the shift (tile index p.ref_tile of every sample): they are the first items of the lowest-numbered CTAs,
 // which the hardware dispatches first and which never wait, so a CTA spinning on a shift value always waits on a CTA
 // that is already running -- whatever else shares the GPU.  The remaining items follow in (n, tile, chunk) order.
-__device__ __forceinline__ void decode_work(long long item, const TcParams& p, int& n, int& d0, int& h0, int& w0, int& chunk) {
-    const long long nprod = (long long)p.n * p.nchunks;
+// 32-bit arithmetic (the host rejects launches with >= 2^31 work items): every role of every tile decodes its work
+// item, and 64-bit divisions by run-time values cost hundreds of cycles on the single-warp epilogue / issue chains.
+__device__ __forceinline__ void decode_work(long long item64, const TcParams& p, int& n, int& d0, int& h0, int& w0, int& chunk) {
+    const unsigned item = (unsigned)item64;
+    const unsigned nprod = (unsigned)(p.n * p.nchunks);
     int r;
     if (item < nprod) {
-        chunk = (int)(item % p.nchunks);
-        n = (int)(item / p.nchunks);
+        chunk = (int)(item % (unsigned)p.nchunks);
+        n = (int)(item / (unsigned)p.nchunks);
         r = p.ref_tile;
     } else {
-        const long long idx = item - nprod;
-        chunk = (int)(idx % p.nchunks);
-        const long long t = idx / p.nchunks;
-        n = (int)(t / (p.tiles_per_n - 1));
-        r = (int)(t % (p.tiles_per_n - 1));
+        const unsigned idx = item - nprod;
+        chunk = (int)(idx % (unsigned)p.nchunks);
+        const unsigned t = idx / (unsigned)p.nchunks;
+        n = (int)(t / (unsigned)(p.tiles_per_n - 1));
+        r = (int)(t % (unsigned)(p.tiles_per_n - 1));
         r += (r >= p.ref_tile);
     }
     w0 = (r % p.tiles_w) * TW; r /= p.tiles_w;
@@ -112,7 +115,7 @@ __device__ __forceinline__ void decode_work(long long item, const TcParams& p, i
 template <int NC, bool CIN8, int NSTAGE>
 __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_constant__ CUtensorMap xmap, TcParams p) {
     constexpr int A_BYTES = CIN8 ? (PLANE_BYTES + PLANE_PAD) : 2 * PLANE_BYTES;
-    constexpr int NMMA = CIN8 ? 18 : 27;                      // MMAs per d-plane per stage
+    constexpr int NMMA = CIN8 ? 14 : 27;                      // MMAs per d-plane per stage
     constexpr int B_BYTES = NMMA * NC * 32;                   // [mma][kc 2][NC/8][8 rows][16 B]
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr int NBUF = 2;
@@ -195,6 +198,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
                 if (active) {
                     const uint32_t a_base = smem_u32(smem + stage * STAGE_BYTES) + (uint32_t)(j * p.bh * p.bw) * 16u;
                     const uint32_t b_base = smem_u32(smem + stage * STAGE_BYTES) + A_BYTES;
+                    if (CIN8) {
+                        // Cin = 8: the two K chunks of an MMA are two filter taps.  Any two taps work -- the second
+                        // chunk is just the first one displaced by a constant number of halo voxels (LBO) -- so the 27
+                        // taps in (kd,kh,kw) order are paired (0,1),(2,3),...,(24,25),(26,zero weights): 14 MMAs.
+#pragma unroll
+                        for (int m = 0; m < 14; ++m) {
+                            const int t1 = 2 * m, t2 = (2 * m + 1 < 27) ? 2 * m + 1 : 26;
+                            const int o1 = ((t1 / 9) * p.bh + (t1 / 3) % 3) * p.bw + t1 % 3;
+                            const int o2 = ((t2 / 9) * p.bh + (t2 / 3) % 3) * p.bw + t2 % 3;
+                            const uint32_t lbo = (2 * m + 1 < 27) ? (uint32_t)(o2 - o1) * 16u : 16u;
+                            const uint64_t ad = make_desc(a_base + (uint32_t)o1 * 16u, lbo, (uint32_t)p.bw * 16u);
+                            const uint64_t bd = make_desc(b_base + m * (NC * 32), NC * 16, 128u);
+                            tc_mma_elect(dcol, ad, bd, idesc, (ks | m) != 0);
+                        }
+                    } else {
                     int m = 0;
 #pragma unroll 1
                     for (int kd = 0; kd < 3; ++kd) {
@@ -202,13 +220,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
                         for (int kh = 0; kh < 3; ++kh) {
                             const uint32_t row = a_base + (uint32_t)((kd * p.bh + kh) * p.bw) * 16u;
 #pragma unroll
-                            for (int kx = 0; kx < (CIN8 ? 2 : 3); ++kx, ++m) {
-                                const uint64_t ad = CIN8 ? make_desc(row + kx * 32u, 16u, (uint32_t)p.bw * 16u)
-                                                         : make_desc(row + kx * 16u, PLANE_BYTES, (uint32_t)p.bw * 16u);
+                            for (int kx = 0; kx < 3; ++kx, ++m) {
+                                const uint64_t ad = make_desc(row + kx * 16u, PLANE_BYTES, (uint32_t)p.bw * 16u);
                                 const uint64_t bd = make_desc(b_base + m * (NC * 32), NC * 16, 128u);
                                 tc_mma_elect(dcol, ad, bd, idesc, (ks | m) != 0);
                             }
                         }
+                    }
                     }
                 }
                 tc_commit_elect(&empty_bar[stage]);             // this warp's reads of the smem stage have retired
@@ -271,6 +289,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
         const uint32_t smean_addr = smem_u32(smean), srstd_addr = smem_u32(srstd);
         const int ref_row = rh * TW + rw;
         const int ref_d0 = (rd / p.td) * p.td;                   // first plane of the work item that owns the reference voxel
+        float shr[NC == 16 ? 16 : 1];
+#pragma unroll
+        for (int k = 0; k < (NC == 16 ? 16 : 1); ++k) shr[k] = 0.f;
         for (long long item = blockIdx.x; item < p.work_items; item += gridDim.x) {
             int n, d0, h0, w0, chunk;
             decode_work(item, p, n, d0, h0, w0, chunk);
@@ -323,6 +344,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
                         sshift[et] = sv;
                     }
                     asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (NC == 16) {
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            const float4 sh = lds128(sshift_addr + k4 * 16);
+                            shr[NC == 16 ? k4 * 4 + 0 : 0] = sh.x; shr[NC == 16 ? k4 * 4 + 1 : 0] = sh.y;
+                            shr[NC == 16 ? k4 * 4 + 2 : 0] = sh.z; shr[NC == 16 ? k4 * 4 + 3 : 0] = sh.w;
+                        }
+                    }
                 }
             }
             const int jmax = min(p.td, p.d - d0);
@@ -346,19 +375,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
             }
             mbar_wait(&tfull_bar[buf], bphase);
             tc_fence_after();
+            // The epilogue is ONE warp per scheduler running a dependent chain: its latencies are not hidden by other
+            // warps, and at the full-resolution levels it -- not the MMAs -- sets the tile time.  NC = 16: the TMEM
+            // load of plane j+1 is in flight while plane j is processed, the shift lives in registers.
+            uint32_t rpipe[NC == 16 ? 2 : 1][16];
+            if (NC == 16) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (buf * TD) * NC, rpipe[0]);
 #pragma unroll
             for (int j = 0; j < TD; ++j) {
                 if (j >= jmax) break;
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (buf * TD + j) * NC;
+                if (NC == 16) {
+                    tmem_ld_wait();
+                    if (j + 1 < jmax) tmem_ld16(taddr + NC, rpipe[NC == 16 ? ((j + 1) & 1) : 0]);
+                }
                 const long long yoff = (((long long)n * p.d + d0 + j) * p.h + gh) * (long long)p.w * p.cout + (long long)gw * p.cout + co0;
                 bf16* py = p.y + yoff;
 #pragma unroll
                 for (int c16 = 0; c16 < NC / 16; ++c16) {
                     uint32_t r[16];
-                    tmem_ld16(taddr + c16 * 16, r);
-                    tmem_ld_wait();
+                    if (NC == 16) {
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) r[k] = rpipe[NC == 16 ? (j & 1) : 0][k];
+                    } else {
+                        tmem_ld16(taddr + c16 * 16, r);
+                        tmem_ld_wait();
+                    }
                     float v[16];
-                    if (has_shift) {
+                    if (has_shift && NC == 16) {
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(r[k]) - shr[k];
+                    } else if (has_shift) {
                         // explicit 128-bit shared loads (warp-broadcast, conflict-free); a generic LD through the
                         // reinterpret-cast pointer costs ~8 wavefronts each on the pipe the MMA operands share
 #pragma unroll
@@ -469,7 +515,7 @@ __device__ __forceinline__ float pack_tc_elem(const float* __restrict__ w, long 
     // GEMM-side channel counts
     const int gin = dgrad ? cout_l : cin_l, gout = dgrad ? cin_l : cout_l;
     const int kslices = cin8 ? 1 : gin / 16;
-    const int nmma = cin8 ? 18 : 27;
+    const int nmma = cin8 ? 14 : 27;
     long long r = i;
     const int ch8 = (int)(r % 8); r /= 8;
     const int r8 = (int)(r % 8); r /= 8;
@@ -481,9 +527,9 @@ __device__ __forceinline__ float pack_tc_elem(const float* __restrict__ w, long 
     const int go = chunk * nc + ng * 8 + r8;               // GEMM output channel
     int gi, tap;
     if (cin8) {
-        const int kdkh = m / 2, pr = m % 2, kw = pr * 2 + kc;
         gi = ch8;
-        tap = kw <= 2 ? kdkh * 3 + kw : -1;
+        tap = 2 * m + kc;                                      // taps paired in (kd,kh,kw) order; the 28th is zero
+        if (tap > 26) tap = -1;
     } else {
         gi = ks * 16 + kc * 8 + ch8;
         tap = m;
@@ -514,7 +560,7 @@ int nc_for(int gout) { return nc_for_dev(gout); }
 template <int NC, bool CIN8, int NSTAGE>
 int launch_tc(const CUtensorMap& map, const TcParams& p, cudaStream_t st) {
     constexpr int A_BYTES = CIN8 ? (PLANE_BYTES + PLANE_PAD) : 2 * PLANE_BYTES;
-    constexpr int B_BYTES = (CIN8 ? 18 : 27) * NC * 32;
+    constexpr int B_BYTES = (CIN8 ? 14 : 27) * NC * 32;
     constexpr int SMEM = NSTAGE * (A_BYTES + B_BYTES) + 128 /*align*/ + 8 * (2 * NSTAGE + 4) + 16 + NC * 4 + NC * 16 + 64;
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
     auto kern = conv3_tc_kernel<NC, CIN8, NSTAGE>;
@@ -538,7 +584,7 @@ extern "C" size_t vs_conv3_tc_pack_bytes(int cin, int cout, int dgrad) {
     const int nc = nc_for(gout);
     const int nchunks = (gout + nc - 1) / nc;
     const int kslices = gin == 8 ? 1 : gin / 16;
-    return (size_t)nchunks * kslices * (gin == 8 ? 18 : 27) * nc * 32;
+    return (size_t)nchunks * kslices * (gin == 8 ? 14 : 27) * nc * 32;
 }
 
 // Padded variants: the fp32 master weight is [cout][cin][27]; the pack is built for cout_pad >= cout output and
@@ -663,6 +709,7 @@ extern "C" int vs_conv3x3x3_tc(const void* x, const void* wtc, void* y, double* 
     p.ref_tile = (min(1, d - 1) / td) * tiles_h * tiles_w;        // voxel (1,1,1): h- and w-tile 0, d-tile 1/td
     p.kslices = gin == 8 ? 1 : gin / 16;
     p.work_items = (long long)n * p.tiles_per_n * p.nchunks;
+    VS_REQUIRE(p.work_items < 2147483647LL, VS_ERR_SHAPE, "conv3_tc: too many work items");
     p.wpack = (const bf16*)wtc; p.y = (bf16*)y; p.stats = stats; p.shift = shift;
     p.yprev = (const bf16*)yprev; p.pstats = pstats; p.psums = psums; p.inv_s = 1.0 / ((double)d * h * w);
     p.planar_mode = planar_mode; p.yplanar = yplanar; p.bias = bias;
