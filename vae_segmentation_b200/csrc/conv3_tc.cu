@@ -112,8 +112,13 @@ __device__ __forceinline__ void decode_work(long long item64, const TcParams& p,
 // NC: output channels per CTA (MMA N); CIN8: single 8-channel plane with paired taps.
 // Shared memory: NSTAGE x { A planes | B taps } + barriers; sized by the host.
 // ---------------------------------------------------------------------------------------------
-template <int NC, bool CIN8, int NSTAGE>
+// H8 (NC = 16 only): the layer has 8 output channels -- the epilogue touches accumulator columns 0..7 only (the MMA
+// still runs at N = 16, its minimum at M = 128; columns 8..15 hold the zero-padded weights' zeros).
+template <int NC, bool CIN8, int NSTAGE, bool H8 = false>
 __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_constant__ CUtensorMap xmap, TcParams p) {
+    static_assert(!H8 || NC == 16, "H8 is a variant of the 16-column kernel");
+    constexpr int NV = H8 ? 8 : 16;                           // accumulator columns the epilogue processes per 16-column group
+    constexpr int NH8 = H8 ? 1 : 2;
     constexpr int A_BYTES = CIN8 ? (PLANE_BYTES + PLANE_PAD) : 2 * PLANE_BYTES;
     constexpr int NMMA = CIN8 ? 14 : 27;                      // MMAs per d-plane per stage
     constexpr int B_BYTES = NMMA * NC * 32;                   // [mma][kc 2][NC/8][8 rows][16 B]
@@ -365,7 +370,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
 #pragma unroll
                 for (int j = 0; j < TD; ++j) {
 #pragma unroll
-                    for (int h8 = 0; h8 < 2; ++h8) {
+                    for (int h8 = 0; h8 < NH8; ++h8) {
                         ypre[NC == 16 ? j : 0][h8] = make_uint4(0u, 0u, 0u, 0u);
                         if (j < jmax && rc_ok && co0 + h8 * 8 < p.cout)
                             ypre[NC == 16 ? j : 0][h8] = __ldg(reinterpret_cast<const uint4*>(
@@ -378,37 +383,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
             // The epilogue is ONE warp per scheduler running a dependent chain: its latencies are not hidden by other
             // warps, and at the full-resolution levels it -- not the MMAs -- sets the tile time.  NC = 16: the TMEM
             // load of plane j+1 is in flight while plane j is processed, the shift lives in registers.
-            uint32_t rpipe[NC == 16 ? 2 : 1][16];
-            if (NC == 16) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (buf * TD) * NC, rpipe[0]);
+            uint32_t rpipe[NC == 16 ? 2 : 1][NV];
+            if constexpr (NC == 16) {
+                if constexpr (H8) tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (buf * TD) * NC, rpipe[0]);
+                else tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (buf * TD) * NC, rpipe[0]);
+            }
 #pragma unroll
             for (int j = 0; j < TD; ++j) {
                 if (j >= jmax) break;
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (buf * TD + j) * NC;
-                if (NC == 16) {
+                if constexpr (NC == 16) {
                     tmem_ld_wait();
-                    if (j + 1 < jmax) tmem_ld16(taddr + NC, rpipe[NC == 16 ? ((j + 1) & 1) : 0]);
+                    if (j + 1 < jmax) {
+                        if constexpr (H8) tmem_ld8(taddr + NC, rpipe[(j + 1) & 1]);
+                        else tmem_ld16(taddr + NC, rpipe[(j + 1) & 1]);
+                    }
                 }
                 const long long yoff = (((long long)n * p.d + d0 + j) * p.h + gh) * (long long)p.w * p.cout + (long long)gw * p.cout + co0;
                 bf16* py = p.y + yoff;
 #pragma unroll
                 for (int c16 = 0; c16 < NC / 16; ++c16) {
-                    uint32_t r[16];
-                    if (NC == 16) {
+                    uint32_t r[NV];
+                    if constexpr (NC == 16) {
 #pragma unroll
-                        for (int k = 0; k < 16; ++k) r[k] = rpipe[NC == 16 ? (j & 1) : 0][k];
+                        for (int k = 0; k < NV; ++k) r[k] = rpipe[j & 1][k];
                     } else {
                         tmem_ld16(taddr + c16 * 16, r);
                         tmem_ld_wait();
                     }
-                    float v[16];
+                    float v[NV];
                     if (has_shift && NC == 16) {
 #pragma unroll
-                        for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(r[k]) - shr[k];
+                        for (int k = 0; k < NV; ++k) v[k] = __uint_as_float(r[k]) - shr[k];
                     } else if (has_shift) {
                         // explicit 128-bit shared loads (warp-broadcast, conflict-free); a generic LD through the
                         // reinterpret-cast pointer costs ~8 wavefronts each on the pipe the MMA operands share
 #pragma unroll
-                        for (int k4 = 0; k4 < 4; ++k4) {
+                        for (int k4 = 0; k4 < NV / 4; ++k4) {
                             const float4 sh = lds128(sshift_addr + (c16 * 16 + k4 * 4) * 4);
                             v[k4 * 4 + 0] = __uint_as_float(r[k4 * 4 + 0]) - sh.x;
                             v[k4 * 4 + 1] = __uint_as_float(r[k4 * 4 + 1]) - sh.y;
@@ -417,11 +428,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
                         }
                     } else {
 #pragma unroll
-                        for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(r[k]);
+                        for (int k = 0; k < NV; ++k) v[k] = __uint_as_float(r[k]);
                     }
                     if (!rc_ok) {
 #pragma unroll
-                        for (int k = 0; k < 16; ++k) v[k] = 0.f;
+                        for (int k = 0; k < NV; ++k) v[k] = 0.f;
                     }
                     if (p.planar_mode != 0) {
                         if (rc_ok && c16 == 0 && co0 == 0) {
@@ -438,7 +449,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
                         }
                     } else if (rc_ok) {
 #pragma unroll
-                        for (int h8 = 0; h8 < 2; ++h8) {
+                        for (int h8 = 0; h8 < NH8; ++h8) {
                             if (co0 + c16 * 16 + h8 * 8 < p.cout) {
                                 float o[8];
 #pragma unroll
@@ -449,13 +460,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
                     }
                     if (has_stats) {
 #pragma unroll
-                        for (int k = 0; k < 16; ++k) { rs[c16][k] += v[k]; rq[c16][k] = fmaf(v[k], v[k], rq[c16][k]); }
+                        for (int k = 0; k < NV; ++k) { rs[c16][k] += v[k]; rq[c16][k] = fmaf(v[k], v[k], rq[c16][k]); }
                     }
                     if (fused) {
                         // g = this launch's output (as stored, i.e. rounded to bf16); mask / xhat from the previous
                         // layer's raw output at the same voxel -- exactly what inorm_relu_bwd_reduce_kernel computes
 #pragma unroll
-                        for (int h8 = 0; h8 < 2; ++h8) {
+                        for (int h8 = 0; h8 < NH8; ++h8) {
                             float yv[8];
                             if (NC == 16) {
                                 const uint4 raw = ypre[NC == 16 ? j : 0][h8];
@@ -557,13 +568,13 @@ __global__ void pack_tc_kernel(const float* __restrict__ w, bf16* __restrict__ o
 __host__ __device__ constexpr int nc_for_dev(int gout) { return gout >= 64 ? VS_NC_WIDE : (gout >= 32 ? 32 : 16); }
 int nc_for(int gout) { return nc_for_dev(gout); }
 
-template <int NC, bool CIN8, int NSTAGE>
+template <int NC, bool CIN8, int NSTAGE, bool H8 = false>
 int launch_tc(const CUtensorMap& map, const TcParams& p, cudaStream_t st) {
     constexpr int A_BYTES = CIN8 ? (PLANE_BYTES + PLANE_PAD) : 2 * PLANE_BYTES;
     constexpr int B_BYTES = (CIN8 ? 14 : 27) * NC * 32;
     constexpr int SMEM = NSTAGE * (A_BYTES + B_BYTES) + 128 /*align*/ + 8 * (2 * NSTAGE + 4) + 16 + NC * 4 + NC * 16 + 64;
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
-    auto kern = conv3_tc_kernel<NC, CIN8, NSTAGE>;
+    auto kern = conv3_tc_kernel<NC, CIN8, NSTAGE, H8>;
     static bool configured = false;
     if (!configured) {
         VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM), "conv3_tc smem attribute");
@@ -730,10 +741,12 @@ extern "C" int vs_conv3x3x3_tc(const void* x, const void* wtc, void* y, double* 
     }
 
     if (gin == 8) {
+        if (nc == 16 && gout == 8) return launch_tc<16, true, 4, true>(map, p, st);
         if (nc == 16) return launch_tc<16, true, 4>(map, p, st);
         if (nc == 32) return launch_tc<32, true, 4>(map, p, st);
         return launch_tc<64, true, 3>(map, p, st);
     }
+    if (nc == 16 && gout == 8) return launch_tc<16, false, 4, true>(map, p, st);
     if (nc == 16) return launch_tc<16, false, 4>(map, p, st);
     if (nc == 32) return launch_tc<32, false, 3>(map, p, st);
     return launch_tc<64, false, 2>(map, p, st);
