@@ -78,3 +78,48 @@ def test_single_process_is_identity():
     assert ts.allreduce_mean_(g) == 1.0 and torch.equal(g, torch.arange(6.0))
     t = torch.tensor([0.3, 1.0, 2.0])
     assert ts.sync_first_term_(t) is t
+
+
+class _FakeArena(object):
+    """What BucketedAllReduce needs of a FlatArena: params (offsets by order), numel, grad."""
+
+    def __init__(self, sizes, rank):
+        self.params = [torch.nn.Parameter(torch.zeros(n)) for n in sizes]
+        self.numel = sum(sizes)
+        self.grad = torch.arange(self.numel, dtype=torch.float64) * (rank + 1)
+
+
+def _bucket_worker(rank, world, port, outdir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sizes = [5, 3, 40, 8, 64, 16, 2]
+        arena = _FakeArena(sizes, rank)
+        b = ts.BucketedAllReduce(arena, nbuckets=3)
+        launched = []
+        for p in reversed(arena.params):                 # backward order: last parameter first
+            b.on_ready(p)
+            launched.append(len(b.works))
+        b.finish()
+        torch.save({"grad": arena.grad, "bounds": b.bounds, "launched": launched}, os.path.join(outdir, "b%d.pt" % rank))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_covers_every_element_once():
+    """train_step.BucketedAllReduce (gradient all-reduce overlapped with backward): buckets tile the arena, are
+    launched as soon as the ready region (growing down from the last parameter) covers them, and the result equals
+    one SUM all-reduce of the whole arena."""
+    world = 2
+    with tempfile.TemporaryDirectory() as outdir:
+        mp.spawn(_bucket_worker, args=(world, _free_port(), outdir), nprocs=world, join=True)
+        outs = [torch.load(os.path.join(outdir, "b%d.pt" % r)) for r in range(world)]
+    n = 138
+    want = torch.arange(n, dtype=torch.float64) * 3            # rank0 (x1) + rank1 (x2): every element reduced exactly once
+    assert torch.equal(outs[0]["grad"], want) and torch.equal(outs[1]["grad"], want)
+    bounds = outs[0]["bounds"]
+    assert bounds[0][0] == 0 and bounds[-1][1] == n and all(a[1] == b[0] for a, b in zip(bounds, bounds[1:]))
+    assert len(bounds) >= 2
+    # the last bucket went out before the first parameters were ready (overlap), everything by the end
+    assert outs[0]["launched"][0] <= outs[0]["launched"][-1] and outs[0]["launched"][-2] >= 1

@@ -213,6 +213,20 @@ def join_wgrad_stream():
     _wgrad_rr[0] = 0
 
 
+# Optional callable(param) invoked right after the kernels that produce a parameter's gradient have been ENQUEUED (on
+# the current stream or a weight-gradient side stream): the data-parallel trainers use it to start the all-reduce of a
+# gradient bucket while the rest of the backward pass is still running (train_step.BucketedAllReduce).
+GRAD_READY_HOOK = None
+
+
+def _grad_ready(*params):
+    hook = GRAD_READY_HOOK
+    if hook is not None:
+        for p in params:
+            if p is not None:
+                hook(p)
+
+
 def _tc_channels(c):
     return c == 8 or (c >= 16 and c % 16 == 0)
 
@@ -363,6 +377,7 @@ def program_backward(tape, g, dtype, need, grads, param_refs, need_input_grad):
                 # exactly zero: the bias cancels in InstanceNorm
                 tgt, acc = _grad_target(param_refs[L.bi], True)
                 grads[L.bi] = None if acc else torch.zeros(L.cout, device=dy.device, dtype=torch.float32)
+            _grad_ready(param_refs[L.wi], param_refs[L.bi])
             g = _sim(ops.conv3_dgrad(dy, wd[0], dims, L.cin, L.cout, dtype, out_planar=L.in_planar, wdtc=wd[1],
                                      prev=None if L.in_planar else fuse_prev(idx, dy, L.cin, L.cout, wd[1])), "g") \
                 if want_dx else None
@@ -373,6 +388,7 @@ def program_backward(tape, g, dtype, need, grads, param_refs, need_input_grad):
                 _wgrad_async(lambda: ops.k2s2_wgrad(g, x_in, dims, L.cout, L.cin, dwt=tw, dbias_coarse=tb, accumulate=acc),
                              acc, g, x_in)
                 _hand_back(grads, need, L.wi, L.bi, tw, tb, acc)
+            _grad_ready(param_refs[L.wi], param_refs[L.bi])
             g = _sim(ops.k2s2_scatter(g, wt, None, dims, L.cout, L.cin), "g") if want_dx else None
         elif L.kind == K2UP:
             # dims are the coarse (input) dims; g is the fine gradient
@@ -381,6 +397,7 @@ def program_backward(tape, g, dtype, need, grads, param_refs, need_input_grad):
                 _wgrad_async(lambda: ops.k2s2_wgrad(x_in, g, dims, L.cin, L.cout, dwt=tw, dbias_fine=tb, accumulate=acc),
                              acc, g, x_in)
                 _hand_back(grads, need, L.wi, L.bi, tw, tb, acc)
+            _grad_ready(param_refs[L.wi], param_refs[L.bi])
             g = _sim(ops.k2s2_gather(g, wt, None, dims, L.cin, L.cout), "g") if want_dx else None
         elif L.kind == HEAD:
             probs = y
@@ -403,6 +420,7 @@ def program_backward(tape, g, dtype, need, grads, param_refs, need_input_grad):
                     _wgrad_async(run_head_wgrad, acc, x_in, dl8)
                 if need[L.wi] or need[L.bi]:
                     _hand_back(grads, need, L.wi, L.bi, tw, tb, acc)
+                _grad_ready(param_refs[L.wi], param_refs[L.bi])
                 g = ops.conv3_dgrad(dl8, None, dims, L.cin, 8, dtype, wdtc=wd[1],
                                     prev=fuse_prev(idx, dl8, L.cin, 8, wd[1])) if want_dx else None
                 continue
@@ -411,6 +429,7 @@ def program_backward(tape, g, dtype, need, grads, param_refs, need_input_grad):
                 tw, tb, acc = _pair_targets(param_refs, need, L.wi, L.bi, (L.cout, L.cin, 3, 3, 3), (L.cout,), g.device)
                 ops.conv3_wgrad(x_in, dlogits, dims, L.cin, L.cout, dw=tw, db=tb, in_planar=L.in_planar, accumulate=acc)
                 _hand_back(grads, need, L.wi, L.bi, tw, tb, acc)
+            _grad_ready(param_refs[L.wi], param_refs[L.bi])
             g = _sim(ops.conv3_dgrad(dlogits, wd[0], dims, L.cin, L.cout, dtype, out_planar=L.in_planar, wdtc=wd[1]), "g") \
                 if want_dx else None
     return g
