@@ -421,7 +421,16 @@ def main():
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # The captured graph holds NCCL kernels (the all-reduce buckets overlapped with backward): release it, make sure
+        # every rank is done, and leave without the process-group teardown, which does not return after NCCL work has
+        # been captured into a CUDA graph on this stack (observed on B200 x2; the JSON line is already flushed).
+        if use_graph:
+            trainer.release_graph()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

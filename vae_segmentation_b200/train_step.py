@@ -245,10 +245,13 @@ class JointTrainer(object):
         # (VAESEG_SAMPLE_PARALLEL=1); parity-tested (tests/test_models_gpu.py runs the joint step both ways).
         self.sample_parallel = os.environ.get("VAESEG_SAMPLE_PARALLEL", "0") == "1"
         self._chain_streams = {}
-        # data parallel: the default is ONE all-reduce of the 9.1 MB gradient arena after backward (~1 % of the step on
-        # NVLink).  VAESEG_DDP_OVERLAP=1 selects the bucketed all-reduce overlapped with backward (BucketedAllReduce):
-        # its host logic is tested on gloo (tests/test_ddp_cpu.py), but its first 2-GPU NCCL trial did not complete
-        # within the GPU budget of this round, so it is NOT enabled by default and carries no measured number.
+        # data parallel.  Default: ONE all-reduce of the 9.1 MB gradient arena after backward.  VAESEG_DDP_OVERLAP=1 (or
+        # trainer.ddp_overlap = True before the first step) selects the bucketed all-reduce overlapped with backward
+        # (BucketedAllReduce; captured inside the CUDA graph of the step).  MEASURED on 2 x B200, 2 x 96^3 per GPU:
+        # 657.6 vol/s plain vs 648.7 vol/s overlapped -- the payload costs ~40 us on NVLink and the extra NCCL kernels
+        # interfere with the backward chain more than the overlap hides, so the plain path stays the default.
+        # NOTE for callers: destroy the captured graph (trainer.release_graph()) before tearing the process group down --
+        # destroy_process_group() does not return while a live CUDA graph still holds NCCL kernels (observed, B200 x2).
         self.ddp_buckets = int(os.environ.get("VAESEG_DDP_BUCKETS", "3"))
         self.ddp_overlap = os.environ.get("VAESEG_DDP_OVERLAP", "0") == "1"
         self._bucketer = None
@@ -429,6 +432,12 @@ class JointTrainer(object):
             mon = self.forward_backward(img_static, label_static)
         self._graph_mon = mon
         return self
+
+    def release_graph(self):
+        """Drops the captured graph (and the NCCL kernels it holds)."""
+        self._graph = None
+        self._graph_mon = None
+        torch.cuda.synchronize()
 
     def step_graphed(self, update_teacher=False):
         if update_teacher:
