@@ -79,8 +79,11 @@ def run_reference_arm(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "joint teacher-student step, 96^3, lambda_vae=1, loss type 0 (BASELINE.json config[2])",
-                       "patch": PATCH, "per_step_batch": batch},
+            "config": {"workload": "joint teacher-student step (student Seg+frozen VAE fwd, teacher Joint fwd, recon + "
+                                   "pseudo Dice, bwd through VAE into Seg, SGD m=.9), BASELINE.json config[2]",
+                       "patch": PATCH, "per_gpu_batch": PER_GPU_BATCH, "global_batch": PER_GPU_BATCH * max(args.gpus, 1),
+                       "lambda_vae": 1.0, "loss_type": 0, "parallelism": "host cores (torch CPU)",
+                       "sample_batch_per_step": batch},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}

@@ -360,3 +360,32 @@ def test_test_time_training_and_ema():
     before = tr.teacher_arena.data.clone()
     tr.ema_teacher()
     assert torch.allclose(tr.teacher_arena.data, 0.995 * before + 0.005 * tr.arena.data, atol=1e-6)
+
+
+def test_checkpoint_resume_through_fused_optimizer(tmp_path):
+    """Reference-format checkpoint written from a trainer (fused SGD momentum arena -> torch.optim state) and resumed
+    in a fresh trainer: the next step matches the uninterrupted run (main_target.py:1049-1062, :358-394)."""
+    from vae_segmentation_b200 import checkpoint as ck
+    from vae_segmentation_b200.synthetic import synth_image, synth_label
+    torch.manual_seed(11)
+    img, label = synth_image(1, 32).to(DEV), synth_label(1, 32).to(DEV)
+    seg = jm.Segmentation(1, 2, norm_type=1).to(DEV).set_precision("fp32")
+    tr = ts.SegTrainer(seg)
+    for _ in range(2):
+        tr.step(img, label)
+    path = str(tmp_path / "model_epoch2.ckpt")
+    ck.save_checkpoint(path, seg, epoch=2, trainer=tr)
+    saved = torch.load(path)
+    assert set(saved) == {"epoch", "model_state_dict", "optimizer_state_dict"}
+    # torch.optim itself accepts the translated optimiser state
+    ref_opt = torch.optim.SGD(seg.parameters(), lr=1e-2, momentum=0.9)
+    ref_opt.load_state_dict(saved["optimizer_state_dict"])
+    seg2 = jm.Segmentation(1, 2, norm_type=1).to(DEV).set_precision("fp32")
+    tr2 = ts.SegTrainer(seg2)
+    assert ck.load_checkpoint(path, seg2, trainer=tr2) == 2
+    assert torch.equal(tr2.arena.data, tr.arena.data) and torch.equal(tr2.opt.buf, tr.opt.buf)
+    tr.step(img, label)
+    tr2.step(img, label)
+    torch.cuda.synchronize()
+    rel = ((tr2.arena.data - tr.arena.data).norm() / tr.arena.data.norm()).item()
+    assert rel < 1e-4, rel            # same weights + same momentum; only the atomics' summation order differs

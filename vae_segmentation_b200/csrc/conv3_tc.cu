@@ -12,7 +12,8 @@
 // tile are the 16 row groups (SBO = one halo row = 160 B) and the two planes are the two K chunks
 // (LBO = plane stride).  A filter tap (kd,kh,kw) is then nothing but a different start address in the
 // same halo: every input voxel is fetched from L2/HBM once per CTA and reused by all 27 taps x 4 planes.
-// For Cin = 8 two taps (kw, kw+1) are paired into one K=16 MMA by setting LBO = 16 B (the next voxel).
+// For Cin = 8 two taps are paired into one K=16 MMA: the second K chunk is the first one displaced by LBO (any
+// constant number of halo voxels), so the 27 taps in (kd,kh,kw) order pair up as (0,1),(2,3),...,(26,zero): 14 MMAs.
 //
 // Pipeline: warp 0 = TMA producer, warps 1-4 = MMA issuers (one per d-plane of the tile; warp 1 also owns the
 // TMEM allocation), warps 5-8 = epilogue (tcgen05.ld -> shift -> InstanceNorm statistics -> bf16 -> global).
@@ -515,7 +516,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
 // ---------------------------------------------------------------------------------------------
 // weight packing: fp32 master [Cout][Cin][27] -> bf16 UMMA B operand blocks
 //   general: [chunk][kslice][tap 27][kc 2][NC/8][8 rows][8 ch]
-//   cin8   : [chunk][1][kdkh 9 x pair 2][kc 2][NC/8][8 rows][8 ch]  (kc0 = tap kw=2*pair, kc1 = kw=2*pair+1 or 0)
+//   cin8   : [chunk][1][pair 14][kc 2][NC/8][8 rows][8 ch]  (kc0 = tap 2*pair, kc1 = tap 2*pair+1 in (kd,kh,kw) order; the 28th is zero)
 // dgrad = same contraction with (ci,co) swapped and taps flipped.
 // ---------------------------------------------------------------------------------------------
 // One element of the bf16 UMMA B-operand pack.  cout_real < cout_l zero-pads the output channels (the head's
