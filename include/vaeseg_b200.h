@@ -194,6 +194,11 @@ int vs_kl_bwd(const float* mean, const float* std, const float* gout, float* gme
               int batch, int dim, void* stream);
 /* elementwise thresholding: mode BINARIZE or CONFIDENT                                     */
 int vs_binarize(const float* a, float* out, int mode, long long count, void* stream);
+/* Input intensity normalisation on the device: out = (clip(x, lo, hi) - sub) / div, IEEE fp32 --
+ * the reference's Clip + CenterIntensities transforms (utils/utils.py:508-533,572-618; main_target.py:223-224).
+ * in_kind 0: x fp32; 2: x int16 (raw Hounsfield units).  out: fp32, same element count (the in-blocks' planar input). */
+int vs_clip_center(int in_kind, const void* x, float* out, long long count, float lo, float hi, float sub, float div,
+                   void* stream);
 /* label[N][1][S] (fp32 class index) -> planar one-hot [N][C][S] (main_target.py:520-522)   */
 int vs_one_hot(const float* label, float* out, int n, int c, long long s, void* stream);
 

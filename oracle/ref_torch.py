@@ -357,3 +357,15 @@ def joint_target_step(student_seg_sd, vae_sd, teacher_seg_sd, img, label, lambda
                dsc_loss_fake=dsc_loss_fake.detach(), klloss=klloss.detach(),
                pred=pred.detach(), recon=recon.detach(), pseudo=pseudo)
     return out, grads
+
+
+def clip_center(x, new_min=-200.0, new_max=400.0, subtrahend=100.0, divisor=300.0):
+    """numpy restatement of the reference's Clip -> CenterIntensities dataset transforms on a float32 volume
+    (utils/utils.py:508-533: np.clip(val, new_min, new_max); :572-618: val -= subtrahend; val /= divisor, in place on the
+    float32 array the loader produced with .astype(np.float32)).  Test infrastructure only."""
+    import numpy as np
+    val = np.asarray(x).astype(np.float32)
+    val = np.clip(val, new_min, new_max)
+    val -= subtrahend
+    val /= divisor
+    return val

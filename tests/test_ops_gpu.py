@@ -5,6 +5,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
+from oracle import ref_torch as R
 from vae_segmentation_b200 import _cabi, ops
 
 pytestmark = pytest.mark.gpu
@@ -370,3 +371,20 @@ def test_joint_target_loss_fused_vs_composed(cfg):
         assert ra is None or ra.abs().max().item() == 0.0
     else:
         assert torch.allclose(ra, rb, rtol=1e-4, atol=1e-9)
+
+
+@pytest.mark.parametrize("kind", ["float32", "int16"])
+def test_clip_center_bit_exact(kind):
+    """Fused Clip + CenterIntensities (utils/utils.py:508-533,572-618 as used at main_target.py:223-224) against the
+    numpy restatement: IEEE fp32 clip / subtract / divide, so the comparison is bit-exact."""
+    from vae_segmentation_b200 import transforms
+    torch.manual_seed(8)
+    if kind == "int16":
+        x = torch.randint(-1024, 3000, (2, 1, 9, 10, 11), dtype=torch.int16)
+    else:
+        x = (torch.randn(2, 1, 9, 10, 11) * 400 + 50)
+    want = torch.from_numpy(R.clip_center(x.numpy()))
+    out = transforms.ClipCenter(["venous"])({"venous": x.to(DEV), "other": None})["venous"]
+    assert out.dtype == torch.float32 and out.shape == x.shape
+    assert torch.equal(out.cpu(), want)
+    assert want.min().item() >= -1.0 and want.max().item() <= 1.0

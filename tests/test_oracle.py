@@ -142,3 +142,17 @@ def test_oracle_equals_real_reference_vae_and_losses():
     sd64 = R.init_vae_state(2, 128, 64)
     out, _, _ = R.vae_forward(sd64, R.one_hot((torch.rand(1, 1, 64, 64, 64) > 0.9).float()))
     assert out.shape == (1, 2, 64, 64, 64)
+
+
+def test_clip_center_oracle_matches_reference_statements():
+    """oracle clip_center == the reference's two transforms written out (utils/utils.py:508-533,572-618)."""
+    import numpy as np
+    from oracle import ref_torch as R
+    rng = np.random.RandomState(0)
+    x = (rng.randn(3, 4, 5) * 500).astype(np.float32)
+    val = np.clip(x.copy(), -200, 400)            # Clip.__call__
+    val = val.reshape((val.shape[0], -1))         # CenterIntensities.__call__
+    val -= 100
+    val /= 300
+    assert np.array_equal(R.clip_center(x), val.reshape(x.shape))
+    assert R.clip_center(np.array([-5000, 100, 5000], dtype=np.int16)).tolist() == [-1.0, 0.0, 1.0]

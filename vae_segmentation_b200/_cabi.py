@@ -52,6 +52,7 @@ _SIGNATURES = {
     "vs_kl_bwd": [_P, _P, _P, _P, _P, _I, _I, _P],
     "vs_binarize": [_P, _P, _I, _L, _P],
     "vs_one_hot": [_P, _P, _I, _I, _L, _P],
+    "vs_clip_center": [_I, _P, _P, _L, _F, _F, _F, _F, _P],
     "vs_sgd_step": [_P, _P, _P, _L, _F, _F, _I, _F, _P],
     "vs_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _P],
     "vs_ema_update": [_P, _P, _L, _F, _P],

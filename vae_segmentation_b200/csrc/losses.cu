@@ -133,6 +133,19 @@ __global__ void __launch_bounds__(NT) binarize_kernel(const float* __restrict__ 
         out[i] = target_transform(a[i], mode);
 }
 
+// Intensity normalisation of the input volumes on the device: out = (clip(x, lo, hi) - sub) / div in IEEE fp32 -- the
+// reference's Clip + CenterIntensities dataset transforms (utils/utils.py:508-533,572-618; main_target.py:223-224 uses
+// Clip(-200, 400), CenterIntensities(100, 300)).  TI = float, or int16 raw Hounsfield units (half the H2D bytes).
+template <typename TI>
+__global__ void __launch_bounds__(NT) clip_center_kernel(const TI* __restrict__ x, float* __restrict__ out, long long count,
+                                                         float lo, float hi, float sub, float div) {
+    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < count; i += (long long)gridDim.x * NT) {
+        float v = (float)x[i];
+        v = fminf(fmaxf(v, lo), hi);
+        out[i] = __fdiv_rn(__fsub_rn(v, sub), div);
+    }
+}
+
 __global__ void __launch_bounds__(NT) one_hot_kernel(const float* __restrict__ label, float* __restrict__ out, int c,
                                                      long long s) {
     const int n = blockIdx.y;
@@ -256,6 +269,17 @@ extern "C" int vs_binarize(const float* a, float* out, int mode, long long count
     VS_REQUIRE(mode == VS_TGT_BINARIZE || mode == VS_TGT_CONFIDENT, VS_ERR_UNSUPPORTED, "binarize: unknown mode %d", mode);
     binarize_kernel<<<(unsigned)max(1LL, min((count + NT - 1) / NT, (long long)vs_sm_count() * 8)), NT, 0, (cudaStream_t)stream>>>(a, out, mode, count);
     VS_CHECK_LAUNCH("binarize_kernel");
+    return VS_OK;
+}
+
+extern "C" int vs_clip_center(int in_kind, const void* x, float* out, long long count, float lo, float hi, float sub,
+                              float div, void* stream) {
+    VS_REQUIRE(x && out && count > 0 && hi >= lo && div != 0.f, VS_ERR_SHAPE, "clip_center: bad arguments");
+    VS_REQUIRE(in_kind == 0 || in_kind == 2, VS_ERR_UNSUPPORTED, "clip_center: input kind %d (0 = fp32, 2 = int16)", in_kind);
+    const unsigned grid = (unsigned)max(1LL, min((count + NT - 1) / NT, (long long)vs_sm_count() * 8));
+    if (in_kind == 0) clip_center_kernel<float><<<grid, NT, 0, (cudaStream_t)stream>>>((const float*)x, out, count, lo, hi, sub, div);
+    else clip_center_kernel<short><<<grid, NT, 0, (cudaStream_t)stream>>>((const short*)x, out, count, lo, hi, sub, div);
+    VS_CHECK_LAUNCH("clip_center_kernel");
     return VS_OK;
 }
 

@@ -28,6 +28,7 @@ C3IN, K2DOWN, K2UP, HEAD = "c3in", "k2down", "k2up", "head"
 USE_TENSOR_CORES = os.environ.get("VAESEG_NO_TC", "0") != "1"
 # VAESEG_NO_FUSE_REDUCE=1 keeps the InstanceNorm-backward reduction a separate pass (A/B measurements, parity tests)
 FUSE_BWD_REDUCE = os.environ.get("VAESEG_NO_FUSE_REDUCE", "0") != "1"
+HEAD_DIRECT = os.environ.get("VAESEG_HEAD_DIRECT", "0") == "1"
 
 # tools/precision_probe*.py only: names of tensor classes to round through bf16 while running the fp32
 # check mode ("y", "a", "g", "dy", "k2"), to attribute bf16-mode error to a storage point.  Empty in production.
@@ -302,6 +303,8 @@ def program_forward(layers, tensors, x, dims, dtype, cache, record=True):
             wtc8 = wdtc = None
             if dtype == torch.bfloat16 and L.cout == 2 and _tc_channels(L.cin) and not L.in_planar:
                 wtc8, wdtc = cache.head_tc(tensors[L.wi])
+                if HEAD_DIRECT:          # A/B switch: fp32-weight CUDA-core head forward (backward stays on the tensor cores)
+                    wtc8 = None
             if wtc8 is not None:
                 # conv + bias + softmax + planar store in ONE tensor-core launch
                 wd = None

@@ -399,3 +399,13 @@ def joint_target_finish(sums_r, sums_g, sums_f, kl, bot, top, eps, lambda_vae, l
 def atomic_add_rows(dst, src, rows, row_len, src_row_stride):
     """dst[r, :row_len] += src[r*src_row_stride : +row_len] with atomics (dst contiguous fp32; src a base pointer)."""
     _cabi.call("vs_atomic_add_rows", _p(_f32(dst, "dst")), src.data_ptr(), int(rows), int(row_len), int(src_row_stride), _stream())
+
+
+def clip_center(x, lo, hi, sub, div):
+    """(clip(x, lo, hi) - sub) / div as fp32; x: CUDA fp32 or int16 tensor (any shape, contiguous)."""
+    kind = {torch.float32: 0, torch.int16: 2}.get(x.dtype)
+    if kind is None:
+        raise RuntimeError("vaeseg_b200: clip_center takes float32 or int16 volumes, got %s" % x.dtype)
+    out = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+    _cabi.call("vs_clip_center", kind, _p(x), _p(out), x.numel(), float(lo), float(hi), float(sub), float(div), _stream())
+    return out

@@ -324,8 +324,7 @@ class JointTrainer(object):
         return final, mon, batch
 
     def _use_chains(self, img):
-        return (self.sample_parallel and self.overlap and self.fused_loss and self.loss_type != 8 and img.shape[0] > 1
-                and self.student is not None)
+        return self.sample_parallel and self.overlap and self.fused_loss and self.loss_type != 8 and img.shape[0] > 1
 
     def _chains(self, b):
         st = self._chain_streams.get(b)
