@@ -248,8 +248,8 @@ class JointTrainer(object):
         # data parallel.  Default: ONE all-reduce of the 9.1 MB gradient arena after backward.  VAESEG_DDP_OVERLAP=1 (or
         # trainer.ddp_overlap = True before the first step) selects the bucketed all-reduce overlapped with backward
         # (BucketedAllReduce; captured inside the CUDA graph of the step).  MEASURED on 2 x B200, 2 x 96^3 per GPU:
-        # 657.6 vol/s plain vs 648.7 vol/s overlapped -- the payload costs ~40 us on NVLink and the extra NCCL kernels
-        # interfere with the backward chain more than the overlap hides, so the plain path stays the default.
+        # 657.6 / 648.6 vol/s plain (two runs) vs 648.7 vol/s overlapped -- inside the run-to-run noise: the payload
+        # costs ~40 us on NVLink (< 1 % of the step), so the simpler plain path stays the default.
         # NOTE for callers: destroy the captured graph (trainer.release_graph()) before tearing the process group down --
         # destroy_process_group() does not return while a live CUDA graph still holds NCCL kernels (observed, B200 x2).
         self.ddp_buckets = int(os.environ.get("VAESEG_DDP_BUCKETS", "3"))
