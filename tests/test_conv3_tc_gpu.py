@@ -165,3 +165,45 @@ def test_tc_inblock2_planar_dgrad(case):
     torch.cuda.synchronize()
     assert dx.shape == ref.shape and dx.dtype == torch.float32
     assert (dx.cpu() - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
+
+
+KDN_CASES = [(1, 4, 16, 8, 8, 8), (2, 5, 17, 9, 8, 8), (1, 8, 18, 10, 16, 8), (1, 7, 20, 19, 8, 16), (2, 6, 9, 11, 16, 16),
+             (1, 12, 24, 24, 32, 16)]
+
+
+@pytest.mark.skipif(__import__("os").environ.get("VAESEG_TEST_KDN", "0") != "1",
+                    reason="experimental kd-in-N kernel (DESIGN.md section 10): opt-in until its first GPU run, VAESEG_TEST_KDN=1")
+@pytest.mark.parametrize("case", KDN_CASES)
+def test_tc_kdn_fprop_and_dgrad(case):
+    """Experimental kd-in-N convolution against torch (same bf16 operands) and against the production kernel."""
+    n, d, h, w, cin, cout = case
+    torch.manual_seed(sum(case) + 7)
+    x = torch.randn(n, cin, d, h, w).bfloat16().float()
+    wt = torch.randn(cout, cin, 3, 3, 3) * 0.1
+    wq = wt.bfloat16().float()
+    y_ref = F.conv3d(x, wq, None, padding=1)
+    wd = wt.to(DEV)
+    dims = (n, d, h, w)
+    wk = ops.pack_conv3_weight_tc_kdn(wd, dgrad=False)
+    assert wk is not None
+    y, stats = ops.conv3_tc_kdn(to_ndhwc(x), wk, dims, cin, cout, want_stats=True)
+    torch.cuda.synchronize()
+    scale = y_ref.abs().max().item()
+    ys_ref = y_ref - F.conv3d(x, wt, None, padding=1)[:, :, 1:2, 1:2, 1:2]          # shifted output
+    assert (from_ndhwc(y) - ys_ref).abs().max().item() < 1.5e-2 * scale
+    s_ref = torch.stack([ys_ref.double().sum((2, 3, 4)), (ys_ref.double() ** 2).sum((2, 3, 4))], -1)
+    assert torch.allclose(stats.cpu(), s_ref, rtol=5e-3, atol=5e-3 * s_ref.abs().max().item())
+    # plain (no shift / statistics) == the production kernel on the same operands
+    y2, _ = ops.conv3_tc_kdn(to_ndhwc(x), wk, dims, cin, cout, want_stats=False)
+    wf, _ = ops.pack_conv3_weight(wd)
+    y3, _ = ops.conv3_fprop(to_ndhwc(x), wf, None, dims, cin, cout, torch.bfloat16, shifted=False, want_stats=False,
+                            wtc=ops.pack_conv3_weight_tc(wd, dgrad=False))
+    assert (y2.float() - y3.float()).abs().max().item() < 1e-2 * scale
+    # dgrad through the same kernel (GEMM input = Cout of the layer must be 8 or 16k, output = Cin in {8,16})
+    wkd = ops.pack_conv3_weight_tc_kdn(wd, dgrad=True)
+    if wkd is not None:
+        gy = torch.randn_like(y_ref).bfloat16().float()
+        dx_ref = F.conv_transpose3d(gy, wq, None, padding=1)
+        dx, _ = ops.conv3_tc_kdn(to_ndhwc(gy), wkd, dims, cout, cin, want_stats=False)
+        torch.cuda.synchronize()
+        assert (from_ndhwc(dx) - dx_ref).abs().max().item() < 1e-2 * dx_ref.abs().max().item()

@@ -27,6 +27,9 @@ _SIGNATURES = {
     "vs_pack_conv3_batched": [_P, _I, _P],
     "vs_pack_conv3_weight_tc_padded": [_P, _P, _I, _I, _I, _I, _I, _P],
     "vs_head_conv_softmax2_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "vs_conv3_tc_kdn_pack_bytes": [_I, _I, _I],
+    "vs_pack_conv3_weight_tc_kdn": [_P, _P, _I, _I, _I, _P],
+    "vs_conv3x3x3_tc_kdn": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "vs_conv3x3x3_fprop": [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "vs_conv3x3x3_dgrad": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "vs_conv3_wgrad_workspace_bytes": [_I, _I, _I, _I, _I, _I],
@@ -61,7 +64,7 @@ _SIGNATURES = {
     "vs_joint_target_finish": [_P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _I, _I, _I, _P, _P, _P],
 }
 _RESTYPES = {"vs_last_error_string": c_char_p, "vs_conv3_wgrad_workspace_bytes": c_size_t,
-             "vs_conv3_tc_pack_bytes": c_size_t}
+             "vs_conv3_tc_pack_bytes": c_size_t, "vs_conv3_tc_kdn_pack_bytes": c_size_t}
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

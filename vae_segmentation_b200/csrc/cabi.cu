@@ -110,6 +110,13 @@ extern "C" int vs_head_conv_softmax2_fwd(const void* x, const void* wtc8, const 
 }
 
 #ifndef VS_WITH_TCGEN05
+extern "C" size_t vs_conv3_tc_kdn_pack_bytes(int, int, int) { return 0; }
+extern "C" int vs_pack_conv3_weight_tc_kdn(const float*, void*, int, int, int, void*) {
+    VS_FAIL(VS_ERR_UNSUPPORTED, "library built without the tcgen05 kernels");
+}
+extern "C" int vs_conv3x3x3_tc_kdn(const void*, const void*, void*, double*, float*, int, int, int, int, int, int, int, void*) {
+    VS_FAIL(VS_ERR_UNSUPPORTED, "library built without the tcgen05 kernels");
+}
 extern "C" int vs_pack_conv3_weight_tc_padded(const float*, void*, int, int, int, int, int, void*) {
     VS_FAIL(VS_ERR_UNSUPPORTED, "library built without the tcgen05 kernels");
 }

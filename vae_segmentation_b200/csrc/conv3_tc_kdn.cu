@@ -1,0 +1,466 @@
+// EXPERIMENTAL (round-2 groundwork, NOT on the default path, first GPU run pending -- see DESIGN.md section 10):
+// "kd-in-N" variant of the tcgen05 3x3x3 convolution for the full-resolution layers (Cout = 8 or 16).
+//
+// conv3_tc.cu issues, for each of the 4 output planes of a tile, all 27 taps: every input voxel's A operand is fetched
+// 27 x from shared memory, which is what bounds those layers once the epilogue is out of the way (operand pipe 58 %).
+// Here the MMAs are issued per INPUT plane q of the halo (6 of them) and in-plane tap (kh,kw):
+//
+//     D[128 voxels, (kd', co)] += A[plane q, shifted by (kh,kw)] * B'[(kd', co), ci]        N = 4 * Cout
+//
+// B' holds the three kd taps of (kh,kw) side by side (block 3 = zeros, N must be a multiple of 16).  Block kd' belongs
+// to OUTPUT plane p = q - kd', so with the accumulator of plane p at TMEM columns (5 - p) * Cout the three blocks of
+// one MMA land in consecutive "slots"; 9 slots (p = -3 .. 5; only p = 0..3 are real, the others collect partial sums
+// of planes outside the tile and are never read) form one buffer, two buffers double-buffer the tile.
+//   * every MMA accumulates (one MMA touches fresh and running slots at once): the epilogue zeroes a buffer with
+//     tcgen05.st after reading it, and zeroes both buffers before the first tile;
+//   * the four issuer warps share the accumulators and simply split the (plane, tap) list round-robin;
+//   * Cin = 8 pairs two in-plane taps per K = 16 MMA (second K chunk = first one displaced by LBO): 5 MMAs per plane.
+// Hardware facts this relies on were probed first (tools/kdn_probe.cu, profiles/r1_kdn_probe.txt): D may start at
+// any column that is a multiple of 8 (N = 32), accumulating MMAs issued by different warps into the same columns add
+// up exactly, tcgen05.st zeroes an accumulator.
+// Per tile and 16-channel slice: 30 (Cin = 8) / 54 MMAs instead of 56 / 108, A-operand traffic halved.
+//
+// v1 feature set: bf16 NDHWC output, optional shift + fp64 InstanceNorm statistics (fprop) or plain (dgrad); tiles of
+// 4 d-planes only (volumes with D >= 4); no fused norm-backward reduction, no planar (head) epilogue.
+#include "tc_ptx.cuh"
+
+namespace {
+
+constexpr int TD = 4, TH = 16, TW = 8;
+constexpr int HD = TD + 2, HH = TH + 2, HW = TW + 2;
+constexpr int HV = HD * HH * HW;
+constexpr int PLANE_BYTES = HV * 16;
+constexpr int PLANE_PAD = 256;
+constexpr int NTHREADS = 288;                          // 1 producer + 4 MMA + 4 epilogue warps
+constexpr int NSLOT = 9;
+
+struct KdnParams {
+    int n, d, h, w, cin, cout;
+    int tiles_d, tiles_h, tiles_w, tiles_per_n;
+    int bw, bh, bd;
+    int ref_tile;
+    int kslices;
+    int work_items;
+    const bf16* wpack;
+    bf16* y;
+    double* stats;
+    float* shift;
+};
+
+__device__ __forceinline__ float transpose_reduce16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], 16);
+#pragma unroll
+    for (int h = 8; h >= 1; h >>= 1) {
+        const bool up = (lane & h) != 0;
+#pragma unroll
+        for (int k = 0; k < h; ++k) {
+            const float send = up ? v[k] : v[k + h];
+            const float keep = up ? v[k + h] : v[k];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+        }
+    }
+    return v[0];
+}
+
+__device__ __forceinline__ void tmem_st8_zero(uint32_t taddr) {
+    const uint32_t z = 0u;
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(z) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// work item -> (sample, tile origin); the tiles holding the shift's reference voxel come first (see conv3_tc.cu)
+__device__ __forceinline__ void decode_item(unsigned item, const KdnParams& p, int& n, int& d0, int& h0, int& w0) {
+    int r;
+    if (item < (unsigned)p.n) {
+        n = (int)item;
+        r = p.ref_tile;
+    } else {
+        const unsigned t = item - (unsigned)p.n;
+        n = (int)(t / (unsigned)(p.tiles_per_n - 1));
+        r = (int)(t % (unsigned)(p.tiles_per_n - 1));
+        r += (r >= p.ref_tile);
+    }
+    w0 = (r % p.tiles_w) * TW; r /= p.tiles_w;
+    h0 = (r % p.tiles_h) * TH; r /= p.tiles_h;
+    d0 = r * TD;
+}
+
+template <bool CIN8, int NCO, int NSTAGE>
+__global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kdn_kernel(const __grid_constant__ CUtensorMap xmap, KdnParams p) {
+    constexpr int N = 4 * NCO;                                // kd' blocks 0..2 + one zero block
+    constexpr int NMP = CIN8 ? 5 : 9;                         // MMAs per input plane per 16-channel slice
+    constexpr int A_BYTES = CIN8 ? (PLANE_BYTES + PLANE_PAD) : 2 * PLANE_BYTES;
+    constexpr int B_BYTES = NMP * N * 32;                     // [mma][kc 2][N/8][8 rows][16 B]
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr int NBUF = 2;
+    constexpr int BUFC = NSLOT * NCO;                         // accumulator columns per buffer (72 / 144)
+    constexpr int TMEM_COLS = NCO == 8 ? 256 : 512;
+    static_assert(STAGE_BYTES % 128 == 0, "stage alignment");
+    static_assert(NBUF * BUFC <= TMEM_COLS, "TMEM budget");
+
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + NSTAGE;
+    uint64_t* tfull_bar = empty_bar + NSTAGE;
+    uint64_t* tempty_bar = tfull_bar + NBUF;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + NBUF);
+    float* sshift = reinterpret_cast<float*>(tmem_slot + 4);          // [16]
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 4); }
+        for (int b = 0; b < NBUF; ++b) { mbar_init(&tfull_bar[b], 4); mbar_init(&tempty_bar[b], 4); }
+        fence_barrier_init();
+    }
+    if (CIN8) {
+        // the zero-weighted last tap of the pairs reads one voxel past the staged box (see conv3_tc.cu)
+        const bool clipped = p.bw < HW || p.bh < HH || p.bd < HD;
+        const int words = clipped ? A_BYTES / 4 : PLANE_PAD / 4, off = clipped ? 0 : PLANE_BYTES;
+        for (int i = threadIdx.x; i < NSTAGE * words; i += NTHREADS) {
+            int s = i / words, k = i % words;
+            reinterpret_cast<uint32_t*>(smem + s * STAGE_BYTES + off)[k] = 0u;
+        }
+        fence_proxy_async();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int item = blockIdx.x; item < p.work_items; item += gridDim.x) {
+                int n, d0, h0, w0;
+                decode_item((unsigned)item, p, n, d0, h0, w0);
+                for (int ks = 0; ks < p.kslices; ++ks) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[stage], (uint32_t)((CIN8 ? 1 : 2) * p.bd * p.bh * p.bw * 16 + B_BYTES));
+                    if (CIN8) tma_load_4d(sa, &xmap, &full_bar[stage], (w0 - 1) * 8, h0 - 1, d0 - 1, n);
+                    else tma_load_5d(sa, &xmap, &full_bar[stage], ks * 16, w0 - 1, h0 - 1, d0 - 1, n);
+                    if (!CIN8) tma_load_5d(sa + PLANE_BYTES, &xmap, &full_bar[stage], ks * 16 + 8, w0 - 1, h0 - 1, d0 - 1, n);
+                    bulk_load(sa + A_BYTES, reinterpret_cast<const uint8_t*>(p.wpack) + (long long)ks * B_BYTES, B_BYTES, &full_bar[stage]);
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp <= 4) {
+        // ===================== MMA issuers: the (input plane, tap) list split round-robin over the 4 warps ==========
+        const int j = warp - 1;
+        constexpr uint32_t idesc = make_idesc(N);
+        uint32_t stage = 0, phase = 0, buf = 0, bphase = 0;
+        for (int item = blockIdx.x; item < p.work_items; item += gridDim.x) {
+            mbar_wait(&tempty_bar[buf], bphase);                 // zeroed and released by the epilogue (also initially)
+            tc_fence_after();
+            const uint32_t dbuf = tmem_base + buf * BUFC;
+            for (int ks = 0; ks < p.kslices; ++ks) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t a0 = smem_u32(smem + stage * STAGE_BYTES);
+                const uint32_t b_base = a0 + A_BYTES;
+#pragma unroll 1
+                for (int i = j; i < HD * NMP; i += 4) {
+                    const int q = i / NMP, m = i - q * NMP;
+                    if (q >= p.bd) continue;                    // plane not staged (never with D >= 4)
+                    const uint32_t a_plane = a0 + (uint32_t)(q * p.bh * p.bw) * 16u;
+                    uint64_t ad;
+                    if (CIN8) {
+                        const int t1 = 2 * m, t2 = (2 * m + 1 < 9) ? 2 * m + 1 : 8;
+                        const int o1 = (t1 / 3) * p.bw + t1 % 3, o2 = (t2 / 3) * p.bw + t2 % 3;
+                        const uint32_t lbo = (2 * m + 1 < 9) ? (uint32_t)(o2 - o1) * 16u : 16u;
+                        ad = make_desc(a_plane + (uint32_t)o1 * 16u, lbo, (uint32_t)p.bw * 16u);
+                    } else {
+                        const int kh = m / 3, kw = m - kh * 3;
+                        ad = make_desc(a_plane + (uint32_t)(kh * p.bw + kw) * 16u, PLANE_BYTES, (uint32_t)p.bw * 16u);
+                    }
+                    const uint64_t bd = make_desc(b_base + m * (N * 32), N * 16, 128u);
+                    tc_mma_elect(dbuf + (uint32_t)((5 - q) * NCO), ad, bd, idesc, 1u);      // slots (5-q) .. (5-q)+3
+                }
+                tc_commit_elect(&empty_bar[stage]);
+                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            }
+            tc_commit_elect(&tfull_bar[buf]);
+            if (++buf == NBUF) { buf = 0; bphase ^= 1; }
+        }
+    } else {
+        // ===================== epilogue (warps 5..8) =====================
+        const int q4 = warp & 3;
+        const int et = threadIdx.x - 32 * 5;
+        const int row = q4 * 32 + lane;
+        const int lh = row >> 3, lw = row & 7;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
+        // both buffers start zeroed and "empty"
+        for (int b = 0; b < NBUF; ++b) {
+            for (int c = 0; c < BUFC; c += 8) tmem_st8_zero(lane_base + b * BUFC + c);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[b]);
+        }
+        uint32_t buf = 0, bphase = 0;
+        int stat_n = -1;
+        float rs[16], rq[16], shr[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { rs[k] = 0.f; rq[k] = 0.f; shr[k] = 0.f; }
+        auto flush_stats = [&]() {
+            if (p.stats != nullptr && stat_n >= 0) {
+                const float s1 = transpose_reduce16(rs, lane);
+                const float s2 = transpose_reduce16(rq, lane);
+                if (lane < NCO) {
+                    atomicAdd(&p.stats[((long long)stat_n * p.cout + lane) * 2], (double)s1);
+                    atomicAdd(&p.stats[((long long)stat_n * p.cout + lane) * 2 + 1], (double)s2);
+                }
+#pragma unroll
+                for (int k = 0; k < 16; ++k) { rs[k] = 0.f; rq[k] = 0.f; }
+            }
+        };
+        if (et < 16) sshift[et] = 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int rd = min(1, p.d - 1), rh = min(1, p.h - 1), rw = min(1, p.w - 1);
+        const bool has_shift = p.shift != nullptr;
+        const bool has_stats = p.stats != nullptr;
+        const uint32_t sshift_addr = smem_u32(sshift);
+        const int ref_row = rh * TW + rw;
+        for (int item = blockIdx.x; item < p.work_items; item += gridDim.x) {
+            int n, d0, h0, w0;
+            decode_item((unsigned)item, p, n, d0, h0, w0);
+            if (n != stat_n) {
+                flush_stats();
+                stat_n = n;
+                if (has_shift) {
+                    // shift hand-off exactly as in conv3_tc.cu: the CTA owning the reference voxel (tile 0 of the sample, the
+                    // first item of CTA n) publishes the fp32 accumulator of voxel (1,1,1); everyone else spins on non-zero
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (d0 == 0 && h0 == 0 && w0 == 0) {
+                        mbar_wait(&tfull_bar[buf], bphase);
+                        tc_fence_after();
+                        if (q4 == (ref_row >> 5)) {
+                            uint32_t r[16];
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) r[k] = 0u;
+                            {
+                                uint32_t r8[8];
+                                tmem_ld8(lane_base + buf * BUFC + (5 - rd) * NCO, r8);
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) r[k] = r8[k];
+                                if (NCO == 16) {
+                                    tmem_ld8(lane_base + buf * BUFC + (5 - rd) * NCO + 8, r8);
+                                    tmem_ld_wait();
+#pragma unroll
+                                    for (int k = 0; k < 8; ++k) r[8 + k] = r8[k];
+                                }
+                            }
+                            if (lane == (ref_row & 31)) {
+#pragma unroll
+                                for (int k = 0; k < NCO; ++k) {
+                                    const uint32_t bits = r[k] | 1u;
+                                    sshift[k] = __uint_as_float(bits);
+                                    *reinterpret_cast<volatile uint32_t*>(p.shift + (long long)n * p.cout + k) = bits;
+                                }
+                            }
+                        }
+                    } else if (et < NCO) {
+                        const volatile uint32_t* flag = reinterpret_cast<const volatile uint32_t*>(p.shift + (long long)n * p.cout + et);
+                        uint32_t bits, spins = 0;
+                        while ((bits = *flag) == 0u) {
+                            __nanosleep(64);
+                            if (++spins > (1u << 23)) __trap();
+                        }
+                        sshift[et] = __uint_as_float(bits);
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        const float4 sh = lds128(sshift_addr + k4 * 16);
+                        shr[k4 * 4 + 0] = sh.x; shr[k4 * 4 + 1] = sh.y; shr[k4 * 4 + 2] = sh.z; shr[k4 * 4 + 3] = sh.w;
+                    }
+                }
+            }
+            const int jmax = min(TD, p.d - d0);
+            const int gh = h0 + lh, gw = w0 + lw;
+            const bool rc_ok = gh < p.h && gw < p.w;
+            mbar_wait(&tfull_bar[buf], bphase);
+            tc_fence_after();
+#pragma unroll
+            for (int pl = 0; pl < TD; ++pl) {
+                if (pl >= jmax) break;
+                const uint32_t taddr = lane_base + buf * BUFC + (5 - pl) * NCO;
+                float v[NCO];
+                {
+                    uint32_t r8[8];
+                    tmem_ld8(taddr, r8);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v[k] = __uint_as_float(r8[k]) - shr[k];
+                    if (NCO == 16) {
+                        tmem_ld8(taddr + 8, r8);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) v[NCO == 16 ? 8 + k : k] = __uint_as_float(r8[k]) - shr[8 + k];
+                    }
+                }
+                if (rc_ok) {
+                    bf16* py = p.y + ((((long long)n * p.d + d0 + pl) * p.h + gh) * (long long)p.w + gw) * p.cout;
+#pragma unroll
+                    for (int h8 = 0; h8 < NCO / 8; ++h8) {
+                        float o[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) o[k] = v[h8 * 8 + k];
+                        Store<bf16>::st8(py + h8 * 8, o);
+                    }
+                    if (has_stats) {
+#pragma unroll
+                        for (int k = 0; k < NCO; ++k) { rs[k] += v[k]; rq[k] = fmaf(v[k], v[k], rq[k]); }
+                    }
+                }
+            }
+            // hand the buffer back ZEROED: every MMA of this kernel accumulates
+            for (int c = 0; c < BUFC; c += 8) tmem_st8_zero(lane_base + buf * BUFC + c);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+            if (++buf == NBUF) { buf = 0; bphase ^= 1; }
+        }
+        flush_stats();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// One element of the kd-in-N pack: [ks][m][kc 2][N/8][8 rows][8 ch], N = 4 * gout.
+//   row group ng -> (kd' = ng / (gout/8), output channel group); kd' = 3 is the zero block
+//   m  -> in-plane tap(s): Cin = 8: taps 2m (kc 0) and 2m+1 (kc 1) of the 9 (kh,kw) taps, the 10th is zero;
+//                          else   : tap m = kh*3 + kw, kc selects channels 0-7 / 8-15 of the slice
+// dgrad = same contraction with (ci,co) swapped and taps flipped.
+__device__ __forceinline__ float pack_kdn_elem(const float* __restrict__ w, long long i, int cin_l, int cout_l, int dgrad) {
+    const int gin = dgrad ? cout_l : cin_l, gout = dgrad ? cin_l : cout_l;
+    const bool cin8 = gin == 8;
+    const int nmp = cin8 ? 5 : 9, ngroups = 4 * gout / 8;
+    long long r = i;
+    const int ch8 = (int)(r % 8); r /= 8;
+    const int r8 = (int)(r % 8); r /= 8;
+    const int ng = (int)(r % ngroups); r /= ngroups;
+    const int kc = (int)(r % 2); r /= 2;
+    const int m = (int)(r % nmp); r /= nmp;
+    const int ks = (int)r;
+    const int kdp = ng / (gout / 8), go = (ng % (gout / 8)) * 8 + r8;
+    int gi, t;
+    if (cin8) { gi = ch8; t = 2 * m + kc; if (t > 8) t = -1; }
+    else { gi = ks * 16 + kc * 8 + ch8; t = m; }
+    if (kdp > 2 || t < 0 || gi >= gin) return 0.f;
+    const int tap = kdp * 9 + t;                              // (kd', kh, kw) in the GEMM's (input-side) orientation
+    if (dgrad) return w[((long long)gi * cin_l + go) * 27 + (26 - tap)];      // w[co = gi][ci = go][flipped tap]
+    return w[((long long)go * cin_l + gi) * 27 + tap];
+}
+
+__global__ void pack_kdn_kernel(const float* __restrict__ w, bf16* __restrict__ out, int cin, int cout, int dgrad, long long total) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+        out[i] = __float2bfloat16_rn(pack_kdn_elem(w, i, cin, cout, dgrad));
+}
+
+template <bool CIN8, int NCO, int NSTAGE>
+int launch_kdn(const CUtensorMap& map, const KdnParams& p, cudaStream_t st) {
+    constexpr int A_BYTES = CIN8 ? (PLANE_BYTES + PLANE_PAD) : 2 * PLANE_BYTES;
+    constexpr int B_BYTES = (CIN8 ? 5 : 9) * 4 * NCO * 32;
+    constexpr int SMEM = NSTAGE * (A_BYTES + B_BYTES) + 128 + 8 * (2 * NSTAGE + 4) + 16 + 64 + 64;
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
+    auto kern = conv3_tc_kdn_kernel<CIN8, NCO, NSTAGE>;
+    static bool configured = false;
+    if (!configured) {
+        VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM), "conv3_tc_kdn smem attribute");
+        configured = true;
+    }
+    const int grid = p.work_items < vs_sm_count() ? p.work_items : vs_sm_count();
+    kern<<<(unsigned)grid, NTHREADS, SMEM, st>>>(map, p);
+    VS_CHECK_LAUNCH("conv3_tc_kdn_kernel");
+    return VS_OK;
+}
+
+}  // namespace
+
+extern "C" size_t vs_conv3_tc_kdn_pack_bytes(int cin, int cout, int dgrad) {
+    const int gin = dgrad ? cout : cin, gout = dgrad ? cin : cout;
+    if (!(gin == 8 || (gin % 16 == 0 && gin >= 16)) || !(gout == 8 || gout == 16)) return 0;
+    const int kslices = gin == 8 ? 1 : gin / 16;
+    return (size_t)kslices * (gin == 8 ? 5 : 9) * 4 * gout * 32;
+}
+
+extern "C" int vs_pack_conv3_weight_tc_kdn(const float* w, void* out, int cin, int cout, int dgrad, void* stream) {
+    const size_t bytes = vs_conv3_tc_kdn_pack_bytes(cin, cout, dgrad);
+    VS_REQUIRE(w && out && bytes > 0, VS_ERR_UNSUPPORTED, "pack_conv3_weight_tc_kdn: unsupported shape Cin=%d Cout=%d", cin, cout);
+    const long long total = (long long)(bytes / 2);
+    pack_kdn_kernel<<<(unsigned)min(1024LL, (total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, (bf16*)out, cin, cout, dgrad, total);
+    VS_CHECK_LAUNCH("pack_kdn_kernel");
+    return VS_OK;
+}
+
+// y[n,d,h,w,gout] = conv3(x[n,d,h,w,gin], wkdn); bf16 NDHWC in and out; gout in {8, 16}; D >= 4.
+// stats / shift: as vs_conv3x3x3_fprop (zeroed here unless prezeroed).
+extern "C" int vs_conv3x3x3_tc_kdn(const void* x, const void* wkdn, void* y, double* stats, float* shift, int prezeroed,
+                                   int n, int d, int h, int w, int gin, int gout, void* stream) {
+    VS_REQUIRE(x && wkdn && y, VS_ERR_SHAPE, "conv3_tc_kdn: null pointer");
+    VS_REQUIRE((gin == 8 || (gin % 16 == 0 && gin >= 16)) && (gout == 8 || gout == 16) && d >= TD, VS_ERR_UNSUPPORTED,
+               "conv3_tc_kdn: needs Cin = 8 or a multiple of 16, Cout in {8,16}, D >= 4 (Cin=%d Cout=%d D=%d)", gin, gout, d);
+    VS_REQUIRE(vs_aligned16(x) && vs_aligned16(y) && vs_aligned16(wkdn), VS_ERR_ALIGN, "conv3_tc_kdn: pointers must be 16B aligned");
+    EncodeTiledFn encode = get_encode_fn();
+    VS_REQUIRE(encode != nullptr, VS_ERR_CUDA, "conv3_tc_kdn: cuTensorMapEncodeTiled unavailable");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int tiles_h = (h + TH - 1) / TH, tiles_w = (w + TW - 1) / TW;
+    const int bw = min(HW, w + 2), bh = min(HH, h + 2), bd = HD;
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUtensorMap map;
+    CUresult cr;
+    if (gin == 8) {
+        const cuuint64_t gdim4[4] = {(cuuint64_t)w * 8, (cuuint64_t)h, (cuuint64_t)d, (cuuint64_t)n};
+        const cuuint64_t gstr4[3] = {(cuuint64_t)w * 16, (cuuint64_t)h * w * 16, (cuuint64_t)d * h * w * 16};
+        const cuuint32_t box4[4] = {(cuuint32_t)bw * 8, (cuuint32_t)bh, (cuuint32_t)bd, 1};
+        cr = encode(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), gdim4, gstr4, box4, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        const cuuint64_t gdim[5] = {(cuuint64_t)gin, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)d, (cuuint64_t)n};
+        const cuuint64_t gstr[4] = {(cuuint64_t)gin * 2, (cuuint64_t)w * gin * 2, (cuuint64_t)h * w * gin * 2,
+                                    (cuuint64_t)d * h * w * gin * 2};
+        const cuuint32_t box[5] = {8, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd, 1};
+        cr = encode(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    VS_REQUIRE(cr == CUDA_SUCCESS, VS_ERR_CUDA, "conv3_tc_kdn: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+
+    KdnParams p;
+    p.n = n; p.d = d; p.h = h; p.w = w; p.cin = gin; p.cout = gout;
+    p.tiles_h = tiles_h; p.tiles_w = tiles_w;
+    p.tiles_d = (d + TD - 1) / TD;
+    p.tiles_per_n = p.tiles_d * tiles_h * tiles_w;
+    p.bw = bw; p.bh = bh; p.bd = bd;
+    p.ref_tile = 0;                                                  // voxel (1,1,1) lies in tile (0,0,0) when D >= 4
+    p.kslices = gin == 8 ? 1 : gin / 16;
+    const long long items = (long long)n * p.tiles_per_n;
+    VS_REQUIRE(items < 2147483647LL, VS_ERR_SHAPE, "conv3_tc_kdn: too many work items");
+    p.work_items = (int)items;
+    p.wpack = (const bf16*)wkdn; p.y = (bf16*)y; p.stats = stats; p.shift = shift;
+    if (!prezeroed) {
+        if (stats) VS_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * (size_t)n * gout, st), "conv3_tc_kdn stats memset");
+        if (shift) VS_CUDA(cudaMemsetAsync(shift, 0, sizeof(float) * (size_t)n * gout, st), "conv3_tc_kdn shift memset");
+    }
+    if (gin == 8) {
+        if (gout == 8) return launch_kdn<true, 8, 4>(map, p, st);
+        return launch_kdn<true, 16, 4>(map, p, st);
+    }
+    if (gout == 8) return launch_kdn<false, 8, 4>(map, p, st);
+    return launch_kdn<false, 16, 4>(map, p, st);
+}

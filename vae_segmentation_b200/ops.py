@@ -409,3 +409,27 @@ def clip_center(x, lo, hi, sub, div):
     out = torch.empty(x.shape, device=x.device, dtype=torch.float32)
     _cabi.call("vs_clip_center", kind, _p(x), _p(out), x.numel(), float(lo), float(hi), float(sub), float(div), _stream())
     return out
+
+
+# ---- experimental: kd-in-N tensor-core convolution (not used by the default path) ----------
+def pack_conv3_weight_tc_kdn(w, dgrad=False):
+    cout, cin = w.shape[0], w.shape[1]
+    nbytes = _cabi.lib().vs_conv3_tc_kdn_pack_bytes(cin, cout, int(dgrad))
+    if nbytes == 0:
+        return None
+    out = torch.empty(nbytes // 2, device=w.device, dtype=torch.bfloat16)
+    _cabi.call("vs_pack_conv3_weight_tc_kdn", _p(_f32(w, "weight")), _p(out), cin, cout, int(dgrad), _stream())
+    return out
+
+
+def conv3_tc_kdn(x, wkdn, dims, gin, gout, want_stats=False):
+    """y (bf16 NDHWC) = conv3(x, wkdn) through the experimental kd-in-N kernel; returns (y, stats or None)."""
+    n, d, h, w = dims
+    y = torch.empty(n, d, h, w, gout, device=x.device, dtype=torch.bfloat16)
+    stats = shift = None
+    if want_stats:
+        buf = torch.empty(stats_words(n, gout), device=x.device, dtype=torch.float64)
+        stats = buf[:n * gout * 2].view(n, gout, 2)
+        shift = buf[n * gout * 2:].view(torch.float32)[:n * gout].view(n, gout)
+    _cabi.call("vs_conv3x3x3_tc_kdn", _p(x), _p(wkdn), _p(y), _p(stats), _p(shift), 0, n, d, h, w, gin, gout, _stream())
+    return y, stats
