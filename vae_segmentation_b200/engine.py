@@ -29,6 +29,9 @@ USE_TENSOR_CORES = os.environ.get("VAESEG_NO_TC", "0") != "1"
 # VAESEG_NO_FUSE_REDUCE=1 keeps the InstanceNorm-backward reduction a separate pass (A/B measurements, parity tests)
 FUSE_BWD_REDUCE = os.environ.get("VAESEG_NO_FUSE_REDUCE", "0") != "1"
 HEAD_DIRECT = os.environ.get("VAESEG_HEAD_DIRECT", "0") == "1"
+# VAESEG_KDN=1 routes the forward 3x3x3 convolutions with 8 / 16 output channels at >= 48^3 through the EXPERIMENTAL
+# kd-in-N kernel (csrc/conv3_tc_kdn.cu).  Off by default: its first GPU run is still pending.
+USE_KDN = os.environ.get("VAESEG_KDN", "0") == "1"
 
 # tools/precision_probe*.py only: names of tensor classes to round through bf16 while running the fp32
 # check mode ("y", "a", "g", "dy", "k2"), to attribute bf16-mode error to a storage point.  Empty in production.
@@ -148,9 +151,18 @@ class PackCache(object):
             ent["key"] = key
         return ent["tcd"]
 
+    def conv3_kdn(self, w):
+        """Experimental kd-in-N pack of a weight (lazy: re-packed on next use after the weights changed), or None."""
+        ent, key = self._entry("kdn", w, True)
+        if ent["key"] != key:
+            ent["tcf"] = ops.pack_conv3_weight_tc_kdn(w.detach(), dgrad=False)
+            ent["tc"] = True
+            ent["key"] = key
+        return ent["tcf"]
+
     def repack_all(self):
         """Re-packs every known entry in place with one launch; entries become current for the present weights."""
-        ents = [e for e in self._store.values() if e["key"] is not None]
+        ents = [e for e in self._store.values() if e["key"] is not None and e["kind"] != "kdn"]
         if not ents:
             self.invalidate()
             return
@@ -279,8 +291,15 @@ def program_forward(layers, tensors, x, dims, dtype, cache, record=True):
             if L.in_planar and L.cin == 2 and record and dtype == torch.bfloat16 and L.cout % 8 == 0:
                 wdtc = cache.inblock2_dgrad_tc(tensors[L.wi])      # planar 2-channel input gradient on the tensor cores
             # the conv bias is a no-op ahead of InstanceNorm(affine=False): skipped
-            y, stats = ops.conv3_fprop(cur, wf, None, (n, d, h, w), L.cin, L.cout, dtype, in_planar=L.in_planar,
-                                       wtc=None if L.in_planar else wtc, arena=arena)
+            wk = None
+            if (USE_KDN and USE_TENSOR_CORES and dtype == torch.bfloat16 and not L.in_planar and L.cout in (8, 16)
+                    and _tc_channels(L.cin) and d >= 4 and d * h * w >= 48 ** 3):
+                wk = cache.conv3_kdn(tensors[L.wi])
+            if wk is not None:
+                y, stats = ops.conv3_tc_kdn(cur, wk, (n, d, h, w), L.cin, L.cout, want_stats=True, arena=arena)
+            else:
+                y, stats = ops.conv3_fprop(cur, wf, None, (n, d, h, w), L.cin, L.cout, dtype, in_planar=L.in_planar,
+                                           wtc=None if L.in_planar else wtc, arena=arena)
             skip = slots[L.skip_from] if L.skip_from is not None else None
             y = _sim(y, "y")
             a = _sim(ops.inorm_relu_apply(y, stats, skip), "a")

@@ -422,14 +422,20 @@ def pack_conv3_weight_tc_kdn(w, dgrad=False):
     return out
 
 
-def conv3_tc_kdn(x, wkdn, dims, gin, gout, want_stats=False):
-    """y (bf16 NDHWC) = conv3(x, wkdn) through the experimental kd-in-N kernel; returns (y, stats or None)."""
+def conv3_tc_kdn(x, wkdn, dims, gin, gout, want_stats=False, arena=None):
+    """y (bf16 NDHWC) = conv3(x, wkdn) through the experimental kd-in-N kernel; returns (y, stats or None).
+    arena: zero-filled StatsArena supplying the statistics / shift words (as conv3_fprop)."""
     n, d, h, w = dims
     y = torch.empty(n, d, h, w, gout, device=x.device, dtype=torch.bfloat16)
     stats = shift = None
+    prezeroed = 0
     if want_stats:
-        buf = torch.empty(stats_words(n, gout), device=x.device, dtype=torch.float64)
+        if arena is not None:
+            buf = arena.take(stats_words(n, gout))
+            prezeroed = 1
+        else:
+            buf = torch.empty(stats_words(n, gout), device=x.device, dtype=torch.float64)
         stats = buf[:n * gout * 2].view(n, gout, 2)
         shift = buf[n * gout * 2:].view(torch.float32)[:n * gout].view(n, gout)
-    _cabi.call("vs_conv3x3x3_tc_kdn", _p(x), _p(wkdn), _p(y), _p(stats), _p(shift), 0, n, d, h, w, gin, gout, _stream())
+    _cabi.call("vs_conv3x3x3_tc_kdn", _p(x), _p(wkdn), _p(y), _p(stats), _p(shift), prezeroed, n, d, h, w, gin, gout, _stream())
     return y, stats
