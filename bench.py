@@ -215,6 +215,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the CUDA-graph-captured step")
     ap.add_argument("--kernel-table", action="store_true", help="also print the per-kernel time table to stderr")
+    ap.add_argument("--e2e-prefetch", action="store_true",
+                    help="e2e leg: double-buffered inputs, the host->device copy of step i+1 overlaps step i (EXPERIMENTAL: "
+                         "written after the GPU budget of round 1 ended, not yet run on a GPU; default off)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -345,8 +348,45 @@ def main():
     ms_total = timed(run_step, args.steps)
     launches = calls_per_step * args.steps
     # ---- timed: end to end from pinned host buffers -----------------------------------------
-    step_e2e_any()
-    ms_e2e = timed(step_e2e_any, args.steps)
+    if args.e2e_prefetch and use_graph:
+        # two static input buffer pairs and two captured graphs: while graph(slot) runs, the next batch is copied into
+        # the other pair on a copy stream.  Every timed step still pays one H2D copy of its inputs and one D2H read of
+        # its loss; the copies are merely enqueued one step ahead.
+        img_d2, lab_d2 = img_d.clone(), lab_d.clone()          # valid data: capture() takes a real warm-up step on them
+        trainer.capture(img_d2, lab_d2, warmup=1, slot=1)
+        bufs = ((img_d, lab_d), (img_d2, lab_d2))
+        copy_stream = torch.cuda.Stream()
+        state = {"i": 0, "primed": False, "done": [None, None]}
+
+        def enqueue_copy(slot):
+            # the pair may only be overwritten once the last step that READ it has finished (its own event), not after
+            # everything enqueued so far -- the step that is running now reads the other pair
+            if state["done"][slot] is not None:
+                copy_stream.wait_event(state["done"][slot])
+            with torch.cuda.stream(copy_stream):
+                bufs[slot][0].copy_(img_h, non_blocking=True)
+                bufs[slot][1].copy_(lab_h, non_blocking=True)
+
+        def step_e2e_prefetch():
+            slot = state["i"] & 1
+            cur = torch.cuda.current_stream()
+            if not state["primed"]:
+                enqueue_copy(slot)
+                state["primed"] = True
+            cur.wait_stream(copy_stream)                                # this step's inputs have arrived
+            mon = trainer.step_graphed(slot=slot)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            state["done"][slot] = ev
+            enqueue_copy(slot ^ 1)                                      # next step's inputs, overlapping this step
+            loss_host.copy_(mon["final_loss"].reshape(1), non_blocking=False)
+            state["i"] += 1
+
+        step_e2e_fn = step_e2e_prefetch
+    else:
+        step_e2e_fn = step_e2e_any
+    step_e2e_fn()
+    ms_e2e = timed(step_e2e_fn, args.steps)
     # ---- the dominant kernel, CUDA events around each of its launches over the same K steps (eager launches:
     #      events cannot be recorded inside a replayed graph) ---------------------------------------
     only = KernelTimer(only_name=dominant)

@@ -256,6 +256,8 @@ class JointTrainer(object):
         self.ddp_overlap = os.environ.get("VAESEG_DDP_OVERLAP", "0") == "1"
         self._bucketer = None
         self._grads_reduced = False
+        self._graphs = {}                        # slot -> (captured CUDA graph, monitored terms), see capture()
+        self._graph = self._graph_mon = None
         # the step's own (critical) chain runs at high priority; the teacher forward and the weight gradients, which
         # only have to finish by the loss / the optimiser step, fill in behind it at the default priority
         hp = -1 if os.environ.get("VAESEG_STREAM_PRIORITY", "1") == "1" else 0
@@ -412,13 +414,15 @@ class JointTrainer(object):
         finally:
             engine.WGRAD_STREAM = None
 
-    def capture(self, img_static, label_static, warmup=2):
+    def capture(self, img_static, label_static, warmup=2, slot=0):
         """CUDA-graph capture of zero_grad + forward (student, teacher, losses) + backward on the given static
         input buffers; the gradient all-reduce and the fused optimiser kernel stay eager (two launches).  At
         ~600 kernel launches per step the Python/launch path, not the GPU, bounds an eager step.
         Autograd pins each parameter's gradient-accumulation node to the stream of its first backward, and a
         capture may not depend on the legacy default stream: run EVERY step of this trainer under
-        `with torch.cuda.stream(trainer.stream)` if it will be captured later."""
+        `with torch.cuda.stream(trainer.stream)` if it will be captured later.
+        `slot`: several graphs over different static input buffers may coexist (e.g. two, so that the host->device copy
+        of the next batch overlaps the current step: bench.py --e2e-prefetch); `step_graphed(slot=...)` replays one."""
         side = self.stream
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):            # autograd's stream bookkeeping must see the capture stream
@@ -426,24 +430,30 @@ class JointTrainer(object):
                 self.step(img_static, label_static)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph, stream=side):
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
             mon = self.forward_backward(img_static, label_static)
-        self._graph_mon = mon
+        if not hasattr(self, "_graphs"):
+            self._graphs = {}
+        self._graphs[slot] = (graph, mon)
+        if slot == 0:
+            self._graph, self._graph_mon = graph, mon
         return self
 
     def release_graph(self):
         """Drops the captured graph (and the NCCL kernels it holds)."""
         self._graph = None
         self._graph_mon = None
+        self._graphs = {}
         torch.cuda.synchronize()
 
-    def step_graphed(self, update_teacher=False):
+    def step_graphed(self, update_teacher=False, slot=0):
         if update_teacher:
             self.ema_teacher()
-        self._graph.replay()
+        graph, mon = self._graphs[slot]
+        graph.replay()
         self.opt.step(self._grad_scale())
-        return self._graph_mon
+        return mon
 
     def test_time_train(self, finetune, img, label, iters=1, lr_finetune=1e-2):
         """main_target.py:807-900: per validation case, `finetune` (a Joint) starts from the
