@@ -389,3 +389,27 @@ def test_checkpoint_resume_through_fused_optimizer(tmp_path):
     torch.cuda.synchronize()
     rel = ((tr2.arena.data - tr.arena.data).norm() / tr.arena.data.norm()).item()
     assert rel < 1e-4, rel            # same weights + same momentum; only the atomics' summation order differs
+
+
+@pytest.mark.skipif(os.environ.get("VAESEG_TEST_UNVERIFIED", "0") != "1",
+                    reason="JointTrainer.validate was written after the GPU budget of round 1 ended: opt-in until its first run")
+def test_validation_pass_with_test_time_training():
+    """main_target.py:795-960: per-case TTT + binary Dice; scores equal avg_dsc(binary=True) of the returned predictions."""
+    torch.manual_seed(21)
+    patch = 32
+    mk = lambda: jm.Joint([jm.Segmentation(1, 2, norm_type=1), jm.VAE(2, 2, norm_type=1, dim=128, patch=patch)]).to(DEV)
+    student, teacher, finetune = mk(), mk(), mk()
+    teacher.load_state_dict(student.state_dict())
+    tr = ts.JointTrainer(student, teacher)
+    cases = [(synth_image(1, patch).to(DEV), synth_label(1, patch).to(DEV)) for _ in range(3)]
+    out0 = tr.validate(cases)
+    assert len(out0["scores"]) == 3 and out0["scores"] == out0["scores_noft"]
+    want = []
+    for img, label in cases:
+        with torch.no_grad():
+            p = student.Seg.predict(img)
+        want.append(ev.avg_dsc({"p": p, "t": ev.one_hot(label, 2)}, "p", "t", binary=True, botindex=1, topindex=2).item())
+    assert np.allclose(out0["scores"], want, atol=1e-6) and abs(out0["dsc"] - np.mean(want)) < 1e-6
+    out1 = tr.validate(cases, finetune=finetune, val_finetune=1)
+    assert np.allclose(out1["scores_noft"], want, atol=1e-6)            # the student itself is untouched by TTT
+    assert all(0.0 <= s <= 1.0 for s in out1["scores"])

@@ -477,3 +477,40 @@ class JointTrainer(object):
             p0 = self.student.Seg.predict(img)
             p1 = finetune.Seg.predict(img)
         return p0, p1
+
+    def validate(self, cases, finetune=None, val_finetune=0, lr_finetune=1e-2):
+        """The validation pass of main_target.py:795-960 (method 'domain_adaptation') over `cases`, an iterable of
+        (img [1,1,D,H,W], label [1,1,D,H,W]) CUDA tensors: per case optionally `val_finetune` test-time-training
+        iterations on a private copy of the student (:807-900), then no-grad inference and the binary (argmax) Dice of
+        the foreground class against the ground truth, `avg_dsc(binary=True, botindex=1, topindex=n_class)` (:941-945),
+        for the student ("noft") and the finetuned model.  Returns {'dsc', 'dsc_noft', 'scores', 'scores_noft'} with
+        dsc = mean over cases (the reference's `dsc_pancreas / len(val_loader)`).  Scores stay on the device until the
+        end (one host sync per pass instead of one `.item()` per case); under data parallelism every rank takes
+        cases[rank::world] and the two sums are all-reduced -- cases are independent, nothing else is exchanged."""
+        world = _world()
+        rank = dist.get_rank() if world > 1 else 0
+        scores, scores_noft = [], []
+        for idx, (img, label) in enumerate(cases):
+            if idx % world != rank:
+                continue
+            if val_finetune and finetune is not None:
+                p0, p1 = self.test_time_train(finetune, img, label, iters=val_finetune, lr_finetune=lr_finetune)
+            else:
+                with torch.no_grad():
+                    p0 = self.student.Seg.predict(img)
+                p1 = p0
+            onehot = ev.one_hot(label, p0.shape[1])
+            top = p0.shape[1]
+            scores_noft.append(ev.avg_dsc({"p": p0, "t": onehot}, "p", "t", binary=True, botindex=1, topindex=top).reshape(()))
+            scores.append(scores_noft[-1] if p1 is p0 else
+                          ev.avg_dsc({"p": p1, "t": onehot}, "p", "t", binary=True, botindex=1, topindex=top).reshape(()))
+        dev = self.arena.data.device
+        local = torch.stack([torch.stack(scores).sum() if scores else torch.zeros((), device=dev),
+                             torch.stack(scores_noft).sum() if scores_noft else torch.zeros((), device=dev),
+                             torch.tensor(float(len(scores)), device=dev)])
+        if world > 1:
+            dist.all_reduce(local, op=dist.ReduceOp.SUM)
+        total = local.cpu()
+        n = max(int(total[2].item()), 1)
+        return {"dsc": total[0].item() / n, "dsc_noft": total[1].item() / n,
+                "scores": [s.item() for s in scores], "scores_noft": [s.item() for s in scores_noft]}
