@@ -396,7 +396,7 @@ def test_checkpoint_resume_through_fused_optimizer(tmp_path):
 def test_validation_pass_with_test_time_training():
     """main_target.py:795-960: per-case TTT + binary Dice; scores equal avg_dsc(binary=True) of the returned predictions."""
     torch.manual_seed(21)
-    patch = 32
+    patch = 64
     mk = lambda: jm.Joint([jm.Segmentation(1, 2, norm_type=1), jm.VAE(2, 2, norm_type=1, dim=128, patch=patch)]).to(DEV)
     student, teacher, finetune = mk(), mk(), mk()
     teacher.load_state_dict(student.state_dict())

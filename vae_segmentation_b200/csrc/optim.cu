@@ -65,7 +65,8 @@ extern "C" int vs_sgd_step(float* p, const float* g, float* buf, long long count
 extern "C" int vs_adam_step(float* p, const float* g, float* m, float* v, long long count, float lr, float beta1,
                             float beta2, float eps, int step, float gscale, void* stream) {
     VS_REQUIRE(p && g && m && v && count > 0 && step >= 1, VS_ERR_SHAPE, "adam_step: bad arguments");
-    const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+    // bias corrections in double on the host, like torch.optim.Adam (1 - 0.999f in fp32 carries ~5e-5 relative error)
+    const float bc1 = (float)(1.0 - pow((double)beta1, (double)step)), bc2 = (float)(1.0 - pow((double)beta2, (double)step));
     adam_kernel<<<ew_grid(count), NT, 0, (cudaStream_t)stream>>>(p, g, m, v, count, lr, beta1, beta2, eps, bc1, bc2, gscale);
     VS_CHECK_LAUNCH("adam_kernel");
     return VS_OK;

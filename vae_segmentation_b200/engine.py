@@ -472,13 +472,14 @@ class ProgramFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, spec, x, *tensors):
-        layers, dtype, cache, param_refs = spec
+        layers, dtype, cache, param_refs = spec[:4]
+        grad_on = spec[4] if len(spec) > 4 else True        # torch.is_grad_enabled() at apply time (always off in here)
         planar = layers[0].in_planar
         if planar:
             n, d, h, w = x.shape[0], x.shape[2], x.shape[3], x.shape[4]
         else:
             n, d, h, w = x.shape[0], x.shape[1], x.shape[2], x.shape[3]
-        record = any(ctx.needs_input_grad)
+        record = grad_on and any(ctx.needs_input_grad)       # needs_input_grad ignores torch.no_grad(): no tape for inference
         out, _, tape = program_forward(layers, tensors, x.contiguous(), (n, d, h, w), dtype, cache, record=record)
         ctx.tape = _record_weights(tape, tensors) if record else None
         ctx.dtype = dtype
@@ -501,9 +502,10 @@ class VAEFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, spec, x, z, scale, use_z, *tensors):
-        enc, dec, fc, dtype, cache, param_refs, dim = spec
+        enc, dec, fc, dtype, cache, param_refs, dim = spec[:7]
+        grad_on = spec[7] if len(spec) > 7 else True
         n, d, h, w = x.shape[0], x.shape[2], x.shape[3], x.shape[4]
-        record = any(ctx.needs_input_grad)
+        record = grad_on and any(ctx.needs_input_grad)
         ctx.set_materialize_grads(False)
         hcur, (n, d2, h2, w2), tape_e = program_forward(enc, tensors, x.contiguous(), (n, d, h, w), dtype, cache, record)
         c = enc[-1].cout
@@ -574,12 +576,13 @@ class DecodeFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, spec, lat, *tensors):
-        dec, fc, dtype, cache, param_refs, dim, side = spec
+        dec, fc, dtype, cache, param_refs, dim, side = spec[:7]
+        grad_on = spec[7] if len(spec) > 7 else True
         w2_, b2_ = tensors[fc[4]].detach(), tensors[fc[5]].detach()
         n = lat.shape[0]
         c = dec[0].cin
         s3 = side ** 3
-        record = any(ctx.needs_input_grad)
+        record = grad_on and any(ctx.needs_input_grad)
         lat = lat.contiguous().float()
         hdec = ops.fc_decode_fwd(lat, w2_, b2_, n, s3, c, dim, dtype, side)
         recon, _, tape = program_forward(dec, tensors, hdec, (n, side, side, side), dtype, cache, record)

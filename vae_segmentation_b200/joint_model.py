@@ -176,7 +176,7 @@ class _Engineered(nn.Module):
         layers, params = self._prog()
         dtype = self.compute_dtype
         xin = x.permute(0, 2, 3, 4, 1).contiguous().to(dtype)
-        out = engine.ProgramFn.apply((layers, dtype, self._cache, params), xin, *params)
+        out = engine.ProgramFn.apply((layers, dtype, self._cache, params, torch.is_grad_enabled()), xin, *params)
         return out.permute(0, 4, 1, 2, 3).float()
 
 
@@ -312,7 +312,7 @@ class Segmentation(_Engineered):
         if x.shape[2] % 16 or x.shape[3] % 16 or x.shape[4] % 16:
             raise RuntimeError("Segmentation: spatial dims must be divisible by 16 (four stride-2 levels), got %s" % (tuple(x.shape[2:]),))
         layers, params = self._prog()
-        return engine.ProgramFn.apply((layers, self.compute_dtype, self._cache, params), x, *params)
+        return engine.ProgramFn.apply((layers, self.compute_dtype, self._cache, params, torch.is_grad_enabled()), x, *params)
 
     def forward(self, data_dict, in_key, out_key, dropout=0.0):
         _no_dropout(dropout, "Segmentation")
@@ -372,7 +372,7 @@ class VAE(_Engineered):
         if mid_input:
             if not x.is_cuda:
                 raise RuntimeError("vaeseg_b200.VAE: input must be a CUDA tensor (no CPU fallback)")
-            return engine.DecodeFn.apply((dec, fc, dtype, self._cache, params, self.dim, self.side), x, *params)
+            return engine.DecodeFn.apply((dec, fc, dtype, self._cache, params, self.dim, self.side, torch.is_grad_enabled()), x, *params)
         _check_input(x, "VAE")
         if x.shape[2] != self.patch or x.shape[3] != self.patch or x.shape[4] != self.patch:
             raise RuntimeError("VAE built for %d^3 patches got input %s" % (self.patch, tuple(x.shape)))
@@ -383,7 +383,7 @@ class VAE(_Engineered):
         if if_random:
             zdev = z if z.is_cuda else z.pin_memory().to(x.device, non_blocking=True)
             zdev = zdev.float().contiguous()
-        return engine.VAEFn.apply((enc, dec, fc, dtype, self._cache, params, self.dim), x, zdev, float(scale),
+        return engine.VAEFn.apply((enc, dec, fc, dtype, self._cache, params, self.dim, torch.is_grad_enabled()), x, zdev, float(scale),
                                   bool(if_random), *params)
 
 

@@ -175,31 +175,85 @@ def sync_first_term_(terms):
     return torch.cat([g / world, terms[1:]])
 
 
-class SegTrainer(object):
+class _GraphedTrainer(object):
+    """Shared plumbing of the single-network trainers: side stream for the weight gradients, CUDA-graph capture of
+    zero_grad + forward + backward on static input buffers, eager all-reduce + fused optimiser after the replay."""
+
+    def _init_streams(self):
+        hp = -1 if os.environ.get("VAESEG_STREAM_PRIORITY", "1") == "1" else 0
+        self.stream = torch.cuda.Stream(priority=hp)
+        self.wgrad_stream = [torch.cuda.Stream()]
+        self.overlap = True
+        self._graphs = {}
+
+    def _backward(self, loss):
+        from . import engine
+        engine.WGRAD_STREAM = self.wgrad_stream if self.overlap else None
+        try:
+            loss.backward()
+            engine.join_wgrad_stream()
+        finally:
+            engine.WGRAD_STREAM = None
+
+    def capture(self, *static_inputs, warmup=2, slot=0):
+        """Same contract as JointTrainer.capture: run every step of this trainer under
+        `with torch.cuda.stream(trainer.stream)` if it will be captured."""
+        side = self.stream
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):          # forward + backward only: no optimiser state is touched
+                self.forward_backward(*static_inputs)
+            self.arena.zero_grad()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            mon = self.forward_backward(*static_inputs)
+        self._graphs[slot] = (graph, mon)
+        return self
+
+    def step_graphed(self, slot=0):
+        graph, mon = self._graphs[slot]
+        graph.replay()
+        self.opt.step(allreduce_mean_(self.arena.grad))
+        return mon
+
+    def release_graph(self):
+        self._graphs = {}
+        torch.cuda.synchronize()
+
+
+class SegTrainer(_GraphedTrainer):
     def __init__(self, seg, lr=1e-2, momentum=0.9, eps=0.0001):
         self.seg = seg
         self.arena = FlatArena(seg)
         self.opt = FusedSGD(self.arena, lr, momentum)
         self.eps = eps                       # main_source.py:150-182 uses 1e-4
+        self._init_streams()
 
     def loss(self, img, label):
         pred = self.seg.predict(img)
         return 1 - ev.avg_dsc_fused(pred, label, "label", botindex=1, topindex=2, eps=self.eps), pred
 
-    def step(self, img, label):
+    def forward_backward(self, img, label):
         self.arena.zero_grad()
         loss, _ = self.loss(img, label)
-        loss.backward()
+        self._backward(loss)
+        return {"dice_loss": loss.detach(), "final_loss": loss.detach()}
+
+    def step(self, img, label):
+        mon = self.forward_backward(img, label)
         self.opt.step(allreduce_mean_(self.arena.grad))
-        return {"dice_loss": loss.detach()}
+        return mon
 
 
-class VAETrainer(object):
+class VAETrainer(_GraphedTrainer):
     def __init__(self, vae, lr=1e-2, momentum=0.9, scale=0.35, eps=0.0001):
         self.vae = vae
         self.arena = FlatArena(vae)
         self.opt = FusedSGD(self.arena, lr, momentum)
         self.scale, self.eps = scale, eps
+        self._init_streams()
 
     def loss(self, label, z=None):
         onehot = ev.one_hot(label, 2)
@@ -208,12 +262,18 @@ class VAETrainer(object):
         dsc = 1 - ev.avg_dsc_fused(recon, label, "label", botindex=1, topindex=2, eps=self.eps)
         return dsc + 0.00002 * kl, dsc, kl, recon
 
-    def step(self, label, z=None):
+    def forward_backward(self, label, z=None):
+        """z: the reparameterisation noise; pass a static CUDA buffer when the step is captured (the reference draws it
+        from the CPU generator every call, joint_model.py:246 -- the caller then refreshes the buffer per step)."""
         self.arena.zero_grad()
         loss, dsc, kl, _ = self.loss(label, z)
-        loss.backward()
-        self.opt.step(allreduce_mean_(self.arena.grad))
+        self._backward(loss)
         return {"final_loss": loss.detach(), "dice_loss": dsc.detach(), "kl_loss": kl.detach()}
+
+    def step(self, label, z=None):
+        mon = self.forward_backward(label, z)
+        self.opt.step(allreduce_mean_(self.arena.grad))
+        return mon
 
 
 class JointTrainer(object):
@@ -274,8 +334,10 @@ class JointTrainer(object):
         ops.ema_update(self.teacher_arena.data, self.arena.data, self.alpha)
         self.teacher.repack_packs()
 
-    def losses(self, img, label, student=None):
-        """Forward of one step; returns (final_loss, dict of monitored terms)."""
+    def losses(self, img, label, student=None, sync=True):
+        """Forward of one step; returns (final_loss, dict of monitored terms).  sync=False: never issue a collective
+        (test-time training / validation: cases are sharded over ranks and the reference thresholds the dynamic lambda
+        on each case's OWN recon loss, main_target.py:838-847)."""
         student = student or self.student
         cur = torch.cuda.current_stream()
 
@@ -301,7 +363,7 @@ class JointTrainer(object):
         else:
             tb = run_teacher()
         pred = batch["pred"]
-        if self.fused_loss and not (self.loss_type == 8 and _world() > 1):
+        if self.fused_loss and not (sync and self.loss_type == 8 and _world() > 1):
             klv = ev.KLloss(tb) if tb.get("mean") is not None else None                                   # :544 (teacher's, F8)
             final, m5 = ev.joint_target_loss(pred, batch["recon_pred"], label, tb["only_fake"], kl=klv,
                                              lambda_vae=self.lambda_vae, loss_type=self.loss_type, use_kl=self.kl,
@@ -317,7 +379,7 @@ class JointTrainer(object):
             final = dsc_loss_fake
         else:
             terms = torch.stack([recon_loss.detach(), dsc_loss_fake.detach(), klloss.detach()])
-            if self.loss_type == 8:
+            if self.loss_type == 8 and sync:
                 terms = sync_first_term_(terms)
             _, wts = ops.compose_target_loss(terms, self.lambda_vae, self.loss_type, self.kl)
             final = wts[0] * recon_loss + wts[1] * dsc_loss_fake + (wts[2] * klloss if self.kl else 0)
@@ -426,8 +488,11 @@ class JointTrainer(object):
         side = self.stream
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):            # autograd's stream bookkeeping must see the capture stream
-            for _ in range(max(warmup, 1)):      # also runs every lazy one-time init (smem attributes, caches)
-                self.step(img_static, label_static)
+            # forward + backward only: warming up must not take optimiser steps (weights, momentum and the Adam step
+            # counter stay exactly where the training schedule left them); also runs every lazy one-time init
+            for _ in range(max(warmup, 1)):
+                self.forward_backward(img_static, label_static)
+            self.arena.zero_grad()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
@@ -465,11 +530,15 @@ class JointTrainer(object):
             for p in finetune.Vae.parameters():
                 p.requires_grad = False
             ft = self._ft_arena = FlatArena(finetune.Seg)
-        ft.data.copy_(self.arena.data)                                                # :810 load_state_dict
+        ft.data.copy_(self.arena.data)                                                # :810 load_state_dict (Seg part)
+        with torch.no_grad():                                                         # ... and the Vae part: the whole
+            for dst, src in zip(finetune.Vae.parameters(), self.student.Vae.parameters()):   # Joint state is loaded
+                if dst.data_ptr() != src.data_ptr():
+                    dst.copy_(src)
         finetune.repack_packs()
         for _ in range(iters):
             ft.zero_grad()
-            final, _, _ = self.losses(img, label, student=finetune)
+            final, _, _ = self.losses(img, label, student=finetune, sync=False)      # per-case: no collective
             final.backward()
             ops.sgd_step(ft.data, ft.grad, None, lr_finetune, 0.0, first=True)       # :886 SGD(lr_finetune, momentum 0)
             finetune.repack_packs()
