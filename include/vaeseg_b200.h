@@ -60,6 +60,11 @@ typedef struct {
     void* tcd;            /* bf16 tensor-core dgrad pack (of [cout_pad][Cin][27]) or NULL */
     long long tcf_elems, tcd_elems;
     int cin, cout, cout_pad, cin_pad;   /* cin_pad > cin zero-pads the input channels of the dgrad pack (0 = none) */
+    void* kdn;            /* bf16 kd-in-N fprop pack (vs_conv3x3x3_tc_kdn) or NULL      */
+    long long kdn_elems;
+    int kind;             /* 0: 3x3x3 layer (fields above).  1: 2x2x2 stride-2 layer: w = wt[A][B][8] with A = cout,
+                           * B = cin; tcf = gather pack, tcd = scatter pack (vs_k2s2_tc_pack_bytes()/2 elements)   */
+    int reserved;
 } vs_pack_job;
 int vs_pack_conv3_batched(const void* jobs_dev, int njobs, void* stream);
 /* One padded pack: master weight [cout][cin][27], pack built for cin_pad >= cin / cout_pad >= cout channels (zeros);
@@ -128,6 +133,16 @@ int vs_k2s2_gather(int dtype, const void* fine, const float* wt, const float* bi
                    int n, int dc, int hc, int wc, int a, int b, void* stream);
 int vs_k2s2_scatter(int dtype, const void* coarse, const float* wt, const float* bias, void* fine,
                     int n, int dc, int hc, int wc, int a, int b, void* stream);
+/* The same two contractions on the tensor cores (tcgen05.mma / TMEM / TMA; bf16 NDHWC in and out; A, B in {8, 16k},
+ * <= 256): GEMM over the coarse voxels, M tile = 16 x 8 voxels of a coarse d-plane; gather K = (kd,kh,kw,b) read
+ * through a [2B][Wc][kh][Hc][n*Df] view of the fine tensor, scatter N = (kd,kh,kw,b) stored as contiguous (kw,b)
+ * runs.  wpack: bf16 UMMA B-operand pack of wt (scatter = 0 / 1), vs_k2s2_tc_pack_bytes() bytes; bias may be NULL. */
+size_t vs_k2s2_tc_pack_bytes(int a, int b, int scatter);
+int vs_pack_k2s2_weight_tc(const float* wt, void* out, int a, int b, int scatter, void* stream);
+int vs_k2s2_gather_tc(const void* fine, const void* wpack, const float* bias, void* coarse,
+                      int n, int dc, int hc, int wc, int a, int b, void* stream);
+int vs_k2s2_scatter_tc(const void* coarse, const void* wpack, const float* bias, void* fine,
+                       int n, int dc, int hc, int wc, int a, int b, void* stream);
 /* dwt[A][B][8] (+)= sum_o coarse[o,a]*fine[2o+k,b]; optional bias grads over either side. */
 int vs_k2s2_wgrad(int dtype, const void* coarse, const void* fine, float* dwt,
                   float* dbias_coarse, float* dbias_fine, int accumulate,

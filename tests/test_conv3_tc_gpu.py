@@ -171,8 +171,6 @@ KDN_CASES = [(1, 4, 16, 8, 8, 8), (2, 5, 17, 9, 8, 8), (1, 8, 18, 10, 16, 8), (1
              (1, 12, 24, 24, 32, 16)]
 
 
-@pytest.mark.skipif(__import__("os").environ.get("VAESEG_TEST_KDN", "0") != "1",
-                    reason="experimental kd-in-N kernel (DESIGN.md section 10): opt-in until its first GPU run, VAESEG_TEST_KDN=1")
 @pytest.mark.parametrize("case", KDN_CASES)
 def test_tc_kdn_fprop_and_dgrad(case):
     """Experimental kd-in-N convolution against torch (same bf16 operands) and against the production kernel."""
@@ -207,3 +205,45 @@ def test_tc_kdn_fprop_and_dgrad(case):
         dx, _ = ops.conv3_tc_kdn(to_ndhwc(gy), wkd, dims, cout, cin, want_stats=False)
         torch.cuda.synchronize()
         assert (from_ndhwc(dx) - dx_ref).abs().max().item() < 1e-2 * dx_ref.abs().max().item()
+
+
+K2_TC_CASES = [(2, 3, 4, 5, 8), (1, 2, 17, 9, 16), (1, 1, 2, 2, 64), (1, 3, 3, 3, 32), (2, 2, 6, 6, 128), (1, 2, 3, 3, 256),
+               (1, 5, 20, 11, 8), (1, 4, 33, 8, 16)]
+
+
+@pytest.mark.parametrize("case", K2_TC_CASES)
+def test_k2s2_tensor_core_gather_and_scatter(case):
+    """Conv3d(C,C,2,stride 2) / ConvTranspose3d(C,C,2,stride 2) forward and input gradient through the tcgen05 kernels
+    (csrc/k2s2_tc.cu) against torch fp32 on the SAME bf16-rounded operands: only accumulation order and the bf16
+    rounding of the output differ.  Ragged tiles (H, W not multiples of 16 / 8) exercise the TMA zero fill."""
+    n, dc, hc, wc, c = case
+    torch.manual_seed(sum(case) + 3)
+    wt = (torch.randn(c, c, 2, 2, 2) * (0.5 / c ** 0.5))
+    wq = wt.bfloat16().float()
+    b = torch.randn(c)
+    wd = wt.to(DEV)
+    pg = ops.pack_k2s2_weight_tc(wd, c, c, scatter=False)
+    ps = ops.pack_k2s2_weight_tc(wd, c, c, scatter=True)
+    assert pg is not None and ps is not None
+    dims = (n, dc, hc, wc)
+
+    def close(got, ref, what):
+        err = (got - ref).abs().max().item()
+        assert err < 1e-2 * ref.abs().max().item(), "%s: max abs err %.3e (scale %.3e)" % (what, err, ref.abs().max().item())
+
+    fine = torch.randn(n, c, 2 * dc, 2 * hc, 2 * wc).bfloat16().float()
+    coarse = torch.randn(n, c, dc, hc, wc).bfloat16().float()
+    # Conv3d fprop = gather (+bias); its dgrad = scatter (no bias)
+    y = ops.k2s2_gather(to_ndhwc(fine), wd, b.to(DEV), dims, c, c, wtc=pg)
+    close(from_ndhwc(y), F.conv3d(fine, wq, b, stride=2), "conv k2s2 fprop")
+    dx = ops.k2s2_scatter(to_ndhwc(coarse), wd, None, dims, c, c, wtc=ps)
+    close(from_ndhwc(dx), F.conv_transpose3d(coarse, wq, None, stride=2), "conv k2s2 dgrad")
+    # ConvTranspose3d fprop = scatter (+bias); its dgrad = gather (no bias).  Weight layout [Cin = A][Cout = B][8].
+    y2 = ops.k2s2_scatter(to_ndhwc(coarse), wd, b.to(DEV), dims, c, c, wtc=ps)
+    close(from_ndhwc(y2), F.conv_transpose3d(coarse, wq, b, stride=2), "convT fprop")
+    dx2 = ops.k2s2_gather(to_ndhwc(fine), wd, None, dims, c, c, wtc=pg)
+    close(from_ndhwc(dx2), F.conv3d(fine, wq, None, stride=2), "convT dgrad")
+    # and against the CUDA-core kernels on the same operands
+    y3 = ops.k2s2_gather(to_ndhwc(fine), wq.to(DEV), b.to(DEV), dims, c, c)
+    assert (y.float() - y3.float()).abs().max().item() < 1e-2 * y3.float().abs().max().item()
+    torch.cuda.synchronize()

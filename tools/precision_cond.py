@@ -39,6 +39,10 @@ def grad_report(tag, got, want, truth=None):
         line += "  | fp32 oracle vs fp64: whole %.3e worst %.3e" % (
             rel(cat(want), cat(truth)), max(rel(want[k], truth[k]) for k in keys))
     print(line, flush=True)
+    bad = sorted((p for p in per if p[0] > 3e-2), reverse=True)
+    if bad:
+        print("     > 3e-2: " + ", ".join("%s %.3f (|g| %.2e of %.2e)" % (k, e, want[k].double().norm().item(),
+                                                                       cat(want).norm().item()) for e, k in bad), flush=True)
 
 
 def main():
@@ -53,9 +57,9 @@ def main():
     ap.add_argument("--precisions", default="bf16,fp32")
     args = ap.parse_args()
     seg_sd, seg_losses = C.train_seg(args.seg_steps, patch=32, lr=args.lr)
-    print("conditioned Seg: loss %.3f -> %.3f" % (seg_losses[0], seg_losses[-1]))
+    print("conditioned Seg: loss %s" % ([round(l, 3) for l in seg_losses[:1] + seg_losses[-1:]],))
     vae_sd, vae_losses = C.train_vae(args.vae_steps, patch=args.patch, lr=args.lr)
-    print("conditioned VAE: loss %.3f -> %.3f" % (vae_losses[0], vae_losses[-1]))
+    print("conditioned VAE: loss %s" % ([round(l, 3) for l in vae_losses[:1] + vae_losses[-1:]],))
     if args.prepare:
         return
     from vae_segmentation_b200 import evaluation as ev

@@ -36,6 +36,10 @@ _SIGNATURES = {
     "vs_conv3x3x3_wgrad": [_I, _I, _P, _P, _P, _P, _P, _Z, _I, _I, _I, _I, _I, _I, _I, _P],
     "vs_k2s2_gather": [_I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "vs_k2s2_scatter": [_I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "vs_k2s2_tc_pack_bytes": [_I, _I, _I],
+    "vs_pack_k2s2_weight_tc": [_P, _P, _I, _I, _I, _P],
+    "vs_k2s2_gather_tc": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "vs_k2s2_scatter_tc": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "vs_k2s2_wgrad": [_I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "vs_inorm_relu_apply": [_I, _P, _P, _P, _P, _I, _L, _I, _P],
     "vs_inorm_relu_bwd_reduce": [_I, _P, _P, _P, _P, _I, _L, _I, _I, _P],
@@ -64,7 +68,7 @@ _SIGNATURES = {
     "vs_joint_target_finish": [_P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _I, _I, _I, _P, _P, _P],
 }
 _RESTYPES = {"vs_last_error_string": c_char_p, "vs_conv3_wgrad_workspace_bytes": c_size_t,
-             "vs_conv3_tc_pack_bytes": c_size_t, "vs_conv3_tc_kdn_pack_bytes": c_size_t}
+             "vs_conv3_tc_pack_bytes": c_size_t, "vs_conv3_tc_kdn_pack_bytes": c_size_t, "vs_k2s2_tc_pack_bytes": c_size_t}
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

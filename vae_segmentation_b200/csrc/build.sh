@@ -5,12 +5,12 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Xcompiler -fvisibility=default"
 SRCS="cabi.cu conv3_direct.cu k2s2.cu norm_act.cu losses.cu fc.cu optim.cu"
-if [ -f conv3_tc.cu ]; then SRCS="$SRCS conv3_tc.cu conv3_wgrad_tc.cu conv3_tc_kdn.cu"; FLAGS="$FLAGS -DVS_WITH_TCGEN05"; fi
+if [ -f conv3_tc.cu ]; then SRCS="$SRCS conv3_tc.cu conv3_wgrad_tc.cu conv3_tc_kdn.cu k2s2_tc.cu"; FLAGS="$FLAGS -DVS_WITH_TCGEN05"; fi
 mkdir -p build
 pids=()
 for s in $SRCS; do
   o=build/${s%.cu}.o
-  if [ ! -f "$o" ] || [ "$s" -nt "$o" ] || [ vs_common.cuh -nt "$o" ] || [ tc_ptx.cuh -nt "$o" ] || [ ../../include/vaeseg_b200.h -nt "$o" ] || [ build.sh -nt "$o" ]; then
+  if [ ! -f "$o" ] || [ "$s" -nt "$o" ] || [ vs_common.cuh -nt "$o" ] || [ tc_ptx.cuh -nt "$o" ] || [ tc_pack.cuh -nt "$o" ] || [ ../../include/vaeseg_b200.h -nt "$o" ] || [ build.sh -nt "$o" ]; then
     $NVCC $FLAGS ${VS_PTXAS_V:+-Xptxas -v} -c "$s" -o "$o" &
     pids+=($!)
   fi

@@ -26,6 +26,7 @@
 // Four warps issuing to four independent accumulators hide that issue latency; all role branches are
 // warp-uniform (shfl-derived warp index, elect.sync inside the asm) so no divergent-region waterfall is emitted.
 #include "tc_ptx.cuh"
+#include "tc_pack.cuh"
 
 namespace {
 
@@ -519,54 +520,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
 //   cin8   : [chunk][1][pair 14][kc 2][NC/8][8 rows][8 ch]  (kc0 = tap 2*pair, kc1 = tap 2*pair+1 in (kd,kh,kw) order; the 28th is zero)
 // dgrad = same contraction with (ci,co) swapped and taps flipped.
 // ---------------------------------------------------------------------------------------------
-// One element of the bf16 UMMA B-operand pack.  cout_real < cout_l zero-pads the output channels (the head's
-// 2 -> 8 channel dgrad pack).
-__device__ __forceinline__ float pack_tc_elem(const float* __restrict__ w, long long i, int cin_l, int cout_l, int cout_real,
-                                              int dgrad, int nc, int cin8, int cin_real = -1) {
-    if (cin_real < 0) cin_real = cin_l;         // cin_real < cin_l zero-pads the input channels (2-channel in-block dgrad)
-    // GEMM-side channel counts
-    const int gin = dgrad ? cout_l : cin_l, gout = dgrad ? cin_l : cout_l;
-    const int kslices = cin8 ? 1 : gin / 16;
-    const int nmma = cin8 ? 14 : 27;
-    long long r = i;
-    const int ch8 = (int)(r % 8); r /= 8;
-    const int r8 = (int)(r % 8); r /= 8;
-    const int ng = (int)(r % (nc / 8)); r /= (nc / 8);
-    const int kc = (int)(r % 2); r /= 2;
-    const int m = (int)(r % nmma); r /= nmma;
-    const int ks = (int)(r % kslices); r /= kslices;
-    const int chunk = (int)r;
-    const int go = chunk * nc + ng * 8 + r8;               // GEMM output channel
-    int gi, tap;
-    if (cin8) {
-        gi = ch8;
-        tap = 2 * m + kc;                                      // taps paired in (kd,kh,kw) order; the 28th is zero
-        if (tap > 26) tap = -1;
-    } else {
-        gi = ks * 16 + kc * 8 + ch8;
-        tap = m;
-    }
-    float v = 0.f;
-    if (go < gout && gi < gin && tap >= 0) {
-        if (dgrad) { if (gi < cout_real && go < cin_real) v = w[((long long)gi * cin_real + go) * 27 + (26 - tap)]; }   // w[co=gi][ci=go][flipped tap]
-        else if (go < cout_real && gi < cin_real) v = w[((long long)go * cin_real + gi) * 27 + tap];
-    }
-    return v;
-}
-
 __global__ void pack_tc_kernel(const float* __restrict__ w, bf16* __restrict__ out, int cin_l, int cout_l, int dgrad,
                                int nc, int cin8, long long total) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
         out[i] = __float2bfloat16_rn(pack_tc_elem(w, i, cin_l, cout_l, cout_l, dgrad, nc, cin8));
 }
 
-// Output channels per CTA (MMA N).  An MMA costs ~(128 + N)/4 cycles (operand delivery from shared memory), so a
-// small N wastes tensor-pipe time in aggregate but shortens each CTA: layers with >= 64 output channels only occur at
-// the deep levels (<= 12^3), whose grids leave most SMs idle, so they are split into more, shorter CTAs.
-#ifndef VS_NC_WIDE
-#define VS_NC_WIDE 16
-#endif
-__host__ __device__ constexpr int nc_for_dev(int gout) { return gout >= 64 ? VS_NC_WIDE : (gout >= 32 ? 32 : 16); }
 int nc_for(int gout) { return nc_for_dev(gout); }
 
 template <int NC, bool CIN8, int NSTAGE, bool H8 = false>
@@ -640,6 +599,18 @@ __global__ void __launch_bounds__(256) pack_batched_kernel(const vs_pack_job* __
     const int cin = j.cin, cout = j.cout, cpad = j.cout_pad;
     const int cinpad = j.cin_pad > cin ? j.cin_pad : cin;
     const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j.kind == 1) {
+        // 2x2x2 stride-2 layer: wt[A = cout][B = cin][8] -> gather / scatter packs (k2s2_tc.cu)
+        if (j.tcf != nullptr) {
+            bf16* o = (bf16*)j.tcf;
+            for (long long i = t0; i < j.tcf_elems; i += stride) o[i] = __float2bfloat16_rn(pack_k2s2_elem(w, i, cout, cin, 0));
+        }
+        if (j.tcd != nullptr) {
+            bf16* o = (bf16*)j.tcd;
+            for (long long i = t0; i < j.tcd_elems; i += stride) o[i] = __float2bfloat16_rn(pack_k2s2_elem(w, i, cout, cin, 1));
+        }
+        return;
+    }
     if (j.wf != nullptr || j.wd != nullptr) {
         float* wf = (float*)j.wf; float* wd = (float*)j.wd;
         const long long total = (long long)cout * cin * 27;
@@ -661,6 +632,10 @@ __global__ void __launch_bounds__(256) pack_batched_kernel(const vs_pack_job* __
         const int nc = nc_for_dev(cinpad);
         for (long long i = t0; i < j.tcd_elems; i += stride)
             o[i] = __float2bfloat16_rn(pack_tc_elem(w, i, cinpad, cpad, cout, 1, nc, cpad == 8, cin));
+    }
+    if (j.kdn != nullptr) {
+        bf16* o = (bf16*)j.kdn;
+        for (long long i = t0; i < j.kdn_elems; i += stride) o[i] = __float2bfloat16_rn(pack_kdn_elem(w, i, cin, cout, 0));
     }
 }
 

@@ -23,6 +23,7 @@
 // v1 feature set: bf16 NDHWC output, optional shift + fp64 InstanceNorm statistics (fprop) or plain (dgrad); tiles of
 // 4 d-planes only (volumes with D >= 4); no fused norm-backward reduction, no planar (head) epilogue.
 #include "tc_ptx.cuh"
+#include "tc_pack.cuh"
 
 namespace {
 
@@ -338,32 +339,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kdn_kernel(const __grid_
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
-}
-
-// One element of the kd-in-N pack: [ks][m][kc 2][N/8][8 rows][8 ch], N = 4 * gout.
-//   row group ng -> (kd' = ng / (gout/8), output channel group); kd' = 3 is the zero block
-//   m  -> in-plane tap(s): Cin = 8: taps 2m (kc 0) and 2m+1 (kc 1) of the 9 (kh,kw) taps, the 10th is zero;
-//                          else   : tap m = kh*3 + kw, kc selects channels 0-7 / 8-15 of the slice
-// dgrad = same contraction with (ci,co) swapped and taps flipped.
-__device__ __forceinline__ float pack_kdn_elem(const float* __restrict__ w, long long i, int cin_l, int cout_l, int dgrad) {
-    const int gin = dgrad ? cout_l : cin_l, gout = dgrad ? cin_l : cout_l;
-    const bool cin8 = gin == 8;
-    const int nmp = cin8 ? 5 : 9, ngroups = 4 * gout / 8;
-    long long r = i;
-    const int ch8 = (int)(r % 8); r /= 8;
-    const int r8 = (int)(r % 8); r /= 8;
-    const int ng = (int)(r % ngroups); r /= ngroups;
-    const int kc = (int)(r % 2); r /= 2;
-    const int m = (int)(r % nmp); r /= nmp;
-    const int ks = (int)r;
-    const int kdp = ng / (gout / 8), go = (ng % (gout / 8)) * 8 + r8;
-    int gi, t;
-    if (cin8) { gi = ch8; t = 2 * m + kc; if (t > 8) t = -1; }
-    else { gi = ks * 16 + kc * 8 + ch8; t = m; }
-    if (kdp > 2 || t < 0 || gi >= gin) return 0.f;
-    const int tap = kdp * 9 + t;                              // (kd', kh, kw) in the GEMM's (input-side) orientation
-    if (dgrad) return w[((long long)gi * cin_l + go) * 27 + (26 - tap)];      // w[co = gi][ci = go][flipped tap]
-    return w[((long long)go * cin_l + gi) * 27 + tap];
 }
 
 __global__ void pack_kdn_kernel(const float* __restrict__ w, bf16* __restrict__ out, int cin, int cout, int dgrad, long long total) {

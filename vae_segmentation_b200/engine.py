@@ -29,9 +29,13 @@ USE_TENSOR_CORES = os.environ.get("VAESEG_NO_TC", "0") != "1"
 # VAESEG_NO_FUSE_REDUCE=1 keeps the InstanceNorm-backward reduction a separate pass (A/B measurements, parity tests)
 FUSE_BWD_REDUCE = os.environ.get("VAESEG_NO_FUSE_REDUCE", "0") != "1"
 HEAD_DIRECT = os.environ.get("VAESEG_HEAD_DIRECT", "0") == "1"
-# VAESEG_KDN=1 routes the forward 3x3x3 convolutions with 8 / 16 output channels at >= 48^3 through the EXPERIMENTAL
-# kd-in-N kernel (csrc/conv3_tc_kdn.cu).  Off by default: its first GPU run is still pending.
-USE_KDN = os.environ.get("VAESEG_KDN", "0") == "1"
+# The forward 3x3x3 convolutions with 8 / 16 output channels at >= 48^3 run through the kd-in-N kernel
+# (csrc/conv3_tc_kdn.cu: the three kd taps folded into the MMA's N, halving the A-operand shared-memory traffic).
+# Measured on B200, joint step 2 x 96^3: 345.3 vs 327.2 vol/s.  VAESEG_KDN=0 falls back to the tap-per-MMA kernel.
+USE_KDN = os.environ.get("VAESEG_KDN", "1") == "1"
+# 2x2x2 stride-2 convolutions / transposed convolutions (forward and input gradient) on the tensor cores
+# (csrc/k2s2_tc.cu); VAESEG_K2_TC=0 keeps the CUDA-core kernels of csrc/k2s2.cu (A/B measurements).
+USE_K2_TC = os.environ.get("VAESEG_K2_TC", "1") == "1"
 
 # tools/precision_probe*.py only: names of tensor classes to round through bf16 while running the fp32
 # check mode ("y", "a", "g", "dy", "k2"), to attribute bf16-mode error to a storage point.  Empty in production.
@@ -57,7 +61,8 @@ class _PackJob(ctypes.Structure):
     # mirrors vs_pack_job (include/vaeseg_b200.h)
     _fields_ = [("w", ctypes.c_void_p), ("wf", ctypes.c_void_p), ("wd", ctypes.c_void_p), ("tcf", ctypes.c_void_p),
                 ("tcd", ctypes.c_void_p), ("tcf_elems", ctypes.c_longlong), ("tcd_elems", ctypes.c_longlong),
-                ("cin", ctypes.c_int), ("cout", ctypes.c_int), ("cout_pad", ctypes.c_int), ("cin_pad", ctypes.c_int)]
+                ("cin", ctypes.c_int), ("cout", ctypes.c_int), ("cout_pad", ctypes.c_int), ("cin_pad", ctypes.c_int),
+                ("kdn", ctypes.c_void_p), ("kdn_elems", ctypes.c_longlong), ("kind", ctypes.c_int), ("reserved", ctypes.c_int)]
 
 
 class PackCache(object):
@@ -87,7 +92,7 @@ class PackCache(object):
         fresh = ent is None or ent["shape"] != tuple(w.shape) or (tc and not ent["tc"])
         if fresh:
             ent = {"w": w, "shape": tuple(w.shape), "tc": False, "key": None, "wf": None, "wd": None, "tcf": None,
-                   "tcd": None, "kind": kind}
+                   "tcd": None, "kdn": None, "kind": kind}
             self._store[(kind, w.data_ptr())] = ent
             self._jobs = None
         return ent, key
@@ -152,17 +157,37 @@ class PackCache(object):
         return ent["tcd"]
 
     def conv3_kdn(self, w):
-        """Experimental kd-in-N pack of a weight (lazy: re-packed on next use after the weights changed), or None."""
+        """kd-in-N fprop pack of a 3x3x3 weight (re-packed in place, part of the batched re-pack), or None."""
         ent, key = self._entry("kdn", w, True)
         if ent["key"] != key:
-            ent["tcf"] = ops.pack_conv3_weight_tc_kdn(w.detach(), dgrad=False)
+            had = ent["kdn"] is not None
+            ent["kdn"] = ops.pack_conv3_weight_tc_kdn(w.detach(), dgrad=False, out=ent["kdn"])
+            if not had:
+                self._jobs = None
             ent["tc"] = True
             ent["key"] = key
-        return ent["tcf"]
+        return ent["kdn"]
+
+    def k2s2(self, w, a, b):
+        """(gather pack, scatter pack) of a 2x2x2 stride-2 weight viewed as wt[A][B][8] for the tcgen05 kernels, or
+        (None, None) when the tensor-core path does not take the channel counts."""
+        if not USE_TENSOR_CORES or not USE_K2_TC:
+            return None, None
+        ent, key = self._entry("k2s2", w, True)
+        if ent["key"] != key:
+            had = ent["tcf"] is not None
+            wdet = w.detach()
+            ent["tcf"] = ops.pack_k2s2_weight_tc(wdet, a, b, scatter=False, out=ent["tcf"])
+            ent["tcd"] = ops.pack_k2s2_weight_tc(wdet, a, b, scatter=True, out=ent["tcd"])
+            if not had:
+                self._jobs = None
+            ent["tc"] = True
+            ent["key"] = key
+        return ent["tcf"], ent["tcd"]
 
     def repack_all(self):
         """Re-packs every known entry in place with one launch; entries become current for the present weights."""
-        ents = [e for e in self._store.values() if e["key"] is not None and e["kind"] != "kdn"]
+        ents = [e for e in self._store.values() if e["key"] is not None]
         if not ents:
             self.invalidate()
             return
@@ -180,6 +205,9 @@ class PackCache(object):
                 j.tcd = e["tcd"].data_ptr() if e["tcd"] is not None else None
                 j.tcf_elems = e["tcf"].numel() if e["tcf"] is not None else 0
                 j.tcd_elems = e["tcd"].numel() if e["tcd"] is not None else 0
+                j.kdn = e["kdn"].data_ptr() if e["kdn"] is not None else None
+                j.kdn_elems = e["kdn"].numel() if e["kdn"] is not None else 0
+                j.kind = 1 if e["kind"] == "k2s2" else 0         # k2s2: w = wt[A = shape[0]][B = shape[1]][8]
             host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
             self._jobs = (host.to(ents[0]["w"].device), len(ents), ents)
         ops.pack_conv3_batched(self._jobs[0], self._jobs[1])
@@ -308,14 +336,16 @@ def program_forward(layers, tensors, x, dims, dtype, cache, record=True):
             cur = a
         elif L.kind == K2DOWN:
             d, h, w = d // 2, h // 2, w // 2
-            out = _sim(ops.k2s2_gather(cur, tensors[L.wi].detach(), tensors[L.bi].detach(), (n, d, h, w), L.cout, L.cin), "k2")
+            k2g, k2s = cache.k2s2(tensors[L.wi], L.cout, L.cin) if dtype == torch.bfloat16 else (None, None)
+            out = _sim(ops.k2s2_gather(cur, tensors[L.wi].detach(), tensors[L.bi].detach(), (n, d, h, w), L.cout, L.cin, wtc=k2g), "k2")
             if record:
-                tape.append((L, cur, None, None, (n, d, h, w), None))
+                tape.append((L, cur, None, None, (n, d, h, w), (k2g, k2s)))
             cur = out
         elif L.kind == K2UP:
-            out = _sim(ops.k2s2_scatter(cur, tensors[L.wi].detach(), tensors[L.bi].detach(), (n, d, h, w), L.cin, L.cout), "k2")
+            k2g, k2s = cache.k2s2(tensors[L.wi], L.cin, L.cout) if dtype == torch.bfloat16 else (None, None)
+            out = _sim(ops.k2s2_scatter(cur, tensors[L.wi].detach(), tensors[L.bi].detach(), (n, d, h, w), L.cin, L.cout, wtc=k2s), "k2")
             if record:
-                tape.append((L, cur, None, None, (n, d, h, w), None))
+                tape.append((L, cur, None, None, (n, d, h, w), (k2g, k2s)))
             d, h, w = d * 2, h * 2, w * 2
             cur = out
         elif L.kind == HEAD:
@@ -411,7 +441,7 @@ def program_backward(tape, g, dtype, need, grads, param_refs, need_input_grad):
                              acc, g, x_in)
                 _hand_back(grads, need, L.wi, L.bi, tw, tb, acc)
             _grad_ready(param_refs[L.wi], param_refs[L.bi])
-            g = _sim(ops.k2s2_scatter(g, wt, None, dims, L.cout, L.cin), "g") if want_dx else None
+            g = _sim(ops.k2s2_scatter(g, wt, None, dims, L.cout, L.cin, wtc=wd[1] if wd else None), "g") if want_dx else None
         elif L.kind == K2UP:
             # dims are the coarse (input) dims; g is the fine gradient
             if need[L.wi] or need[L.bi]:
@@ -420,7 +450,7 @@ def program_backward(tape, g, dtype, need, grads, param_refs, need_input_grad):
                              acc, g, x_in)
                 _hand_back(grads, need, L.wi, L.bi, tw, tb, acc)
             _grad_ready(param_refs[L.wi], param_refs[L.bi])
-            g = _sim(ops.k2s2_gather(g, wt, None, dims, L.cin, L.cout), "g") if want_dx else None
+            g = _sim(ops.k2s2_gather(g, wt, None, dims, L.cin, L.cout, wtc=wd[0] if wd else None), "g") if want_dx else None
         elif L.kind == HEAD:
             probs = y
             if wd[1] is not None:

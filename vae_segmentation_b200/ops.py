@@ -190,18 +190,37 @@ def conv3_wgrad(x, dy, dims, cin, cout, dw=None, db=None, in_planar=False, accum
 
 
 # ---- k2s2 ------------------------------------------------------------------------------
-def k2s2_gather(fine, wt, bias, cdims, a, b):
-    """fine [N,2dc,2hc,2wc,B] -> coarse [N,dc,hc,wc,A]; cdims = (N,dc,hc,wc)."""
+def pack_k2s2_weight_tc(wt, a, b, scatter, out=None):
+    """bf16 tensor-core (UMMA B operand) pack of a k2s2 weight viewed as wt[A][B][8], or None when the tcgen05 path
+    does not take the channel counts.  `out` re-packs in place."""
+    nbytes = _cabi.lib().vs_k2s2_tc_pack_bytes(a, b, int(scatter))
+    if nbytes == 0:
+        return None
+    if out is None:
+        out = torch.empty(nbytes // 2, device=wt.device, dtype=torch.bfloat16)
+    _cabi.call("vs_pack_k2s2_weight_tc", _p(_f32(wt, "wt")), _p(out), a, b, int(scatter), _stream())
+    return out
+
+
+def k2s2_gather(fine, wt, bias, cdims, a, b, wtc=None):
+    """fine [N,2dc,2hc,2wc,B] -> coarse [N,dc,hc,wc,A]; cdims = (N,dc,hc,wc).  wtc: tensor-core gather pack (bf16
+    activations only) -> tcgen05 kernel, else the CUDA-core kernel on the fp32 weight."""
     n, dc, hc, wc = cdims
     coarse = torch.empty(n, dc, hc, wc, a, device=fine.device, dtype=fine.dtype)
+    if wtc is not None and fine.dtype == torch.bfloat16:
+        _cabi.call("vs_k2s2_gather_tc", _p(fine), _p(wtc), _p(_f32(bias, "bias")), _p(coarse), n, dc, hc, wc, a, b, _stream())
+        return coarse
     _cabi.call("vs_k2s2_gather", _dt(fine), _p(fine), _p(_f32(wt, "wt")), _p(_f32(bias, "bias")), _p(coarse),
                n, dc, hc, wc, a, b, _stream())
     return coarse
 
 
-def k2s2_scatter(coarse, wt, bias, cdims, a, b):
+def k2s2_scatter(coarse, wt, bias, cdims, a, b, wtc=None):
     n, dc, hc, wc = cdims
     fine = torch.empty(n, 2 * dc, 2 * hc, 2 * wc, b, device=coarse.device, dtype=coarse.dtype)
+    if wtc is not None and coarse.dtype == torch.bfloat16:
+        _cabi.call("vs_k2s2_scatter_tc", _p(coarse), _p(wtc), _p(_f32(bias, "bias")), _p(fine), n, dc, hc, wc, a, b, _stream())
+        return fine
     _cabi.call("vs_k2s2_scatter", _dt(coarse), _p(coarse), _p(_f32(wt, "wt")), _p(_f32(bias, "bias")), _p(fine),
                n, dc, hc, wc, a, b, _stream())
     return fine
@@ -411,13 +430,14 @@ def clip_center(x, lo, hi, sub, div):
     return out
 
 
-# ---- experimental: kd-in-N tensor-core convolution (not used by the default path) ----------
-def pack_conv3_weight_tc_kdn(w, dgrad=False):
+# ---- kd-in-N tensor-core convolution (full-resolution forward layers, csrc/conv3_tc_kdn.cu) ----------------------
+def pack_conv3_weight_tc_kdn(w, dgrad=False, out=None):
     cout, cin = w.shape[0], w.shape[1]
     nbytes = _cabi.lib().vs_conv3_tc_kdn_pack_bytes(cin, cout, int(dgrad))
     if nbytes == 0:
         return None
-    out = torch.empty(nbytes // 2, device=w.device, dtype=torch.bfloat16)
+    if out is None:
+        out = torch.empty(nbytes // 2, device=w.device, dtype=torch.bfloat16)
     _cabi.call("vs_pack_conv3_weight_tc_kdn", _p(_f32(w, "weight")), _p(out), cin, cout, int(dgrad), _stream())
     return out
 
