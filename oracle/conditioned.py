@@ -10,8 +10,11 @@ reference, written by oracle/make_golden.py) on a synthetic task where the label
 
     image = clamp(0.5 * randn + label - 0.25, -1, 1)        label = pancreas-like ellipsoid blob (synthetic.synth_label)
 
-  seg:  main_source.py:415-437,660-661  (1 - Dice_fg, SGD lr 1e-2 momentum .9)
+  seg:  main_source.py:415-437,660-661  (1 - Dice_fg, SGD momentum .9)
   vae:  main_source.py:389-406,660-661  (1 - Dice_fg + 2e-5 KL, if_random, scale .35)
+
+The parity tests use lr 0.1 (the reference's default 1e-2 needs hundreds of steps to leave the random-init regime):
+60 steps bring the Seg Dice loss from 0.97 to ~0.18 and the logit margin from N(.46,.51) to |margin| ~ 6.
 
 Everything is drawn from the torch CPU generator, so the same seeds give the same tensors on the authoring container
 and on the GPU box; results are cached per (kind, arguments) for the life of the process.
@@ -25,6 +28,7 @@ from oracle import ref_torch as R
 from vae_segmentation_b200.synthetic import synth_image, synth_label
 
 _CACHE = {}
+EPS = 0.000001          # utils/evaluation.py:48 avg_dsc (the importable twin of main_source.py's eps=1e-4 copy)
 # optional on-disk cache (git-ignored; travels to the GPU box with the gpurun snapshot so the box does not re-train)
 _DISK = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_cache")
 
@@ -57,7 +61,7 @@ def blob_batch(batch, patch):
 def train_seg(steps, patch=32, batch=2, seed=7, lr=1e-2, momentum=0.9, step_fn=None):
     """K reference Seg train steps from default init.  Returns (state_dict, losses list).  `step_fn(sd, img, label)
     -> (loss, grads)` lets oracle/make_golden.py run the same recipe through the real reference modules."""
-    key = ("seg", steps, patch, batch, seed, lr, momentum, step_fn is None)
+    key = ("seg", steps, patch, batch, seed, lr, momentum, EPS, step_fn is None)
     if key in _CACHE:
         return _CACHE[key]
     hit = _disk_get(key) if step_fn is None else None
@@ -70,7 +74,7 @@ def train_seg(steps, patch=32, batch=2, seed=7, lr=1e-2, momentum=0.9, step_fn=N
     for _ in range(steps):
         img, label = blob_batch(batch, patch)
         if step_fn is None:
-            loss, grads, _ = R.seg_train_step(sd, img, label, eps=0.0001)
+            loss, grads, _ = R.seg_train_step(sd, img, label, eps=EPS)
         else:
             loss, grads = step_fn(sd, img, label)
         sd, bufs = R.sgd_step(sd, grads, bufs, lr=lr, momentum=momentum)
@@ -84,7 +88,7 @@ def train_seg(steps, patch=32, batch=2, seed=7, lr=1e-2, momentum=0.9, step_fn=N
 
 def train_vae(steps, patch=64, batch=2, seed=8, lr=1e-2, momentum=0.9, scale=0.35, step_fn=None):
     """K reference VAE train steps (main_source.py:389-406) from default init on blob masks."""
-    key = ("vae", steps, patch, batch, seed, lr, momentum, scale, step_fn is None)
+    key = ("vae", steps, patch, batch, seed, lr, momentum, scale, EPS, step_fn is None)
     if key in _CACHE:
         return _CACHE[key]
     hit = _disk_get(key) if step_fn is None else None
@@ -98,7 +102,7 @@ def train_vae(steps, patch=64, batch=2, seed=8, lr=1e-2, momentum=0.9, scale=0.3
         label = synth_label(batch, patch)
         z = torch.randn(batch, 128)
         if step_fn is None:
-            loss, _, _, grads, _ = R.vae_train_step(sd, label, scale=scale, z=z, eps=0.0001)
+            loss, _, _, grads, _ = R.vae_train_step(sd, label, scale=scale, z=z, eps=EPS)
         else:
             loss, grads = step_fn(sd, label, z)
         sd, bufs = R.sgd_step(sd, grads, bufs, lr=lr, momentum=momentum)

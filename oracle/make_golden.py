@@ -21,6 +21,7 @@ SEG_CASE = dict(seed=100, batch=2, patch=32)
 VAE_CASE = dict(seed=101, batch=1, patch=128)
 JOINT_CASE = dict(seed=102, batch=1, patch=128)
 LOSS_CASE = dict(seed=103)
+COND_CASE = dict(steps=4, patch_seg=32, patch_vae=64, lr=0.1)     # pinned prefix of the conditioned recipes
 
 
 def grad_summary(grads):
@@ -124,6 +125,50 @@ def main():
                         std=b["std"].detach().numpy(),
                         grad_summary=grad_summary(grads), grad_names=np.array(list(grads.keys())))
     print("joint_p128 final", float(final), "recon", float(recon_loss))
+
+    # ---- conditioned fixtures (oracle/conditioned.py): the same K-step recipes through the REAL reference modules and
+    #      torch.optim.SGD; tests/test_oracle.py checks the oracle-trained weights against these checksums ----
+    from oracle import conditioned as C
+
+    def real_seg_step(sd, img, label):
+        with torch.random.fork_rng():                 # module construction draws from the generator the recipe's data uses
+            seg = jm.Segmentation(1, 2, norm_type=1)
+        seg.load_state_dict(sd, strict=True)
+        b = seg({"img": img}, "img", "pred")
+        b["onehot"] = R.one_hot(label)
+        loss = 1 - ev.avg_dsc(b, source_key="pred", target_key="onehot", botindex=1, topindex=2)
+        loss.backward()
+        return loss.detach(), OrderedDict((k, p.grad) for k, p in seg.named_parameters())
+
+    def real_vae_step(sd, label, z):
+        flat = sd["fc_mean.weight"].shape[1]
+        with torch.random.fork_rng():
+            vae = jm.VAE(2, 2, norm_type=1, dim=128)
+            # the reference hard-codes the 128^3 flat dimension: re-size its three Linear layers for the fixture's patch
+            vae.fc_mean = torch.nn.Linear(flat, 128)
+            vae.fc_std = torch.nn.Linear(flat, 128)
+            vae.fc2 = torch.nn.Linear(128, flat)
+        vae.load_state_dict(sd, strict=True)
+        oh = R.one_hot(label)
+        side = round((flat // 256) ** (1.0 / 3.0))
+        # VAE.forward with the generalised view (joint_model.py:233-266 verbatim otherwise)
+        out = vae.down5(vae.down4(vae.down3(vae.down2(vae.down1(vae.in_block(oh))))))
+        out = out.view(out.size(0), flat)
+        mean, std = vae.fc_mean(out), torch.relu(vae.fc_std(out))
+        lat = mean + z * std * 0.35
+        h = vae.fc2(lat).view(out.size(0), 256, side, side, side)
+        recon = vae.final(vae.out_block(vae.up5(vae.up4(vae.up3(vae.up2(vae.up1(h)))))))
+        d = {"recon": recon, "onehot": oh, "mean": mean, "std": std}
+        loss = 1 - ev.avg_dsc(d, source_key="recon", target_key="onehot", botindex=1, topindex=2) + 0.00002 * ev.KLloss(d)
+        loss.backward()
+        return loss.detach(), OrderedDict((k, p.grad) for k, p in vae.named_parameters())
+
+    K = COND_CASE["steps"]
+    sd_real, l_real = C.train_seg(K, patch=COND_CASE["patch_seg"], lr=COND_CASE["lr"], step_fn=real_seg_step)
+    vd_real, lv_real = C.train_vae(K, patch=COND_CASE["patch_vae"], lr=COND_CASE["lr"], step_fn=real_vae_step)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "conditioned.npz"), seg_losses=np.array(l_real), vae_losses=np.array(lv_real),
+                        seg_checksum=C.checksum(sd_real), vae_checksum=C.checksum(vd_real))
+    print("conditioned seg losses", l_real, "vae", lv_real)
 
     # ---- loss functions on small random tensors (utils/evaluation.py) ----
     torch.manual_seed(LOSS_CASE["seed"])

@@ -211,12 +211,26 @@ K2_TC_CASES = [(2, 3, 4, 5, 8), (1, 2, 17, 9, 16), (1, 1, 2, 2, 64), (1, 3, 3, 3
                (1, 5, 20, 11, 8), (1, 4, 33, 8, 16)]
 
 
+@pytest.mark.parametrize("variant", [1, 0])
 @pytest.mark.parametrize("case", K2_TC_CASES)
-def test_k2s2_tensor_core_gather_and_scatter(case):
+def test_k2s2_tensor_core_gather_and_scatter(case, variant):
+    import ctypes
+    from vae_segmentation_b200 import _cabi
+    try:
+        _k2s2_tc_case(case, variant)
+    finally:
+        ctypes.CDLL(_cabi.LIB_PATH).vs_debug_set_k2_tc(1)
+
+
+def _k2s2_tc_case(case, variant):
     """Conv3d(C,C,2,stride 2) / ConvTranspose3d(C,C,2,stride 2) forward and input gradient through the tcgen05 kernels
     (csrc/k2s2_tc.cu) against torch fp32 on the SAME bf16-rounded operands: only accumulation order and the bf16
     rounding of the output differ.  Ragged tiles (H, W not multiples of 16 / 8) exercise the TMA zero fill."""
     n, dc, hc, wc, c = case
+    # variant 1 = swizzled gather operand rows (default), 0 = 8-channel no-swizzle planes
+    import ctypes
+    from vae_segmentation_b200 import _cabi
+    ctypes.CDLL(_cabi.LIB_PATH).vs_debug_set_k2_tc(variant)
     torch.manual_seed(sum(case) + 3)
     wt = (torch.randn(c, c, 2, 2, 2) * (0.5 / c ** 0.5))
     wq = wt.bfloat16().float()

@@ -156,3 +156,20 @@ def test_clip_center_oracle_matches_reference_statements():
     val /= 300
     assert np.array_equal(R.clip_center(x), val.reshape(x.shape))
     assert R.clip_center(np.array([-5000, 100, 5000], dtype=np.int16)).tolist() == [-1.0, 0.0, 1.0]
+
+
+def test_conditioned_recipe_matches_real_reference_golden(golden_dir):
+    """oracle/conditioned.py (weights after K SGD steps of the reference's train step, the fixture of the bf16 parity
+    tests) against the same recipe run through the REAL reference modules (tests/golden/conditioned.npz, written by
+    oracle/make_golden.py): loss trajectory and per-parameter (sum, l2) checksums of the trained weights."""
+    import numpy as np
+    from oracle import conditioned as C
+    from oracle.make_golden import COND_CASE
+    g = np.load(os.path.join(golden_dir, "conditioned.npz"))
+    K, lr = COND_CASE["steps"], COND_CASE["lr"]
+    sd, losses = C.train_seg(K, patch=COND_CASE["patch_seg"], lr=lr)
+    np.testing.assert_allclose(losses, g["seg_losses"], rtol=2e-4)
+    np.testing.assert_allclose(C.checksum(sd)[:, 1], g["seg_checksum"][:, 1], rtol=1e-4)
+    vd, vlosses = C.train_vae(K, patch=COND_CASE["patch_vae"], lr=lr)
+    np.testing.assert_allclose(vlosses, g["vae_losses"], rtol=2e-4)
+    np.testing.assert_allclose(C.checksum(vd)[:, 1], g["vae_checksum"][:, 1], rtol=1e-4)

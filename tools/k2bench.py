@@ -1,6 +1,9 @@
 #!/usr/bin/env python
-"""k2s2 (Conv3d / ConvTranspose3d k2 s2) kernels at the joint step's shapes: tcgen05 (csrc/k2s2_tc.cu) vs CUDA-core
-(csrc/k2s2.cu), CUDA events, L2 flushed between iterations.  Diagnostic (numbers go to profiles/ by hand)."""
+"""k2s2 (Conv3d / ConvTranspose3d k2 s2) kernels at the joint step's shapes: tcgen05 (csrc/k2s2_tc.cu, with and without
+the swizzled operand rows / TMA-store epilogue) vs CUDA-core (csrc/k2s2.cu).  Each timing = CUDA events around 8
+back-to-back launches over 8 DIFFERENT input/output sets (> L2 in total at the big shapes), queued behind a spin kernel so
+the host's launch latency is not charged.  Diagnostic (numbers go to profiles/ by hand)."""
+import ctypes
 import os
 import sys
 
@@ -8,46 +11,65 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
-from vae_segmentation_b200 import ops  # noqa: E402
+from vae_segmentation_b200 import _cabi, ops  # noqa: E402
 
 dev = "cuda"
 PEAK = 6546.6
-flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
+NSET = 8
+handle = ctypes.CDLL(_cabi.LIB_PATH)
 
 
-def timeit(fn, iters=10):
+def timeit(fns):
+    for f in fns[:2]:
+        f()
+    torch.cuda.synchronize()
+    best = 1e9
     for _ in range(3):
-        fn()
-    tot = 0.0
-    for _ in range(iters):
-        flush.zero_()
+        torch.cuda._sleep(int(2e-3 * 1.9e9))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        fn()
+        for f in fns:
+            f()
         e1.record()
         torch.cuda.synchronize()
-        tot += e0.elapsed_time(e1)
-    return tot / iters * 1e3
+        best = min(best, e0.elapsed_time(e1) / len(fns) * 1e3)
+    return best
 
 
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 96
 N = 2
-print("%-8s %5s %4s %10s %10s %8s %8s" % ("op", "coarse", "C", "cuda us", "tc us", "tc GB/s", "frac"))
+print("%-8s %6s %4s %9s %9s %9s %9s %8s" % ("op", "coarse", "C", "cuda us", "tc0 us", "tc us", "GB/s", "frac"))
+shapes = []
 side, c = P // 2, 8
-while side >= 3 and c <= 256:
-    if (2 * side) % 2 == 0:
-        w = torch.randn(c, c, 2, 2, 2, device=dev) * 0.1
-        b = torch.randn(c, device=dev)
-        fine = torch.randn(N, 2 * side, 2 * side, 2 * side, c, device=dev).bfloat16()
-        coarse = torch.randn(N, side, side, side, c, device=dev).bfloat16()
-        pg = ops.pack_k2s2_weight_tc(w, c, c, False)
-        ps = ops.pack_k2s2_weight_tc(w, c, c, True)
-        dims = (N, side, side, side)
-        byts = (fine.numel() + coarse.numel()) * 2
-        for name, f_cuda, f_tc in (
-                ("gather", lambda: ops.k2s2_gather(fine, w, b, dims, c, c), lambda: ops.k2s2_gather(fine, w, b, dims, c, c, wtc=pg)),
-                ("scatter", lambda: ops.k2s2_scatter(coarse, w, b, dims, c, c), lambda: ops.k2s2_scatter(coarse, w, b, dims, c, c, wtc=ps))):
-            t0, t1 = timeit(f_cuda), timeit(f_tc)
-            print("%-8s %5d %4d %10.1f %10.1f %8.0f %8.3f" % (name, side, c, t0, t1, byts / t1 / 1e3, byts / t1 / 1e3 / PEAK), flush=True)
+while side >= 3 and c <= 256:                      # Down path: C at 2*side -> side
+    shapes.append((side, c))
     side //= 2
     c *= 2
+side, c = P // 2, 16
+while side >= 3 and c <= 256:                      # Up path: C at side -> 2*side
+    shapes.append((side, c))
+    side //= 2
+    c *= 2
+for side, c in sorted(set(shapes), key=lambda t: (-t[0], t[1])):
+    w = torch.randn(c, c, 2, 2, 2, device=dev) * 0.1
+    b = torch.randn(c, device=dev)
+    nset = NSET if side >= 24 else 2
+    fines = [torch.randn(N, 2 * side, 2 * side, 2 * side, c, device=dev).bfloat16() for _ in range(nset)]
+    coarses = [torch.randn(N, side, side, side, c, device=dev).bfloat16() for _ in range(nset)]
+    pg = ops.pack_k2s2_weight_tc(w, c, c, False)
+    ps = ops.pack_k2s2_weight_tc(w, c, c, True)
+    dims = (N, side, side, side)
+    byts = (fines[0].numel() + coarses[0].numel()) * 2
+    for name in ("gather", "scatter"):
+        if name == "gather":
+            cuda = [lambda f=f: ops.k2s2_gather(f, w, b, dims, c, c) for f in fines]
+            tc = [lambda f=f: ops.k2s2_gather(f, w, b, dims, c, c, wtc=pg) for f in fines]
+        else:
+            cuda = [lambda x=x: ops.k2s2_scatter(x, w, b, dims, c, c) for x in coarses]
+            tc = [lambda x=x: ops.k2s2_scatter(x, w, b, dims, c, c, wtc=ps) for x in coarses]
+        t_cuda = timeit(cuda)
+        handle.vs_debug_set_k2_tc(0)
+        t_tc0 = timeit(tc)
+        handle.vs_debug_set_k2_tc(1)
+        t_tc = timeit(tc)
+        print("%-8s %6d %4d %9.1f %9.1f %9.1f %9.0f %8.3f" % (name, side, c, t_cuda, t_tc0, t_tc, byts / t_tc / 1e3, byts / t_tc / 1e3 / PEAK), flush=True)
