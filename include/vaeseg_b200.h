@@ -38,6 +38,10 @@ const char* vs_last_error_string(void);
 int vs_version(void);
 /* 1 when the library was built with the tcgen05/TMA (sm_100a) conv kernels */
 int vs_has_tcgen05(void);
+/* Programmatic dependent launch for the kernels of the hot chain (convolutions, k2s2, InstanceNorm passes): launches
+ * of at most `max_ctas` CTAs may be scheduled while their predecessor in the stream drains (the prologue overlaps the
+ * predecessor's tail; the kernel waits before touching global memory).  0 disables.  Returns the previous setting. */
+int vs_set_pdl(int max_ctas);
 
 /* ---- weight repacking (derived caches of the fp32 master weights) ------------------- */
 /* Conv3d 3x3x3 weight [Cout,Cin,27] -> wf[27][Cin][Cout] (fprop) and, when wd != NULL,

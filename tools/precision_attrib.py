@@ -33,3 +33,24 @@ for sim in ([], ["y"], ["a"], ["g"], ["dy"], ["k2"], ["y", "a", "dy", "k2"], ["y
     print("== simulate bf16 on %s: probs rel-L2 %.3e" % (sim, rel(pred, pred_ref)))
     grad_report("   ", got, g_ref)
 engine.SIMULATE_BF16 = set()
+
+# ---- VAE train step (main_source.py:389-406): no skip connections, every gradient passes through the 2^3 .. 4^3 levels
+from vae_segmentation_b200.synthetic import synth_label  # noqa: E402
+vae_sd, _ = C.train_vae(60, patch=P, lr=0.1)
+torch.manual_seed(1235)
+label = synth_label(2, P)
+z = torch.randn(2, 128)
+loss_ref, dsc_ref, kl_ref, g_ref, rec_ref = R.vae_train_step(vae_sd, label, scale=0.35, z=z, eps=0.0001)
+for sim in ([], ["y"], ["a"], ["g"], ["dy"], ["k2"], ["y", "a", "g", "dy", "k2"]):
+    engine.SIMULATE_BF16 = set(sim)
+    vae = jm.VAE(2, 2, norm_type=1, dim=128, patch=P)
+    vae.load_state_dict(vae_sd, strict=True)
+    vae = vae.to("cuda").set_precision("fp32")
+    oh = ev.one_hot(label.to("cuda"), 2)
+    recon, mean, std = vae(oh, if_random=True, scale=0.35, z=z)
+    d = {"recon": recon, "onehot": oh, "mean": mean, "std": std}
+    (1 - ev.avg_dsc(d, source_key="recon", target_key="onehot", botindex=1, topindex=2, eps=0.0001) + 0.00002 * ev.KLloss(d)).backward()
+    got = OrderedDict((k, p.grad.detach().cpu().clone()) for k, p in vae.named_parameters() if p.grad is not None)
+    print("== VAE, simulate bf16 on %s: recon rel-L2 %.3e" % (sim, rel(recon, rec_ref)))
+    grad_report("   ", got, g_ref)
+engine.SIMULATE_BF16 = set()

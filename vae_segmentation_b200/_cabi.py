@@ -21,6 +21,7 @@ _SIGNATURES = {
     "vs_last_error_string": [],
     "vs_version": [],
     "vs_has_tcgen05": [],
+    "vs_set_pdl": [_I],
     "vs_pack_conv3_weight": [_P, _P, _P, _I, _I, _P],
     "vs_conv3_tc_pack_bytes": [_I, _I, _I],
     "vs_pack_conv3_weight_tc": [_P, _P, _I, _I, _I, _P],
@@ -73,6 +74,7 @@ _RESTYPES = {"vs_last_error_string": c_char_p, "vs_conv3_wgrad_workspace_bytes":
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
 _lib = None
+PDL_DEFAULT = "0"
 
 
 def lib():
@@ -88,6 +90,10 @@ def lib():
             fn = getattr(handle, name)
             fn.argtypes = argtypes
             fn.restype = _RESTYPES.get(name, c_int)
+        # programmatic dependent launch for launches of at most VAESEG_PDL CTAs (include/vaeseg_b200.h: vs_set_pdl); 0 disables
+        handle.vs_set_pdl(int(os.environ.get("VAESEG_PDL", PDL_DEFAULT)))
+        if os.environ.get("VAESEG_CONV3_KSPLIT", "1") == "0":          # A/B switch (tools): K split over the conv issuer warps
+            handle.vs_debug_set_conv3_ksplit(0)
         _lib = handle
     return _lib
 

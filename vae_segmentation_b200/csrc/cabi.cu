@@ -5,6 +5,7 @@
 #include "vs_common.cuh"
 
 static thread_local char g_err[512] = "";
+int g_vs_pdl = 0;
 
 void vs_set_error(const char* fmt, ...) {
     va_list ap;
@@ -45,6 +46,7 @@ static bool tc_eligible(int gin, int gout) {
 
 extern "C" const char* vs_last_error_string(void) { return g_err; }
 extern "C" int vs_version(void) { return 100; }
+extern "C" int vs_set_pdl(int max_ctas) { const int old = g_vs_pdl; g_vs_pdl = max_ctas > 0 ? max_ctas : 0; return old; }
 extern "C" int vs_has_tcgen05(void) {
 #ifdef VS_WITH_TCGEN05
     return 1;

@@ -44,6 +44,10 @@ struct TcParams {
                             // volumes do not pay for rows that are pure zero fill (TMA cost is per 16-byte row)
     int ref_tile;           // tile (within a sample) that holds the shift's reference voxel
     int td;                 // d-planes per work item (1, 2 or 4): deep levels use fewer so that the grid fills the SMs
+    int nsum;               // accumulators per d-plane (K split): with td < 4 the 4 / td issuer warps that share a plane
+                            // take the 16-channel K slices round-robin into their own TMEM accumulators and the epilogue
+                            // adds them -- a single thread issues one MMA per ~100 cycles, so at the deep levels
+                            // (Cin >= 32, one or two planes per CTA) the issue chain, not the tensor pipe, set the time
     int nchunks;            // cout chunks of NC
     int kslices;            // cin / 16 (1 for cin == 8)
     long long work_items;   // n * tiles_per_n * nchunks
@@ -63,7 +67,9 @@ struct TcParams {
     int planar_mode;
     float* yplanar;
     const float* bias;      // [2] or null (mode 1)
+    long long* dbg;         // tools/tc_phase_probe.py: clock64 of CTA 0 at the phases of its first work item, or null
 };
+#define TC_DBG(slot) do { if (p.dbg != nullptr && blockIdx.x == 0) p.dbg[slot] = clock64(); } while (0)
 
 // Column sums of a 32-lane x 16-value register tile in 31 shuffles: afterwards v[0] of lane L holds the
 // sum over all lanes of column (L & 15).
@@ -142,6 +148,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);      // warp-uniform for the compiler
     const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) TC_DBG(0);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], TD); }
@@ -161,10 +168,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
         fence_proxy_async();
     }
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    pdl_trigger();                       // the next kernel of the chain may set itself up behind this one
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    pdl_wait();                          // everything above overlapped the predecessor; global memory from here on
+    if (threadIdx.x == 0) TC_DBG(1);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -183,27 +193,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
                     const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) +
                                           ((long long)chunk * p.kslices + ks) * B_BYTES;
                     bulk_load(sa + A_BYTES, wsrc, B_BYTES, &full_bar[stage]);
+                    if (item == blockIdx.x && ks == 0) TC_DBG(2);
+                    if (item == blockIdx.x && ks == p.kslices - 1) TC_DBG(3);
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp <= TD) {
-        // ===================== MMA issuers: warp 1 + j owns d-plane j of every tile =====================
+        // ===================== MMA issuers: warp 1 + j owns d-plane j % td of every tile (and, when several warps
+        // share a plane, the K slices ks with ks % nsplit == j / td, accumulated in its own TMEM accumulator j) ========
         const int j = warp - 1;
+        const int pl = j % p.td, part = j / p.td, nsplit = TD / p.td;
         constexpr uint32_t idesc = make_idesc(NC);
         uint32_t stage = 0, phase = 0, buf = 0, bphase = 0;
         for (long long item = blockIdx.x; item < p.work_items; item += gridDim.x) {
             int n, d0, h0, w0, chunk;
             decode_work(item, p, n, d0, h0, w0, chunk);
-            const bool active = j < min(p.td, p.d - d0);
+            const bool active = pl < min(p.td, p.d - d0) && part < p.nsum;
             mbar_wait(&tempty_bar[buf], bphase ^ 1);
             tc_fence_after();
             const uint32_t dcol = tmem_base + (buf * TD + j) * NC;
             for (int ks = 0; ks < p.kslices; ++ks) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                if (active) {
-                    const uint32_t a_base = smem_u32(smem + stage * STAGE_BYTES) + (uint32_t)(j * p.bh * p.bw) * 16u;
+                if (j == 0 && lane == 0 && item == blockIdx.x && ks == 0) TC_DBG(4);
+                const int ksl = p.nsum > 1 ? ks - part : ks;     // >= 0 and a multiple of nsplit on this warp's slices; 0 on its first
+                if (active && (p.nsum == 1 || (ks % nsplit) == part)) {
+                    const uint32_t a_base = smem_u32(smem + stage * STAGE_BYTES) + (uint32_t)(pl * p.bh * p.bw) * 16u;
                     const uint32_t b_base = smem_u32(smem + stage * STAGE_BYTES) + A_BYTES;
                     if (CIN8) {
                         // Cin = 8: the two K chunks of an MMA are two filter taps.  Any two taps work -- the second
@@ -217,7 +233,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
                             const uint32_t lbo = (2 * m + 1 < 27) ? (uint32_t)(o2 - o1) * 16u : 16u;
                             const uint64_t ad = make_desc(a_base + (uint32_t)o1 * 16u, lbo, (uint32_t)p.bw * 16u);
                             const uint64_t bd = make_desc(b_base + m * (NC * 32), NC * 16, 128u);
-                            tc_mma_elect(dcol, ad, bd, idesc, (ks | m) != 0);
+                            tc_mma_elect(dcol, ad, bd, idesc, (ksl | m) != 0);
                         }
                     } else {
                     int m = 0;
@@ -230,7 +246,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
                             for (int kx = 0; kx < 3; ++kx, ++m) {
                                 const uint64_t ad = make_desc(row + kx * 16u, PLANE_BYTES, (uint32_t)p.bw * 16u);
                                 const uint64_t bd = make_desc(b_base + m * (NC * 32), NC * 16, 128u);
-                                tc_mma_elect(dcol, ad, bd, idesc, (ks | m) != 0);
+                                tc_mma_elect(dcol, ad, bd, idesc, (ksl | m) != 0);
                             }
                         }
                     }
@@ -240,6 +256,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
             tc_commit_elect(&tfull_bar[buf]);                   // this warp's accumulator plane is complete
+            if (j == 0 && lane == 0 && item == blockIdx.x) TC_DBG(5);
             if (++buf == NBUF) { buf = 0; bphase ^= 1; }
         }
     } else {
@@ -326,6 +343,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
                                 uint32_t r[16];
                                 tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (buf * TD + (rd - ref_d0)) * NC + c16 * 16, r);
                                 tmem_ld_wait();
+                                for (int part = 1; part < p.nsum; ++part) {          // K-split accumulators of the plane
+                                    uint32_t r2[16];
+                                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (buf * TD + (rd - ref_d0) + part * p.td) * NC + c16 * 16, r2);
+                                    tmem_ld_wait();
+#pragma unroll
+                                    for (int k = 0; k < 16; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) + __uint_as_float(r2[k]));
+                                }
                                 if (lane == (ref_row & 31)) {
 #pragma unroll
                                     for (int k = 0; k < 16; ++k) {
@@ -380,8 +404,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
                     }
                 }
             }
+            if (et == 0 && item == blockIdx.x) TC_DBG(6);
             mbar_wait(&tfull_bar[buf], bphase);
             tc_fence_after();
+            if (et == 0 && item == blockIdx.x) TC_DBG(7);
             // The epilogue is ONE warp per scheduler running a dependent chain: its latencies are not hidden by other
             // warps, and at the full-resolution levels it -- not the MMAs -- sets the tile time.  NC = 16: the TMEM
             // load of plane j+1 is in flight while plane j is processed, the shift lives in registers.
@@ -412,6 +438,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
                     } else {
                         tmem_ld16(taddr + c16 * 16, r);
                         tmem_ld_wait();
+                    }
+                    for (int part = 1; part < p.nsum; ++part) {                  // K-split accumulators of the plane
+                        uint32_t r2[NV];
+                        if constexpr (H8) tmem_ld8(taddr + part * p.td * NC + c16 * 16, r2);
+                        else tmem_ld16(taddr + part * p.td * NC + c16 * 16, r2);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int k = 0; k < NV; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) + __uint_as_float(r2[k]));
                     }
                     float v[NV];
                     if (has_shift && NC == 16) {
@@ -502,9 +536,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+            if (et == 0 && item == blockIdx.x) TC_DBG(8);
             if (++buf == NBUF) { buf = 0; bphase ^= 1; }
         }
         flush_stats();
+        if (et == 0) TC_DBG(9);
     }
     tc_fence_before();
     __syncthreads();
@@ -512,6 +548,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
+    if (threadIdx.x == 0) TC_DBG(10);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -527,6 +564,8 @@ __global__ void pack_tc_kernel(const float* __restrict__ w, bf16* __restrict__ o
 }
 
 int nc_for(int gout) { return nc_for_dev(gout); }
+long long* g_tc_dbg = nullptr;   // vs_debug_set_tc_phase_buffer: device buffer of >= 16 clock64 slots (tools/tc_phase_probe.py)
+int g_conv3_ksplit = 1;          // A/B switch (vs_debug_set_conv3_ksplit): K split over the issuer warps that share a plane
 
 template <int NC, bool CIN8, int NSTAGE, bool H8 = false>
 int launch_tc(const CUtensorMap& map, const TcParams& p, cudaStream_t st) {
@@ -541,7 +580,7 @@ int launch_tc(const CUtensorMap& map, const TcParams& p, cudaStream_t st) {
         configured = true;
     }
     const long long grid = p.work_items < (long long)vs_sm_count() ? p.work_items : (long long)vs_sm_count();
-    kern<<<(unsigned)grid, NTHREADS, SMEM, st>>>(map, p);
+    VS_CUDA(vs_launch(kern, dim3((unsigned)grid), dim3(NTHREADS), SMEM, st, map, p), "conv3_tc_kernel launch");
     VS_CHECK_LAUNCH("conv3_tc_kernel");
     return VS_OK;
 }
@@ -691,6 +730,10 @@ extern "C" int vs_conv3x3x3_tc(const void* x, const void* wtc, void* y, double* 
     p.tiles_h = tiles_h; p.tiles_w = tiles_w;
     p.nchunks = nchunks;
     p.td = td; p.bw = bw; p.bh = bh; p.bd = bd;
+    {
+        const int nsplit = TD / td, ksl = gin == 8 ? 1 : gin / 16;
+        p.nsum = g_conv3_ksplit ? (nsplit < ksl ? nsplit : ksl) : 1;
+    }
     p.tiles_d = (d + p.td - 1) / p.td;
     p.tiles_per_n = p.tiles_d * p.tiles_h * p.tiles_w;
     p.ref_tile = (min(1, d - 1) / td) * tiles_h * tiles_w;        // voxel (1,1,1): h- and w-tile 0, d-tile 1/td
@@ -700,6 +743,7 @@ extern "C" int vs_conv3x3x3_tc(const void* x, const void* wtc, void* y, double* 
     p.wpack = (const bf16*)wtc; p.y = (bf16*)y; p.stats = stats; p.shift = shift;
     p.yprev = (const bf16*)yprev; p.pstats = pstats; p.psums = psums; p.inv_s = 1.0 / ((double)d * h * w);
     p.planar_mode = planar_mode; p.yplanar = yplanar; p.bias = bias;
+    p.dbg = g_tc_dbg;
     if (psums != nullptr) {
         VS_REQUIRE(yprev && pstats && stats == nullptr && shift == nullptr, VS_ERR_SHAPE,
                    "conv3_tc: the fused norm-backward reduction needs y_prev + stats_prev and no forward statistics");
@@ -727,6 +771,9 @@ extern "C" int vs_conv3x3x3_tc(const void* x, const void* wtc, void* y, double* 
     if (nc == 32) return launch_tc<32, false, 3>(map, p, st);
     return launch_tc<64, false, 2>(map, p, st);
 }
+
+extern "C" void vs_debug_set_conv3_ksplit(int on) { g_conv3_ksplit = on; }
+extern "C" void vs_debug_set_tc_phase_buffer(void* dev_ptr) { g_tc_dbg = (long long*)dev_ptr; }
 
 extern "C" int vs_pack_conv3_batched(const void* jobs_dev, int njobs, void* stream) {
     VS_REQUIRE(jobs_dev && njobs > 0, VS_ERR_SHAPE, "pack_conv3_batched: bad arguments");

@@ -128,10 +128,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kdn_kernel(const __grid_
         fence_proxy_async();
     }
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    pdl_trigger();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    pdl_wait();                          // see vs_common.cuh: no global-memory access above this line
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -359,7 +361,7 @@ int launch_kdn(const CUtensorMap& map, const KdnParams& p, cudaStream_t st) {
         configured = true;
     }
     const int grid = p.work_items < vs_sm_count() ? p.work_items : vs_sm_count();
-    kern<<<(unsigned)grid, NTHREADS, SMEM, st>>>(map, p);
+    VS_CUDA(vs_launch(kern, dim3((unsigned)grid), dim3(NTHREADS), SMEM, st, map, p), "conv3_tc_kdn_kernel launch");
     VS_CHECK_LAUNCH("conv3_tc_kdn_kernel");
     return VS_OK;
 }

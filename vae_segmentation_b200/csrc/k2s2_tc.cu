@@ -90,15 +90,13 @@ __global__ void __launch_bounds__(128 + 128 * NEPI, 1) k2s2_tc_kernel(const __gr
         for (int b = 0; b < NBUF; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
         fence_barrier_init();
     }
-    {
-        const int nbias = SCATTER ? p.b : p.a;
-        for (int i = threadIdx.x; i < nbias; i += blockDim.x) sbias[i] = p.bias != nullptr ? p.bias[i] : 0.f;
-    }
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    pdl_trigger();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    pdl_wait();                          // see vs_common.cuh: no global-memory access above this line
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -171,6 +169,12 @@ __global__ void __launch_bounds__(128 + 128 * NEPI, 1) k2s2_tc_kernel(const __gr
         const int lh = row >> 3, lw = row & 7;
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(e * NC);
         const uint32_t sbias_addr = smem_u32(sbias);
+        {
+            // the bias (a parameter) is read after pdl_wait like everything else; only the epilogue warps use it
+            const int nbias = SCATTER ? p.b : p.a;
+            for (int i = (int)threadIdx.x - 128; i < nbias; i += 128 * NEPI) sbias[i] = p.bias != nullptr ? p.bias[i] : 0.f;
+            asm volatile("bar.sync 1, %0;" ::"n"(128 * NEPI) : "memory");
+        }
         uint32_t bphase = 0;
         const int wf = 2 * p.wc, hwf = 4 * p.hc * p.wc;          // fine row / plane pitch in voxels (32-bit: host-checked)
         for (int item = blockIdx.x + e * (int)gridDim.x; item < p.work_items; item += NEPI * (int)gridDim.x) {
@@ -272,7 +276,7 @@ int launch_k2(const CUtensorMap& map, const K2TcParams& p, cudaStream_t st) {
         configured = smem;
     }
     const int grid = p.work_items < vs_sm_count() ? p.work_items : vs_sm_count();
-    kern<<<(unsigned)grid, 128 + 128 * NEPI, smem, st>>>(map, p);
+    VS_CUDA(vs_launch(kern, dim3((unsigned)grid), dim3(128 + 128 * NEPI), (size_t)smem, st, map, p), "k2s2_tc_kernel launch");
     VS_CHECK_LAUNCH("k2s2_tc_kernel");
     return VS_OK;
 }

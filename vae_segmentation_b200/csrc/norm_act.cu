@@ -14,6 +14,8 @@ __global__ void __launch_bounds__(NT) inorm_relu_apply_kernel(const T* __restric
                                                               const T* __restrict__ skip, T* __restrict__ a,
                                                               long long s, int c) {
     __shared__ float sm[256], sr[256];
+    pdl_trigger();
+    pdl_wait();
     const int n = blockIdx.y, t = threadIdx.x;
     const double inv_s = 1.0 / (double)s;
     for (int ch = t; ch < c; ch += NT) in_mean_rstd(stats + ((long long)n * c + ch) * 2, inv_s, sm[ch], sr[ch]);
@@ -44,6 +46,8 @@ __global__ void __launch_bounds__(NT) inorm_relu_bwd_reduce_kernel(const T* __re
                                                                    double* __restrict__ sums, long long s, int c) {
     __shared__ float sm[256], sr[256];
     __shared__ double red[NT][17];
+    pdl_trigger();
+    pdl_wait();
     const int n = blockIdx.y, t = threadIdx.x;
     const double inv_s = 1.0 / (double)s;
     for (int ch = t; ch < c; ch += NT) in_mean_rstd(stats + ((long long)n * c + ch) * 2, inv_s, sm[ch], sr[ch]);
@@ -86,6 +90,8 @@ __global__ void __launch_bounds__(NT) inorm_relu_bwd_apply_kernel(const T* __res
                                                                   const double* __restrict__ sums, T* __restrict__ dy,
                                                                   long long s, int c) {
     __shared__ float sm[256], sr[256], m0[256], m1[256];
+    pdl_trigger();
+    pdl_wait();
     const int n = blockIdx.y, t = threadIdx.x;
     const double inv_s = 1.0 / (double)s;
     for (int ch = t; ch < c; ch += NT) {
@@ -114,6 +120,8 @@ __global__ void __launch_bounds__(NT) inorm_relu_bwd_apply_kernel(const T* __res
 
 template <typename T>
 __global__ void __launch_bounds__(NT) add_inplace_kernel(T* __restrict__ dst, const T* __restrict__ src, long long nvec) {
+    pdl_trigger();
+    pdl_wait();
     for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < nvec; i += (long long)gridDim.x * NT) {
         float a[8], b[8];
         Store<T>::ld8(dst + i * 8, a);
@@ -218,8 +226,8 @@ extern "C" int vs_inorm_relu_apply(int dtype, const void* y, const double* stats
     int rc = check_norm(y, a, n, s, c, "inorm_relu_apply");
     if (rc) return rc;
     dim3 grid(stream_grid(s * (c / 8) / 4 + 1), n);
-    VS_DISPATCH_DTYPE(dtype, T, { inorm_relu_apply_kernel<T><<<grid, NT, 0, (cudaStream_t)stream>>>(
-        (const T*)y, stats, (const T*)skip, (T*)a, s, c); });
+    VS_DISPATCH_DTYPE(dtype, T, { VS_CUDA(vs_launch(inorm_relu_apply_kernel<T>, grid, dim3(NT), 0, (cudaStream_t)stream,
+        (const T*)y, stats, (const T*)skip, (T*)a, s, c), "inorm_relu_apply launch"); });
     VS_CHECK_LAUNCH("inorm_relu_apply_kernel");
     return VS_OK;
 }
@@ -233,8 +241,8 @@ extern "C" int vs_inorm_relu_bwd_reduce(int dtype, const void* g, const void* y,
     const int lanes = NT / (c / 8);
     long long blocks = (s + (long long)lanes * 8 - 1) / ((long long)lanes * 8);
     dim3 grid((unsigned)max(1LL, min(blocks, (long long)vs_sm_count() * 4)), n);
-    VS_DISPATCH_DTYPE(dtype, T, { inorm_relu_bwd_reduce_kernel<T><<<grid, NT, 0, st>>>(
-        (const T*)g, (const T*)y, stats, sums, s, c); });
+    VS_DISPATCH_DTYPE(dtype, T, { VS_CUDA(vs_launch(inorm_relu_bwd_reduce_kernel<T>, grid, dim3(NT), 0, st,
+        (const T*)g, (const T*)y, stats, sums, s, c), "inorm_relu_bwd_reduce launch"); });
     VS_CHECK_LAUNCH("inorm_relu_bwd_reduce_kernel");
     return VS_OK;
 }
@@ -244,8 +252,8 @@ extern "C" int vs_inorm_relu_bwd_apply(int dtype, const void* g, const void* y, 
     int rc = check_norm(g, dy, n, s, c, "inorm_relu_bwd_apply");
     if (rc) return rc;
     dim3 grid(stream_grid(s * (c / 8) / 4 + 1), n);
-    VS_DISPATCH_DTYPE(dtype, T, { inorm_relu_bwd_apply_kernel<T><<<grid, NT, 0, (cudaStream_t)stream>>>(
-        (const T*)g, (const T*)y, stats, sums, (T*)dy, s, c); });
+    VS_DISPATCH_DTYPE(dtype, T, { VS_CUDA(vs_launch(inorm_relu_bwd_apply_kernel<T>, grid, dim3(NT), 0, (cudaStream_t)stream,
+        (const T*)g, (const T*)y, stats, sums, (T*)dy, s, c), "inorm_relu_bwd_apply launch"); });
     VS_CHECK_LAUNCH("inorm_relu_bwd_apply_kernel");
     return VS_OK;
 }
@@ -254,8 +262,8 @@ extern "C" int vs_add_inplace(int dtype, void* dst, const void* src, long long c
     VS_REQUIRE(dst && src && count > 0 && count % 8 == 0, VS_ERR_SHAPE, "add_inplace: count must be a positive multiple of 8");
     VS_REQUIRE(vs_aligned16(dst) && vs_aligned16(src), VS_ERR_ALIGN, "add_inplace: pointers must be 16B aligned");
     const long long nvec = count / 8;
-    VS_DISPATCH_DTYPE(dtype, T, { add_inplace_kernel<T><<<stream_grid(nvec / 4 + 1), NT, 0, (cudaStream_t)stream>>>(
-        (T*)dst, (const T*)src, nvec); });
+    VS_DISPATCH_DTYPE(dtype, T, { VS_CUDA(vs_launch(add_inplace_kernel<T>, dim3(stream_grid(nvec / 4 + 1)), dim3(NT), 0,
+        (cudaStream_t)stream, (T*)dst, (const T*)src, nvec), "add_inplace launch"); });
     VS_CHECK_LAUNCH("add_inplace_kernel");
     return VS_OK;
 }

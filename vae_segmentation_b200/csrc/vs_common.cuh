@@ -17,6 +17,33 @@ void vs_set_error(const char* fmt, ...);
     if (e_ != cudaSuccess) VS_FAIL(VS_ERR_CUDA, "%s: %s", name, cudaGetErrorString(e_)); } while (0)
 #define VS_REQUIRE(cond, code, ...) do { if (!(cond)) VS_FAIL(code, __VA_ARGS__); } while (0)
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------
+// The step is a chain of ~500 short dependent kernels.  Kernels launched through vs_launch() carry
+// cudaLaunchAttributeProgrammaticStreamSerialization (when enabled, vs_set_pdl): the next kernel of the stream may be
+// scheduled as soon as every CTA of this one has executed pdl_trigger() -- its launch latency, barrier init, TMEM
+// allocation and shared-memory carve-up then overlap this kernel's tail -- and it blocks in pdl_wait() until this
+// kernel has completed and flushed its memory.  RULE: a kernel launched through vs_launch() executes pdl_wait() in
+// every thread before its first global-memory access (reads of activations AND writes: the predecessor may still be
+// reading what this kernel overwrites).  Without the attribute both instructions are no-ops.
+extern int g_vs_pdl;
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t vs_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    // g_vs_pdl = largest grid (CTAs) launched programmatically: a dependent that is scheduled early holds its SM slots
+    // while it waits, which on the big persistent grids starves the concurrent streams (teacher forward, weight
+    // gradients) -- measured 334 vs 384 vol/s with every launch programmatic -- so only the small latency-bound
+    // launches of the deep levels use it
+    cfg.numAttrs = (g_vs_pdl > 0 && (long long)grid.x * grid.y * grid.z <= (long long)g_vs_pdl) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 static inline bool vs_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 int vs_sm_count();
 __device__ __forceinline__ bool vs_aligned16_dev(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
