@@ -267,10 +267,16 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    stdout_fd = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
+            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL prints its version banner on stdout whatever the debug level: park fd 1 on stderr until the JSON line so
+        # that stdout carries exactly that one line
+        sys.stdout.flush()
+        stdout_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
     from vae_segmentation_b200 import _cabi
@@ -535,6 +541,9 @@ def main():
         line["cpu_baseline"] = {"value": 1.0 / sec, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                                 "sample": "2 timed steps (1 warm-up) of the same %s step at batch 1, %d^3, oracle "
                                           "port of the reference's torch CPU fp32 path" % (mode, P)}
+    if stdout_fd is not None:
+        sys.stdout.flush()
+        os.dup2(stdout_fd, 1)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

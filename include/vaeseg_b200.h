@@ -202,6 +202,14 @@ int vs_fc_encode_bwd(int dtype, const void* x, const float* wm, const float* ws,
                      float* dwm, float* dbm, float* dws, float* dbs, int accumulate,
                      int batch, int s3, int c, int dim, void* stream);
 
+/* Generic Linear (+ activation) of the encoder / discriminator head (joint_model.py:287-304: fc1 -> ReLU -> fc2 -> ReLU ->
+ * fc_mean -> sigmoid).  x [batch][in_f], w [out_f][in_f], bias [out_f] or NULL, y [batch][out_f]; act 0 = identity,
+ * 1 = ReLU, 2 = sigmoid.  Backward: gbuf [batch][out_f] scratch; dx / dw / db may be NULL; accumulate adds onto dw / db. */
+int vs_linear_fwd(const float* x, const float* w, const float* bias, float* y, int batch, int in_f, int out_f, int act,
+                  void* stream);
+int vs_linear_bwd(const float* x, const float* w, const float* y, const float* dy, float* gbuf, float* dx, float* dw,
+                  float* db, int accumulate, int batch, int in_f, int out_f, int act, void* stream);
+
 /* ---- losses (utils/evaluation.py:6-18,42-80; main_source.py:150-182) ------------------ */
 typedef enum { VS_TGT_TENSOR = 0, VS_TGT_BINARIZE = 1, VS_TGT_CONFIDENT = 2, VS_TGT_LABEL = 3,
                VS_TGT_ARGMAX = 4 } vs_target_mode;
@@ -227,6 +235,15 @@ int vs_binarize(const float* a, float* out, int mode, long long count, void* str
  * in_kind 0: x fp32; 2: x int16 (raw Hounsfield units).  out: fp32, same element count (the in-blocks' planar input). */
 int vs_clip_center(int in_kind, const void* x, float* out, long long count, float lo, float hi, float sub, float div,
                    void* stream);
+/* CropResize (utils/utils.py:220-293) on the device: `src` [sd][sh][sw] fp32 is cropped to crop9 = {start[3], length[3],
+ * leading zero padding[3]} (HOST array of 9 ints; the caller derives it from the label's bounding box exactly as the
+ * reference does) inside a zero cube of side `side`, optionally anti-alias filtered, and resampled to out [od][oh][ow]:
+ * order 1 = skimage.transform.resize(img, size) (Gaussian pre-filter sigma = max(0, (side/out - 1)/2), linear, mode
+ * 'mirror'), order 0 + anti_alias 0 = resize(label, size, order=0, anti_aliasing=False).  tmp0 / tmp1: side^3 fp32
+ * workspaces (may be NULL when no axis is downsampled or anti_alias = 0).  The crop cube is never materialised.    */
+int vs_crop_resize(const float* src, int sd, int sh, int sw, const int* crop9_host, int side, float* out, int od, int oh,
+                   int ow, int order, int anti_alias, float* tmp0, float* tmp1, void* stream);
+int vs_gauss_radius(double sigma);
 /* label[N][1][S] (fp32 class index) -> planar one-hot [N][C][S] (main_target.py:520-522)   */
 int vs_one_hot(const float* label, float* out, int n, int c, long long s, void* stream);
 

@@ -184,6 +184,32 @@ def vae_forward(sd, x, if_random=False, scale=1, mid_input=False, z=None):
     return vae_decode(sd, lat), mean, std
 
 
+def encoder_forward(sd, x):
+    """Encoder.forward (joint_model.py:290-305): conv trunk -> fc1 -> ReLU -> fc2 -> ReLU -> fc_mean -> sigmoid; the flat
+    dimension is generalised like the VAE's (16384 at 128^3 patches)."""
+    h = conv_in_relu(sd, "in_block.conv.0", x)
+    for i in range(1, 6):
+        h = down(sd, "down%d" % i, h)
+    h = h.reshape(h.size(0), -1)
+    h = F.relu(F.linear(h, sd["fc1.weight"], sd["fc1.bias"]))
+    h = F.relu(F.linear(h, sd["fc2.weight"], sd["fc2.bias"]))
+    return torch.sigmoid(F.linear(h, sd["fc_mean.weight"], sd["fc_mean.bias"]))
+
+
+def fusion_forward(sd, img, mask):
+    """Fusion.forward (joint_model.py:415-436)."""
+    x2 = down(sd, "down1", conv_in_relu(sd, "in_block.conv.0", img)) + \
+        down(sd, "down1_mask", conv_in_relu(sd, "in_block_mask.conv.0", mask))
+    x2 = conv_in_relu(sd, "merge.conv.0", x2)
+    x3 = down(sd, "down2", x2)
+    x5 = down(sd, "down4", down(sd, "down3", x3))
+    y = up(sd, "up2", x5)
+    y = up(sd, "up3", y) + x3
+    y = up(sd, "up4", y) + x2
+    y = up(sd, "up5", y)
+    return F.softmax(F.conv3d(y, sd["out_block.weight"], sd["out_block.bias"], padding=1), dim=1)
+
+
 def joint_forward(seg_sd, vae_sd, x, dropout=False, vae_forward_scale=0.0):
     """Joint.forward (joint_model.py:447-452).  With dropout=True the student's mean/std
     are discarded; decoder/seg dropout probabilities are 0 in every shipped

@@ -1,0 +1,43 @@
+"""The driver shim accepts the reference's own command lines (scripts/target/*.bash -> main_target.py:28-82)."""
+import glob
+import os
+import shlex
+
+import pytest
+
+from vae_segmentation_b200 import main_target as cli
+
+REF_SCRIPTS = "/root/reference/scripts/target"
+# argument vector of scripts/target/domain_msd_dh_ft1.bash (BASELINE.json configs[3]); kept here for boxes without the tree
+DH_FT1 = ("domain_msd_dh_ft1 -G 0 --method domain_adaptation --load_prefix seg_nih --load_prefix_vae vae_nih --train_list MSD_train "
+          "--val_list MSD_val --data_root X --val_data_root X --data_path data/Multi_all.json --pan_index 10 --lambda_vae 1.0 "
+          "--domain_loss_type 8 --val_finetune 1 --eval_epoch 2 --save_epoch 100 --max_epoch 50")
+
+
+def test_parser_accepts_the_shipped_preset():
+    a = cli.build_parser().parse_args(shlex.split(DH_FT1))
+    assert a.method == "domain_adaptation" and a.domain_loss_type == 8 and a.val_finetune == 1 and a.lambda_vae == 1.0
+    assert cli.mask_index_from(a.pan_index) == [[0, 0], [[1, 2], 1]]
+    assert cli.mask_index_from("1,3") == [[0, 0], [1, 1], [3, 2]]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SCRIPTS), reason="reference tree not present")
+def test_parser_accepts_every_reference_target_script():
+    scripts = sorted(glob.glob(os.path.join(REF_SCRIPTS, "*.bash")))
+    assert len(scripts) >= 8
+    for path in scripts:
+        text = open(path).read().replace("\\\n", " ")
+        line = [l for l in text.splitlines() if "main_target.py" in l][0]
+        argv = shlex.split(line.replace("$1", "0").replace("<Your_MSD_data_path>", "X").replace("<Your_Synapse_data_path>", "X"))
+        argv = [t for t in argv[argv.index("main_target.py") + 1:]]
+        argv = [("X" if (t.startswith("<") and t.endswith(">")) else t) for t in argv]
+        a = cli.build_parser().parse_args(argv)
+        assert a.method == "domain_adaptation", path
+
+
+def test_no_cuda_is_an_error_not_a_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(SystemExit, match="no CUDA device"):
+        cli.main(shlex.split(DH_FT1) + ["--synthetic", "2"])

@@ -257,6 +257,16 @@ def _k2s2_tc_case(case, variant):
     close(from_ndhwc(y2), F.conv_transpose3d(coarse, wq, b, stride=2), "convT fprop")
     dx2 = ops.k2s2_gather(to_ndhwc(fine), wd, None, dims, c, c, wtc=pg)
     close(from_ndhwc(dx2), F.conv3d(fine, wq, None, stride=2), "convT dgrad")
+    # weight gradient on the tensor cores (csrc/k2s2_wgrad_tc.cu): dwt[a][b][k] = sum_o coarse[o,a] fine[2o+k,b], i.e.
+    # the Conv3d weight gradient for dy = coarse, x = fine; accumulate = True adds onto the existing buffer
+    fr = fine.clone().requires_grad_(False)
+    wr = torch.zeros(c, c, 2, 2, 2, requires_grad=True)
+    F.conv3d(fr, wr, None, stride=2).backward(coarse)
+    dw = ops.k2s2_wgrad(to_ndhwc(coarse), to_ndhwc(fine), dims, c, c)
+    scale = wr.grad.abs().max().item()
+    assert (dw.cpu() - wr.grad).abs().max().item() < 2e-3 * scale + 1e-4, "k2s2 wgrad: %.3e (scale %.3e)" % ((dw.cpu() - wr.grad).abs().max().item(), scale)
+    dw2 = ops.k2s2_wgrad(to_ndhwc(coarse), to_ndhwc(fine), dims, c, c, dwt=dw.clone(), accumulate=True)
+    assert (dw2.cpu() - 2 * wr.grad).abs().max().item() < 4e-3 * scale + 2e-4
     # and against the CUDA-core kernels on the same operands
     y3 = ops.k2s2_gather(to_ndhwc(fine), wq.to(DEV), b.to(DEV), dims, c, c)
     assert (y.float() - y3.float()).abs().max().item() < 1e-2 * y3.float().abs().max().item()

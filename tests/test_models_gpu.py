@@ -558,3 +558,57 @@ def test_forward_is_reproducible_to_rounding():
         p2 = seg.predict(img.to(DEV))
     assert torch.equal(p1.argmax(1), p2.argmax(1))
     assert (p1 - p2).abs().max().item() < 1e-5
+
+
+def test_encoder_fusion_joint2_variants_vs_oracle():
+    """The remaining model variants on the same kernels (joint_model.py:274-305 Encoder, :392-436 Fusion, :454-465
+    Joint2): fp32 check mode against the oracle restatements (pinned torch.equal to the real modules by
+    tests/test_oracle.py) -- outputs 1e-4, gradients against the float64-calibrated bound."""
+    patch = 64
+    torch.manual_seed(61)
+    enc = jm.Encoder(1, 1, norm_type=1, patch=patch)
+    esd = OrderedDict((k, v.clone()) for k, v in enc.state_dict().items())
+    x = torch.rand(2, 1, patch, patch, patch)
+    leaf = OrderedDict((k, v.clone().requires_grad_()) for k, v in esd.items())
+    want = R.encoder_forward(leaf, x)
+    want.sum().backward()
+    enc = enc.to(DEV).set_precision("fp32")
+    got = enc(x.to(DEV))
+    got.sum().backward()
+    assert (got.cpu() - want.detach()).abs().max().item() < 1e-4
+    g = grads_of(enc)
+    for k in ("fc_mean.weight", "fc2.weight", "fc1.bias", "down5.conv.1.conv.6.weight", "in_block.conv.0.weight"):
+        assert rel_l2(g[k], leaf[k].grad) < 2e-2, (k, rel_l2(g[k], leaf[k].grad))
+    # Fusion
+    fus = jm.Fusion(1, 2, 2, norm_type=1)
+    fsd = OrderedDict((k, v.clone()) for k, v in fus.state_dict().items())
+    img, mask = synth_image(1, 32), R.one_hot(synth_label(1, 32))
+    with torch.no_grad():
+        want_f = R.fusion_forward(fsd, img, mask)
+    fus = fus.to(DEV).set_precision("fp32")
+    out = fus({"i": img.to(DEV), "m": mask.to(DEV)}, "i", "m", "o")["o"]
+    assert (out.cpu() - want_f).abs().max().item() < 1e-4
+    out[:, 1].mean().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in fus.parameters())
+    # Joint2 = Segmentation + discriminator on the foreground probability; bf16 path runs too
+    seg = jm.Segmentation(1, 2, norm_type=1)
+    dis = jm.Encoder(1, 1, norm_type=1, patch=patch)
+    j2 = jm.Joint2([seg, dis]).to(DEV)
+    d = j2({"img": synth_image(1, patch).to(DEV)}, "img", "pred", "score")
+    assert d["score"].shape == (1, 1) and 0.0 < d["score"].item() < 1.0
+
+
+def test_main_target_cli_shim_synthetic_run(tmp_path):
+    """vae_segmentation_b200.main_target with the flags of scripts/target/domain_msd_dh_ft1.bash on synthetic volumes:
+    trains a few iterations (dynamic lambda, EMA teacher), validates with one TTT iteration per case, writes
+    reference-format checkpoints that load strictly into a fresh Segmentation."""
+    from vae_segmentation_b200 import main_target as cli
+    root = str(tmp_path)
+    argv = ["clitest", "-G", "0", "--method", "domain_adaptation", "--lambda_vae", "1.0", "--domain_loss_type", "8",
+            "--val_finetune", "1", "--eval_epoch", "2", "--save_epoch", "2", "--max_epoch", "6", "--pseudo_save_epoch", "2",
+            "-b", "2", "--synthetic", "4", "--patch", "64", "--save_root", root]
+    assert cli.main(argv) == 0
+    ckpt = torch.load(os.path.join(root, "clitest", "model_latest.ckpt"))
+    assert set(ckpt) == {"epoch", "model_state_dict", "optimizer_state_dict"} and len(ckpt["model_state_dict"]) == 68
+    jm.Segmentation(1, 2, norm_type=1).load_state_dict(ckpt["model_state_dict"], strict=True)
+    assert os.path.isfile(os.path.join(root, "clitest", "best_model.ckpt"))

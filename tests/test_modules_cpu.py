@@ -58,3 +58,27 @@ def test_layer_programs():
     (enc, dec, fc), vparams = vae._prog()
     assert len(enc) == 1 + 5 * 4 and len(dec) == 5 * 4 + 1
     assert tuple(vparams[fc[0]].shape) == (128, 2048)
+
+
+def test_variant_modules_state_dict_matches_the_real_reference():
+    """Encoder / Fusion / Joint2 / Embed (joint_model.py:274-305,392-501): same state_dict keys and shapes as the real
+    modules, so reference checkpoints load strictly."""
+    import pytest
+    from oracle import reference_shim
+    if not reference_shim.available():
+        pytest.skip("reference tree not present")
+    rjm, _ = reference_shim.load()
+    pairs = [(joint_model.Encoder(1, 1, norm_type=1), rjm.Encoder(1, 1, norm_type=1)),
+             (joint_model.Fusion(1, 2, 2, norm_type=1), rjm.Fusion(1, 2, 2, norm_type=1))]
+    for ours, ref in pairs:
+        a, b = ours.state_dict(), ref.state_dict()
+        assert list(a.keys()) == list(b.keys())
+        assert all(a[k].shape == b[k].shape for k in a)
+        ours.load_state_dict(b, strict=True)
+    j2 = joint_model.Joint2([joint_model.Segmentation(1, 2, norm_type=1), joint_model.Encoder(1, 1, norm_type=1)])
+    r2 = rjm.Joint2([rjm.Segmentation(1, 2, norm_type=1), rjm.Encoder(1, 1, norm_type=1)])
+    assert list(j2.state_dict().keys()) == list(r2.state_dict().keys())
+    em = joint_model.Embed([joint_model.Encoder(1, 128, norm_type=1), joint_model.VAE(2, 2, norm_type=1, dim=128),
+                            joint_model.Fusion(1, 2, 2, norm_type=1)])
+    rm = rjm.Embed([rjm.Encoder(1, 128, norm_type=1), rjm.VAE(2, 2, norm_type=1, dim=128), rjm.Fusion(1, 2, 2, norm_type=1)])
+    assert list(em.state_dict().keys()) == list(rm.state_dict().keys())

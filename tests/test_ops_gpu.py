@@ -388,3 +388,37 @@ def test_clip_center_bit_exact(kind):
     assert out.dtype == torch.float32 and out.shape == x.shape
     assert torch.equal(out.cpu(), want)
     assert want.min().item() >= -1.0 and want.max().item() <= 1.0
+
+
+@pytest.mark.parametrize("case", [(40, 44, 36, (14, 12, 10), (20, 20, 18), 32, 0), (64, 64, 64, (30, 26, 28), (32, 30, 34), 32, 0),
+                                  (48, 40, 56, (10, 8, 12), (3, 36, 50), 24, 2), (36, 36, 36, None, None, 16, 0)])
+def test_crop_resize_matches_skimage_restatement(case):
+    """Device CropResize (csrc/resize.cu) against the restatement of utils/utils.py:220-293 + skimage 0.18.3 resize over
+    scipy.ndimage (oracle/ref_resize.py): image within 1e-5 of its range (float32 storage of double arithmetic on both
+    sides), label bit-exact.  Cases: downsampling (anti-aliasing filter active), upsampling, a blob touching the volume
+    border (clamped crop + the reference's centred re-padding) with a shift, and an empty label (the reference's fallback
+    cube)."""
+    import numpy as np
+    from oracle import ref_resize as RR
+    from vae_segmentation_b200.transforms import CropResize
+    d, h, w, radii, centre, out, shift = case
+    rng = np.random.RandomState(d + h + w)
+    img = (rng.randn(d, h, w) * 300 + 50).astype(np.float32)
+    zz, yy, xx = np.meshgrid(np.arange(d), np.arange(h), np.arange(w), indexing="ij")
+    if radii is None:
+        label = np.zeros((d, h, w), np.float32)
+        label_big = np.zeros((128, 128, 128), np.float32)          # the fallback cube is centred at (64,64,64): needs a big volume
+        img_big = (rng.randn(128, 128, 128) * 300).astype(np.float32)
+        img, label = img_big, label_big
+    else:
+        label = ((((zz - centre[0]) / radii[0]) ** 2 + ((yy - centre[1]) / radii[1]) ** 2 + ((xx - centre[2]) / radii[2]) ** 2) <= 1).astype(np.float32)
+    want_img, want_lab, want_shape = RR.crop_resize(img, label, [out] * 3, shift=shift)
+    dd = {"venous": torch.from_numpy(img).to(DEV), "venous_pancreas": torch.from_numpy(label).to(DEV)}
+    dd = CropResize(["venous"], [out] * 3, shift=shift)(dd)
+    torch.cuda.synchronize()
+    got_img, got_lab = dd["venous"].cpu().numpy(), dd["venous_pancreas"].cpu().numpy()
+    assert got_img.shape == want_img.shape == (out, out, out)
+    assert np.array_equal(got_lab, want_lab), "label patch differs in %d voxels" % int((got_lab != want_lab).sum())
+    scale = float(np.abs(want_img).max())
+    assert np.abs(got_img - want_img).max() < 1e-5 * scale, np.abs(got_img - want_img).max()
+    assert dd["ori_shape"].tolist() == want_shape.tolist()

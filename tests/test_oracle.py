@@ -173,3 +173,37 @@ def test_conditioned_recipe_matches_real_reference_golden(golden_dir):
     vd, vlosses = C.train_vae(K, patch=COND_CASE["patch_vae"], lr=lr)
     np.testing.assert_allclose(vlosses, g["vae_losses"], rtol=2e-4)
     np.testing.assert_allclose(C.checksum(vd)[:, 1], g["vae_checksum"][:, 1], rtol=1e-4)
+
+
+def test_resize_restatement_basic_properties():
+    """oracle.ref_resize.resize (skimage 0.18.3's n-D path over scipy.ndimage): same-size resize is the identity, constants
+    stay constant, 2x linear upsampling of a ramp interpolates at the half-sample positions, nearest picks floor(x + .5)."""
+    import numpy as np
+    from oracle import ref_resize as RR
+    rng = np.random.RandomState(0)
+    v = rng.randn(6, 7, 5).astype(np.float32)
+    assert np.allclose(RR.resize(v, v.shape), v, atol=1e-6)
+    assert np.allclose(RR.resize(np.full((9, 9, 9), 3.5, np.float32), (4, 6, 13)), 3.5, atol=1e-6)
+    ramp = np.tile(np.arange(4, dtype=np.float32)[:, None, None], (1, 2, 2))
+    up = RR.resize(ramp, (8, 2, 2))[:, 0, 0]
+    assert np.allclose(up, [0.25, 0.25, 0.75, 1.25, 1.75, 2.25, 2.75, 2.75], atol=1e-6)      # x = .5 (i + .5) - .5, mirror edges
+    lab = (rng.rand(5, 5, 5) > 0.5).astype(np.float32)
+    near = RR.resize(lab, (10, 10, 10), order=0, anti_aliasing=False)
+    assert set(np.unique(near)) <= {0.0, 1.0} and np.array_equal(near[::2, ::2, ::2], lab)     # x = .5 i - .25 -> floor(.5 i + .25)
+
+
+@needs_ref
+@pytest.mark.timeout(600)
+def test_oracle_equals_real_reference_encoder_and_fusion():
+    """The remaining model variants (joint_model.py:274-305 Encoder, :392-436 Fusion): functional restatements against
+    the real modules on the same state_dict."""
+    jm, ev = reference_shim.load()
+    torch.manual_seed(12)
+    enc = jm.Encoder(1, 1, norm_type=1)
+    x = torch.rand(1, 1, 128, 128, 128)
+    with torch.no_grad():
+        assert torch.equal(enc(x), R.encoder_forward(enc.state_dict(), x))
+    fus = jm.Fusion(1, 2, 2, norm_type=1)
+    img, mask = torch.randn(1, 1, 32, 32, 32), R.one_hot((torch.rand(1, 1, 32, 32, 32) > 0.9).float())
+    with torch.no_grad():
+        assert torch.equal(fus({"i": img, "m": mask}, "i", "m", "o")["o"], R.fusion_forward(fus.state_dict(), img, mask))

@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/c15_pytest.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/c15_pytest.log; tail -25 gpurun_out/c15_pytest.log | cut -c1-300
+timeout 600 python bench.py --mode joint --kernel-table > gpurun_out/c15_bench_joint.json 2> gpurun_out/c15_bench_joint.err
+cut -c1-200 gpurun_out/c15_bench_joint.json

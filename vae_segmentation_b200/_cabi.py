@@ -54,6 +54,8 @@ _SIGNATURES = {
     "vs_fc_decode_fwd": [_I, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "vs_fc_decode_bwd": [_I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "vs_fc_encode_bwd": [_I, _P, _P, _P, _P, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "vs_linear_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "vs_linear_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "vs_dice_sums": [_P, _P, _I, _P, _I, _I, _L, _P],
     "vs_dice_bwd": [_P, _P, _I, _P, _P, _F, _P, _P, _I, _I, _I, _L, _P],
     "vs_kl_fwd": [_P, _P, _P, _I, _I, _P],
@@ -61,6 +63,8 @@ _SIGNATURES = {
     "vs_binarize": [_P, _P, _I, _L, _P],
     "vs_one_hot": [_P, _P, _I, _I, _L, _P],
     "vs_clip_center": [_I, _P, _P, _L, _F, _F, _F, _F, _P],
+    "vs_crop_resize": [_P, _I, _I, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P],
+    "vs_gauss_radius": [ctypes.c_double],
     "vs_sgd_step": [_P, _P, _P, _L, _F, _F, _I, _F, _P],
     "vs_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _P],
     "vs_ema_update": [_P, _P, _L, _F, _P],

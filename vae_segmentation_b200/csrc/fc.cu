@@ -272,3 +272,120 @@ extern "C" int vs_fc_encode_bwd(int dtype, const void* x, const float* wm, const
     VS_CHECK_LAUNCH("fc_encode_bwd_kernel");
     return VS_OK;
 }
+
+// ---- generic Linear (+ activation) for the discriminator / encoder head (joint_model.py:287-304: fc1, fc2, fc_mean) --------
+// y[b][o] = act(bias[o] + sum_i W[o][i] x[b][i]); act 0 = identity, 1 = ReLU, 2 = sigmoid.  Batch <= 8 rows per pass:
+// weight-bandwidth-bound (W is read once), one warp per output row.
+namespace {
+
+__device__ __forceinline__ float act_fwd(float v, int act) {
+    if (act == 1) return fmaxf(v, 0.f);
+    if (act == 2) return 1.f / (1.f + expf(-v));
+    return v;
+}
+// derivative expressed through the OUTPUT y (what the backward pass has at hand)
+__device__ __forceinline__ float act_bwd(float y, int act) {
+    if (act == 1) return y > 0.f ? 1.f : 0.f;
+    if (act == 2) return y * (1.f - y);
+    return 1.f;
+}
+
+__global__ void __launch_bounds__(NT) linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, float* __restrict__ y, int batch,
+                                                        int in_f, int out_f, int act) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int o = blockIdx.x * (NT / 32) + warp; o < out_f; o += gridDim.x * (NT / 32)) {
+        const float* wr = w + (long long)o * in_f;
+        for (int b0 = 0; b0 < batch; b0 += MAXB) {
+            const int nb = min(MAXB, batch - b0);
+            float acc[MAXB];
+#pragma unroll
+            for (int b = 0; b < MAXB; ++b) acc[b] = 0.f;
+            for (int i = lane; i < in_f; i += 32) {
+                const float wv = wr[i];
+#pragma unroll
+                for (int b = 0; b < MAXB; ++b)
+                    if (b < nb) acc[b] = fmaf(wv, x[(long long)(b0 + b) * in_f + i], acc[b]);
+            }
+#pragma unroll
+            for (int b = 0; b < MAXB; ++b) {
+                const float s = warp_sum(acc[b]);
+                if (lane == 0 && b < nb) y[(long long)(b0 + b) * out_f + o] = act_fwd(s + (bias ? bias[o] : 0.f), act);
+            }
+        }
+    }
+}
+
+// g[b][o] = dy[b][o] * act'(y[b][o]);  db[o] (+)= sum_b g
+__global__ void __launch_bounds__(NT) linear_bwd_prep_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                                             float* __restrict__ g, float* __restrict__ db, int accumulate,
+                                                             int batch, int out_f, int act) {
+    const int o = blockIdx.x * NT + threadIdx.x;
+    if (o >= out_f) return;
+    float s = 0.f;
+    for (int b = 0; b < batch; ++b) {
+        const float v = dy[(long long)b * out_f + o] * act_bwd(y[(long long)b * out_f + o], act);
+        g[(long long)b * out_f + o] = v;
+        s += v;
+    }
+    if (db != nullptr) db[o] = accumulate ? db[o] + s : s;
+}
+
+// dx[b][i] = sum_o g[b][o] W[o][i]  and  dW[o][i] (+)= sum_b g[b][o] x[b][i]; thread = input column i (coalesced over W rows)
+__global__ void __launch_bounds__(NT) linear_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ g, float* __restrict__ dx,
+                                                        float* __restrict__ dw, int accumulate, int batch, int in_f, int out_f) {
+    const int i = blockIdx.x * NT + threadIdx.x;
+    if (i >= in_f) return;
+    for (int b0 = 0; b0 < batch; b0 += MAXB) {
+        const int nb = min(MAXB, batch - b0);
+        float xv[MAXB], acc[MAXB];
+#pragma unroll
+        for (int b = 0; b < MAXB; ++b) { xv[b] = (b < nb && x != nullptr) ? x[(long long)(b0 + b) * in_f + i] : 0.f; acc[b] = 0.f; }
+        for (int o = 0; o < out_f; ++o) {
+            const float wv = w[(long long)o * in_f + i];
+            float dwv = 0.f;
+#pragma unroll
+            for (int b = 0; b < MAXB; ++b) {
+                if (b < nb) {
+                    const float gv = g[(long long)(b0 + b) * out_f + o];          // warp-uniform address: broadcast
+                    acc[b] = fmaf(gv, wv, acc[b]);
+                    dwv = fmaf(gv, xv[b], dwv);
+                }
+            }
+            if (dw != nullptr) {
+                float* p = dw + (long long)o * in_f + i;
+                *p = (accumulate || b0 > 0) ? *p + dwv : dwv;
+            }
+        }
+        if (dx != nullptr) {
+#pragma unroll
+            for (int b = 0; b < MAXB; ++b)
+                if (b < nb) dx[(long long)(b0 + b) * in_f + i] = acc[b];
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int vs_linear_fwd(const float* x, const float* w, const float* bias, float* y, int batch, int in_f, int out_f,
+                             int act, void* stream) {
+    VS_REQUIRE(x && w && y && batch > 0 && in_f > 0 && out_f > 0 && act >= 0 && act <= 2, VS_ERR_SHAPE, "linear_fwd: bad arguments");
+    const int blocks = min(vs_ceil_div(out_f, NT / 32), vs_sm_count() * 8);
+    linear_fwd_kernel<<<blocks, NT, 0, (cudaStream_t)stream>>>(x, w, bias, y, batch, in_f, out_f, act);
+    VS_CHECK_LAUNCH("linear_fwd_kernel");
+    return VS_OK;
+}
+
+extern "C" int vs_linear_bwd(const float* x, const float* w, const float* y, const float* dy, float* gbuf, float* dx, float* dw,
+                             float* db, int accumulate, int batch, int in_f, int out_f, int act, void* stream) {
+    VS_REQUIRE(w && y && dy && gbuf && batch > 0 && in_f > 0 && out_f > 0 && act >= 0 && act <= 2, VS_ERR_SHAPE, "linear_bwd: bad arguments");
+    VS_REQUIRE(dw == nullptr || x != nullptr, VS_ERR_SHAPE, "linear_bwd: the weight gradient needs x");
+    cudaStream_t st = (cudaStream_t)stream;
+    linear_bwd_prep_kernel<<<vs_ceil_div(out_f, NT), NT, 0, st>>>(dy, y, gbuf, db, accumulate, batch, out_f, act);
+    VS_CHECK_LAUNCH("linear_bwd_prep_kernel");
+    if (dx == nullptr && dw == nullptr) return VS_OK;
+    linear_bwd_kernel<<<vs_ceil_div(in_f, NT), NT, 0, st>>>(x, w, gbuf, dx, dw, accumulate, batch, in_f, out_f);
+    VS_CHECK_LAUNCH("linear_bwd_kernel");
+    return VS_OK;
+}

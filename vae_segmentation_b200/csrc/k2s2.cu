@@ -349,6 +349,12 @@ int check_k2(const void* p0, const void* p1, const void* p2, int n, int dc, int 
 }  // namespace
 
 extern "C" void vs_debug_set_k2_ksplit_max(int v) { g_k2_ksplit_max = v; }
+#ifdef VS_WITH_TCGEN05
+extern "C" int vs_k2s2_wgrad_tc(const void* coarse, const void* fine, float* dwt, int accumulate, int n, int dc, int hc,
+                                int wc, int a, int b, void* stream);
+#endif
+static int g_k2_wgrad_tc = 1;      // A/B switch: weight gradient on the tensor cores (bf16 operands) or the CUDA-core kernel
+extern "C" void vs_debug_set_k2_wgrad_tc(int on) { g_k2_wgrad_tc = on; }
 
 extern "C" int vs_k2s2_gather(int dtype, const void* fine, const float* wt, const float* bias, void* coarse,
                               int n, int dc, int hc, int wc, int a, int b, void* stream) {
@@ -410,11 +416,24 @@ extern "C" int vs_k2s2_wgrad(int dtype, const void* coarse, const void* fine, fl
     K2Dims p = {n, dc, hc, wc, a, b};
     const long long total = (long long)n * dc * hc * wc;
     cudaStream_t st = (cudaStream_t)stream;
+    bool tc = false;
+#ifdef VS_WITH_TCGEN05
+    tc = g_k2_wgrad_tc && dtype == VS_BF16 && a <= 256 && b <= 256 && (a == 8 || a % 16 == 0) && (b == 8 || b % 16 == 0);
+#endif
     if (!accumulate) {
-        VS_CUDA(cudaMemsetAsync(dwt, 0, sizeof(float) * 8 * a * b, st), "k2s2 wgrad memset");
+        if (!tc) VS_CUDA(cudaMemsetAsync(dwt, 0, sizeof(float) * 8 * a * b, st), "k2s2 wgrad memset");
         if (dbias_coarse) VS_CUDA(cudaMemsetAsync(dbias_coarse, 0, sizeof(float) * a, st), "k2s2 wgrad memset");
         if (dbias_fine) VS_CUDA(cudaMemsetAsync(dbias_fine, 0, sizeof(float) * b, st), "k2s2 wgrad memset");
     }
+#ifdef VS_WITH_TCGEN05
+    if (tc) {
+        rc = vs_k2s2_wgrad_tc(coarse, fine, dwt, accumulate, n, dc, hc, wc, a, b, stream);
+        if (rc) return rc;
+        if (dbias_coarse) { rc = channel_sum<bf16>((const bf16*)coarse, dbias_coarse, total, a, st); if (rc) return rc; }
+        if (dbias_fine) { rc = channel_sum<bf16>((const bf16*)fine, dbias_fine, total * 8, b, st); if (rc) return rc; }
+        return VS_OK;
+    }
+#endif
     VS_DISPATCH_DTYPE(dtype, T, {
         dim3 grid(1, a / 8, b / 8);
         const long long blocks = (long long)grid.y * grid.z;

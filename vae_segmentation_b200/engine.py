@@ -638,3 +638,35 @@ class DecodeFn(torch.autograd.Function):
         else:
             dlat = ops.fc_decode_bwd(dh, lat, w2_, n, s3, c, dim)
         return (None, dlat if ctx.needs_input_grad[1] else None) + tuple(grads)
+
+
+class LinearFn(torch.autograd.Function):
+    """y = act(x @ W.T + b) through vs_linear_fwd / vs_linear_bwd (the encoder / discriminator head,
+    joint_model.py:287-304)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act):
+        x = x.contiguous().float()
+        y = ops.linear_fwd(x, w.detach(), b.detach(), act)
+        ctx.save_for_backward(x, w.detach(), y)
+        ctx.act = act
+        ctx.refs = (w, b)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        wref, bref = ctx.refs
+        need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        tw, aw = _grad_target(wref, need_w)
+        tb, ab = _grad_target(bref, need_b)
+        if need_w and tw is None:
+            tw = torch.empty_like(w)
+        if need_b and tb is None:
+            tb = torch.empty_like(y[0])
+        acc = bool(aw and (ab or not need_b))
+        if need_w and need_b and aw != ab:
+            raise RuntimeError("Linear weight and bias must both have (or both lack) a .grad buffer")
+        dx = ops.linear_bwd(x, w, y, dy.contiguous(), ctx.act, want_dx=need_x, dw=tw if need_w else None,
+                            db=tb if need_b else None, accumulate=acc)
+        return dx, (None if (acc or not need_w) else tw), (None if (acc or not need_b) else tb), None

@@ -387,6 +387,153 @@ class VAE(_Engineered):
                                   bool(if_random), *params)
 
 
+class Encoder(_Engineered):
+    # joint_model.py:274-305 -- conv trunk (in_block + five Down) -> fc1 -> ReLU -> fc2 -> ReLU -> fc_mean -> sigmoid;
+    # the discriminator of `Joint2` and the latent predictor of `Embed`.  `patch` generalises the hard-coded 16384
+    # (= 256 * 4^3 at 128^3 patches) like VAE.patch.
+    def __init__(self, n_channels, dim, norm_type=2, n_fmaps=[8, 16, 32, 64, 128, 256], soft=False, patch=128):
+        super().__init__()
+        if patch % 32:
+            raise ValueError("Encoder patch size must be divisible by 32 (five stride-2 levels)")
+        f = list(n_fmaps)
+        self.n_fmaps, self.n_channels, self.patch, self.side = f, n_channels, patch, patch // 32
+        flat = f[5] * self.side ** 3
+        self.in_block = Conv(n_channels, f[0], norm_type=norm_type, soft=False)
+        self.down1 = Down(f[0], f[1], norm_type=norm_type, soft=False)
+        self.down2 = Down(f[1], f[2], norm_type=norm_type, soft=False)
+        self.down3 = Down(f[2], f[3], norm_type=norm_type, soft=False)
+        self.down4 = Down(f[3], f[4], norm_type=norm_type, soft=False)
+        self.down5 = Down(f[4], f[5], norm_type=norm_type, soft=False)
+        self.fc1 = _LinearParams(flat, 1024)
+        self.fc2 = _LinearParams(1024, 128)
+        self.fc_mean = _LinearParams(128, dim)
+        self._engine_init()
+
+    def _build(self, idx):
+        f = self.n_fmaps
+        ls = _conv_layers(idx, "in_block.conv.0", self.n_channels, f[0], in_planar=True)
+        for i in range(1, 6):
+            ls += _down_layers(idx, "down%d" % i, f[i - 1], f[i])
+        return ls
+
+    def forward(self, x):
+        _check_input(x, "Encoder")
+        if self.n_channels > 2:
+            raise NotImplementedError("Encoder: the planar in-block kernel takes 1 or 2 input channels")
+        layers, params = self._prog()
+        h = engine.ProgramFn.apply((layers, self.compute_dtype, self._cache, params, torch.is_grad_enabled()), x.contiguous(), *params)
+        # internal NDHWC -> the reference's NCDHW flatten order (x.view(B, 16384)); a [B, 256 * side^3] tensor: not hot
+        h = h.permute(0, 4, 1, 2, 3).reshape(h.shape[0], -1).float()
+        h = engine.LinearFn.apply(h, self.fc1.weight, self.fc1.bias, engine.ops.ACT_RELU)
+        h = engine.LinearFn.apply(h, self.fc2.weight, self.fc2.bias, engine.ops.ACT_RELU)
+        return engine.LinearFn.apply(h, self.fc_mean.weight, self.fc_mean.bias, engine.ops.ACT_SIGMOID)
+
+
+class Fusion(_Engineered):
+    # joint_model.py:392-436 -- two in-block + Down branches (image, mask) summed, a merge Conv, then the Segmentation
+    # trunk from down2 on with the same two additive skips
+    def __init__(self, n_channels_img, n_channels_mask, n_class, norm_type=2, n_fmaps=[8, 16, 32, 64, 128, 256]):
+        super().__init__()
+        if n_class != 2:
+            raise NotImplementedError("vaeseg_b200 implements the 2-class softmax head only (n_class=%r)" % (n_class,))
+        f = list(n_fmaps)
+        self.n_fmaps, self.n_class = f, n_class
+        self.n_channels_img, self.n_channels_mask = n_channels_img, n_channels_mask
+        self.in_block = Conv(n_channels_img, f[0], norm_type=norm_type, soft=False)
+        self.down1 = Down(f[0], f[1], norm_type=norm_type, soft=False)
+        self.in_block_mask = Conv(n_channels_mask, f[0], norm_type=norm_type, soft=False)
+        self.down1_mask = Down(f[0], f[1], norm_type=norm_type, soft=False)
+        self.merge = Conv(f[1], f[1], norm_type=norm_type, soft=False)
+        self.down2 = Down(f[1], f[2], norm_type=norm_type, soft=False)
+        self.down3 = Down(f[2], f[3], norm_type=norm_type, soft=False)
+        self.down4 = Down(f[3], f[4], norm_type=norm_type, soft=False)
+        self.up2 = Up(f[4], f[3], norm_type=norm_type, soft=False)
+        self.up3 = Up(f[3], f[2], norm_type=norm_type, soft=False)
+        self.up4 = Up(f[2], f[1], norm_type=norm_type, soft=False)
+        self.up5 = Up(f[1], f[0], norm_type=norm_type, soft=False)
+        self.out_block = _ConvParams(f[0], n_class, 3)
+        self.final = _Fused("Softmax(dim=1)")
+        self._engine_init()
+
+    def _build(self, idx):
+        f = self.n_fmaps
+        img = _conv_layers(idx, "in_block.conv.0", self.n_channels_img, f[0], in_planar=True) + _down_layers(idx, "down1", f[0], f[1])
+        mask = _conv_layers(idx, "in_block_mask.conv.0", self.n_channels_mask, f[0], in_planar=True) + \
+            _down_layers(idx, "down1_mask", f[0], f[1])
+        trunk = _conv_layers(idx, "merge.conv.0", f[1], f[1], save_as="x2")
+        trunk += _down_layers(idx, "down2", f[1], f[2], save_as="x3")
+        trunk += _down_layers(idx, "down3", f[2], f[3])
+        trunk += _down_layers(idx, "down4", f[3], f[4])
+        trunk += _up_layers(idx, "up2", f[4], f[3])
+        trunk += _up_layers(idx, "up3", f[3], f[2], skip_from="x3")
+        trunk += _up_layers(idx, "up4", f[2], f[1], skip_from="x2")
+        trunk += _up_layers(idx, "up5", f[1], f[0])
+        trunk += [Layer(HEAD, "out_block", f[0], self.n_class, idx["out_block.weight"], idx["out_block.bias"])]
+        return img, mask, trunk
+
+    def forward(self, data_dict, in_key_img, in_key_mask, out_key):
+        x_img, x_mask = data_dict[in_key_img], data_dict[in_key_mask]
+        _check_input(x_img, "Fusion")
+        _check_input(x_mask, "Fusion")
+        (img, mask, trunk), params = self._prog()
+        spec = lambda ls: (ls, self.compute_dtype, self._cache, params, torch.is_grad_enabled())
+        a = engine.ProgramFn.apply(spec(img), x_img.contiguous(), *params)
+        b = engine.ProgramFn.apply(spec(mask), x_mask.contiguous(), *params)
+        data_dict[out_key] = engine.ProgramFn.apply(spec(trunk), a + b, *params)      # x2_img + x2_mask, joint_model.py:424
+        return data_dict
+
+
+class Joint2(_Engineered):
+    # joint_model.py:454-465 -- segmentation + discriminator on the foreground probability
+    def __init__(self, models, seg_dropout=0.0):
+        super().__init__()
+        self.Seg = models[0]
+        self.Dis = models[1]
+        self.seg_dropout = seg_dropout
+        self._engine_init()
+
+    def forward(self, data_dict, in_key, out_key, score_key, dropout=False):
+        if dropout:
+            data_dict = self.Seg(data_dict, in_key, out_key, dropout=self.seg_dropout)
+        else:
+            data_dict = self.Seg(data_dict, in_key, out_key)
+        data_dict[score_key] = self.Dis(data_dict[out_key][:, 1:2, :, :, :].contiguous())
+        return data_dict
+
+
+class Embed(_Engineered):
+    # joint_model.py:468-501
+    def __init__(self, models):
+        super().__init__()
+        self.Encoder = models[0]
+        self.Vae = models[1]
+        self.Fusion = models[2]
+        self._engine_init()
+
+    def forward(self, data_dict, in_key, out_key, test_mode=False, loop_input=None, seg_input=None, latent_input=None):
+        if latent_input:
+            data_dict["latent_code"] = data_dict[latent_input]
+        else:
+            data_dict["latent_code"] = self.Encoder(data_dict[in_key])
+        data_dict["gt_recon"], data_dict["latent_code_gt"], data_dict["latent_code_std"] = self.Vae(
+            data_dict["venous_pancreas_only"], if_random=True, scale=0.5, mid_input=False)
+        if loop_input:
+            data_dict[loop_input], data_dict["latent_code_loop"], _ = self.Vae(data_dict[loop_input], if_random=False, scale=0,
+                                                                               mid_input=False)
+        if seg_input:
+            data_dict["init_seg"] = data_dict[seg_input]
+        else:
+            data_dict["init_seg"] = self.Vae(data_dict["latent_code"], if_random=False, scale=0, mid_input=True)
+        if loop_input:
+            data_dict = self.Fusion(data_dict, in_key, loop_input, out_key)
+        elif test_mode:
+            data_dict = self.Fusion(data_dict, in_key, "init_seg", out_key)
+        else:
+            data_dict = self.Fusion(data_dict, in_key, "gt_recon", out_key)
+        data_dict["seg_recon"], _, _ = self.Vae(data_dict["init_seg"].detach(), if_random=False, scale=0, mid_input=False)
+        return data_dict
+
+
 class Joint(_Engineered):
     # joint_model.py:438-452
     def __init__(self, models, vae_forward_scale=0.0, vae_decoder_dropout=0.0, seg_dropout=0.0):

@@ -334,6 +334,26 @@ def fc_encode_bwd(x, wm, ws, z, scale, use_z, std, dlat, gmean_ext, gstd_ext, ba
     return dx
 
 
+ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
+
+
+def linear_fwd(x, w, bias, act=ACT_NONE):
+    """y = act(x @ w.T + bias); x [B,in] fp32, w [out,in] fp32."""
+    y = torch.empty(x.shape[0], w.shape[0], device=x.device, dtype=torch.float32)
+    _cabi.call("vs_linear_fwd", _p(_f32(x, "x")), _p(_f32(w, "w")), _p(_f32(bias, "bias")), _p(y), x.shape[0], w.shape[1],
+               w.shape[0], int(act), _stream())
+    return y
+
+
+def linear_bwd(x, w, y, dy, act=ACT_NONE, want_dx=True, dw=None, db=None, accumulate=False):
+    """Returns dx (or None); dw / db (+)= in place when given."""
+    gbuf = torch.empty_like(y)
+    dx = torch.empty_like(x) if want_dx else None
+    _cabi.call("vs_linear_bwd", _p(x), _p(w), _p(y), _p(_f32(dy, "dy")), _p(gbuf), _p(dx), _p(dw), _p(db), int(accumulate),
+               x.shape[0], w.shape[1], w.shape[0], int(act), _stream())
+    return dx
+
+
 # ---- losses ----------------------------------------------------------------------------
 def dice_sums(src, tgt, mode):
     n, c = src.shape[0], src.shape[1]
@@ -427,6 +447,23 @@ def clip_center(x, lo, hi, sub, div):
         raise RuntimeError("vaeseg_b200: clip_center takes float32 or int16 volumes, got %s" % x.dtype)
     out = torch.empty(x.shape, device=x.device, dtype=torch.float32)
     _cabi.call("vs_clip_center", kind, _p(x), _p(out), x.numel(), float(lo), float(hi), float(sub), float(div), _stream())
+    return out
+
+
+def crop_resize(src, crop9, side, out_size, order=1, anti_alias=True):
+    """src [D,H,W] fp32 CUDA volume -> [od,oh,ow]: crop (start[3], length[3], leading pad[3]) inside a zero cube of side
+    `side`, then skimage-style resize (see vs_crop_resize).  Data-pipeline op (allocates its workspaces per call)."""
+    import ctypes
+    if src.dim() != 3:
+        raise RuntimeError("vaeseg_b200: crop_resize takes one [D,H,W] volume")
+    od, oh, ow = [int(v) for v in out_size]
+    out = torch.empty(od, oh, ow, device=src.device, dtype=torch.float32)
+    need_filter = anti_alias and any(side > o for o in (od, oh, ow))
+    tmp0 = torch.empty(side ** 3, device=src.device, dtype=torch.float32) if need_filter else None
+    tmp1 = torch.empty_like(tmp0) if need_filter else None
+    arr = (ctypes.c_int * 9)(*[int(v) for v in crop9])
+    _cabi.call("vs_crop_resize", _p(_f32(src, "volume")), src.shape[0], src.shape[1], src.shape[2], arr, int(side), _p(out),
+               od, oh, ow, int(order), int(bool(anti_alias)), _p(tmp0), _p(tmp1), _stream())
     return out
 
 
