@@ -68,7 +68,7 @@ typedef struct {
     long long kdn_elems;
     int kind;             /* 0: 3x3x3 layer (fields above).  1: 2x2x2 stride-2 layer: w = wt[A][B][8] with A = cout,
                            * B = cin; tcf = gather pack, tcd = scatter pack (vs_k2s2_tc_pack_bytes()/2 elements)   */
-    int reserved;
+    int kdn_dgrad;        /* the kd-in-N pack is the dgrad one (flipped taps, channels swapped)         */
 } vs_pack_job;
 int vs_pack_conv3_batched(const void* jobs_dev, int njobs, void* stream);
 /* One padded pack: master weight [cout][cin][27], pack built for cin_pad >= cin / cout_pad >= cout channels (zeros);
@@ -109,15 +109,18 @@ int vs_conv3x3x3_dgrad(int in_dtype, int out_dtype, int out_planar,
  * zero-padded to 8); bias fp32 [2] or NULL.  Replaces Conv3d + nn.Softmax(dim=1) at joint_model.py:224-225,366-367. */
 int vs_head_conv_softmax2_fwd(const void* x, const void* wtc8, const float* bias, float* probs,
                               int n, int d, int h, int w, int cin, void* stream);
-/* EXPERIMENTAL, not used by the default path: "kd-in-N" variant of the tensor-core convolution for
- * Cout in {8, 16} and D >= 4 -- MMAs issued per input plane with the three kd taps side by side in N, halving the
+/* "kd-in-N" variant of the tensor-core convolution for GEMM outputs of 8 or 16 channels and D >= 4 (the full-resolution
+ * layers, forward and input gradient) -- MMAs issued per input plane with the three kd taps side by side in N, halving the
  * shared-memory operand traffic.  Same contract as the tensor-core branch of vs_conv3x3x3_fprop / _dgrad (bf16 NDHWC in
- * and out, optional shift + statistics), with its own weight pack.  vs_conv3_tc_kdn_pack_bytes() returns 0 for shapes it
- * does not take.  Only built with the tcgen05 kernels.                                                            */
+ * and out, optional shift + statistics; _ex: the fused norm-backward reduction of the previous layer, psums pre-zeroed
+ * by the caller), with its own weight pack.  vs_conv3_tc_kdn_pack_bytes() returns 0 for shapes it does not take.   */
 size_t vs_conv3_tc_kdn_pack_bytes(int cin, int cout, int dgrad);
 int vs_pack_conv3_weight_tc_kdn(const float* w, void* out, int cin, int cout, int dgrad, void* stream);
 int vs_conv3x3x3_tc_kdn(const void* x, const void* wkdn, void* y, double* stats, float* shift, int prezeroed,
                         int n, int d, int h, int w, int gin, int gout, void* stream);
+int vs_conv3x3x3_tc_kdn_ex(const void* x, const void* wkdn, void* y, double* stats, float* shift, int prezeroed,
+                           const void* yprev, const double* pstats, double* psums,
+                           int n, int d, int h, int w, int gin, int gout, void* stream);
 /* dw[Cout,Cin,27] (+)= sum_v dy[v,co] * x[v+tap,ci]; db[Cout] (+)= sum_v dy (db may be NULL).
  * x may be planar fp32 (in_planar=1).  accumulate=0 overwrites.  workspace: fp32
  * vs_conv3_wgrad_workspace_bytes() bytes (partial sums).                                 */

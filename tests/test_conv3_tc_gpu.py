@@ -205,6 +205,20 @@ def test_tc_kdn_fprop_and_dgrad(case):
         dx, _ = ops.conv3_tc_kdn(to_ndhwc(gy), wkd, dims, cout, cin, want_stats=False)
         torch.cuda.synchronize()
         assert (from_ndhwc(dx) - dx_ref).abs().max().item() < 1e-2 * dx_ref.abs().max().item()
+        # dgrad with the previous layer's InstanceNorm-backward sums fused into the epilogue == the standalone reduction
+        import vae_segmentation_b200._cabi as cabi
+        yprev = (torch.randn(n, cin, d, h, w) * 1.5 + 0.3).bfloat16().float()
+        pst = torch.stack([yprev.double().sum((2, 3, 4)), (yprev.double() ** 2).sum((2, 3, 4))], -1).to(DEV)
+        ypd = to_ndhwc(yprev)
+        sums = torch.zeros(n, cin, 2, device=DEV, dtype=torch.float64)
+        dx2, _ = ops.conv3_tc_kdn(to_ndhwc(gy), wkd, dims, cout, cin, prev=(ypd, pst, sums))
+        sums_ref = torch.empty(n, cin, 2, device=DEV, dtype=torch.float64)
+        cabi.call("vs_inorm_relu_bwd_reduce", cabi.VS_BF16, dx2.data_ptr(), ypd.data_ptr(), pst.data_ptr(), sums_ref.data_ptr(),
+                  n, d * h * w, cin, 0, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert (dx2.float() - dx.float()).abs().max().item() < 1e-3 * dx_ref.abs().max().item()     # issue-order rounding only
+        sc = sums_ref.abs().max().item() + 1e-6
+        assert (sums - sums_ref).abs().max().item() < 2e-5 * sc + 1e-4, (sums - sums_ref).abs().max().item()
 
 
 K2_TC_CASES = [(2, 3, 4, 5, 8), (1, 2, 17, 9, 16), (1, 1, 2, 2, 64), (1, 3, 3, 3, 32), (2, 2, 6, 6, 128), (1, 2, 3, 3, 256),
@@ -220,6 +234,7 @@ def test_k2s2_tensor_core_gather_and_scatter(case, variant):
         _k2s2_tc_case(case, variant)
     finally:
         ctypes.CDLL(_cabi.LIB_PATH).vs_debug_set_k2_tc(1)
+        ctypes.CDLL(_cabi.LIB_PATH).vs_debug_set_k2_wgrad_tc(1)
 
 
 def _k2s2_tc_case(case, variant):
@@ -259,6 +274,7 @@ def _k2s2_tc_case(case, variant):
     close(from_ndhwc(dx2), F.conv3d(fine, wq, None, stride=2), "convT dgrad")
     # weight gradient on the tensor cores (csrc/k2s2_wgrad_tc.cu): dwt[a][b][k] = sum_o coarse[o,a] fine[2o+k,b], i.e.
     # the Conv3d weight gradient for dy = coarse, x = fine; accumulate = True adds onto the existing buffer
+    ctypes.CDLL(_cabi.LIB_PATH).vs_debug_set_k2_wgrad_tc(2)          # force the tensor-core kernel at these small shapes
     fr = fine.clone().requires_grad_(False)
     wr = torch.zeros(c, c, 2, 2, 2, requires_grad=True)
     F.conv3d(fr, wr, None, stride=2).backward(coarse)

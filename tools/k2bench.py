@@ -38,7 +38,7 @@ def timeit(fns):
 
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 96
 N = 2
-print("%-8s %6s %4s %9s %9s %9s %9s %8s" % ("op", "coarse", "C", "cuda us", "tc0 us", "tc us", "GB/s", "frac"))
+print("%-8s %6s %4s %9s %9s %9s %9s %8s   (wgrad: cuda = CUDA-core kernel, tc0 = tc = tensor-core kernel, no bias sums)" % ("op", "coarse", "C", "cuda us", "tc0 us", "tc us", "GB/s", "frac"))
 shapes = []
 side, c = P // 2, 8
 while side >= 3 and c <= 256:                      # Down path: C at 2*side -> side
@@ -60,14 +60,19 @@ for side, c in sorted(set(shapes), key=lambda t: (-t[0], t[1])):
     ps = ops.pack_k2s2_weight_tc(w, c, c, True)
     dims = (N, side, side, side)
     byts = (fines[0].numel() + coarses[0].numel()) * 2
-    for name in ("gather", "scatter"):
+    for name in ("gather", "scatter", "wgrad"):
         if name == "gather":
             cuda = [lambda f=f: ops.k2s2_gather(f, w, b, dims, c, c) for f in fines]
             tc = [lambda f=f: ops.k2s2_gather(f, w, b, dims, c, c, wtc=pg) for f in fines]
-        else:
+        elif name == "scatter":
             cuda = [lambda x=x: ops.k2s2_scatter(x, w, b, dims, c, c) for x in coarses]
             tc = [lambda x=x: ops.k2s2_scatter(x, w, b, dims, c, c, wtc=ps) for x in coarses]
+        else:
+            dws = [torch.zeros(c, c, 2, 2, 2, device=dev) for _ in coarses]
+            cuda = tc = [lambda x=x, f=f, d=d: ops.k2s2_wgrad(x, f, dims, c, c, dwt=d, accumulate=True) for x, f, d in zip(coarses, fines, dws)]
+            handle.vs_debug_set_k2_wgrad_tc(0)
         t_cuda = timeit(cuda)
+        handle.vs_debug_set_k2_wgrad_tc(1)
         handle.vs_debug_set_k2_tc(0)
         t_tc0 = timeit(tc)
         handle.vs_debug_set_k2_tc(1)

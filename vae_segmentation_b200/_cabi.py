@@ -8,7 +8,7 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_longlong, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libvaeseg_b200.so")
+LIB_PATH = os.environ.get("VAESEG_LIB") or os.path.join(_HERE, "csrc", "libvaeseg_b200.so")      # VAESEG_LIB: A/B builds (tools)
 
 VS_F32, VS_BF16 = 0, 1
 VS_FLAG_PREZEROED = 1
@@ -31,6 +31,7 @@ _SIGNATURES = {
     "vs_conv3_tc_kdn_pack_bytes": [_I, _I, _I],
     "vs_pack_conv3_weight_tc_kdn": [_P, _P, _I, _I, _I, _P],
     "vs_conv3x3x3_tc_kdn": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "vs_conv3x3x3_tc_kdn_ex": [_P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "vs_conv3x3x3_fprop": [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "vs_conv3x3x3_dgrad": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "vs_conv3_wgrad_workspace_bytes": [_I, _I, _I, _I, _I, _I],

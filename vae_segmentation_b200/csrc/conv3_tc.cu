@@ -674,7 +674,7 @@ __global__ void __launch_bounds__(256) pack_batched_kernel(const vs_pack_job* __
     }
     if (j.kdn != nullptr) {
         bf16* o = (bf16*)j.kdn;
-        for (long long i = t0; i < j.kdn_elems; i += stride) o[i] = __float2bfloat16_rn(pack_kdn_elem(w, i, cin, cout, 0));
+        for (long long i = t0; i < j.kdn_elems; i += stride) o[i] = __float2bfloat16_rn(pack_kdn_elem(w, i, cin, cout, j.kdn_dgrad));
     }
 }
 

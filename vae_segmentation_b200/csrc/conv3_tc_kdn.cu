@@ -1,5 +1,5 @@
-// EXPERIMENTAL (round-2 groundwork, NOT on the default path, first GPU run pending -- see DESIGN.md section 10):
-// "kd-in-N" variant of the tcgen05 3x3x3 convolution for the full-resolution layers (Cout = 8 or 16).
+// "kd-in-N" variant of the tcgen05 3x3x3 convolution for the full-resolution layers (Cout = 8 or 16): the default kernel
+// for their forward AND input-gradient passes (engine.USE_KDN).
 //
 // conv3_tc.cu issues, for each of the 4 output planes of a tile, all 27 taps: every input voxel's A operand is fetched
 // 27 x from shared memory, which is what bounds those layers once the epilogue is out of the way (operand pipe 58 %).
@@ -20,8 +20,17 @@
 // up exactly, tcgen05.st zeroes an accumulator.
 // Per tile and 16-channel slice: 30 (Cin = 8) / 54 MMAs instead of 56 / 108, A-operand traffic halved.
 //
-// v1 feature set: bf16 NDHWC output, optional shift + fp64 InstanceNorm statistics (fprop) or plain (dgrad); tiles of
-// 4 d-planes only (volumes with D >= 4); no fused norm-backward reduction, no planar (head) epilogue.
+// Feature set: bf16 NDHWC output; fprop: shift + fp64 InstanceNorm statistics; dgrad: optionally the PREVIOUS layer's
+// InstanceNorm-backward sums fused into the epilogue (as conv3_tc.cu); tiles of 4 d-planes only (volumes with D >= 4);
+// no planar (head) epilogue.
+// What bounds it (profiles/r2_kdn_phase_probe.txt, clock64 stamps around a steady-state tile): the MMAs themselves.
+// A tile of 512 voxels is 30 (Cin = 8) / 54 MMAs at N = 32, each paced by its 4 KB A-operand read from shared memory
+// (~40 cycles): ~1250 cycles per tile, which the epilogue (one warpgroup, ~1100 cycles of stores + 850 of decode and
+// prefetch, overlapped through 3-4 TMEM buffers) just keeps up with.  Tried and measured (same profile): a second
+// epilogue warpgroup (VS_KDN_NEPI=2: 36.7 vs 39.1 us on the 8 -> 8 layer but 28.5 vs 23.2 on 16 -> 16, slower in total),
+// descriptors precomputed once per kernel (45 -> 10 uniform instructions per MMA, no change: the issue slots were not
+// the limit), 2 vs 4 accumulator buffers (no change).  Warp roles are ordered epilogue < producer < issuers because
+// the scheduler favours the highest warp index of a sub-partition.
 #include "tc_ptx.cuh"
 #include "tc_pack.cuh"
 
@@ -32,7 +41,14 @@ constexpr int HD = TD + 2, HH = TH + 2, HW = TW + 2;
 constexpr int HV = HD * HH * HW;
 constexpr int PLANE_BYTES = HV * 16;
 constexpr int PLANE_PAD = 256;
-constexpr int NTHREADS = 288;                          // 1 producer + 4 MMA + 4 epilogue warps
+#ifndef VS_KDN_NEPI
+#define VS_KDN_NEPI 1
+#endif
+#ifndef VS_KDN_NBUF8
+#define VS_KDN_NBUF8 4
+#endif
+constexpr int NEPI = VS_KDN_NEPI;                      // epilogue warpgroups
+constexpr int NTHREADS = 160 + 128 * NEPI;             // NEPI x 4 epilogue warps + 1 producer + 4 MMA warps
 constexpr int NSLOT = 9;
 
 struct KdnParams {
@@ -46,7 +62,15 @@ struct KdnParams {
     bf16* y;
     double* stats;
     float* shift;
+    // dgrad only -- fused InstanceNorm+ReLU backward reduction of the PREVIOUS layer (see conv3_tc.cu TcParams)
+    const bf16* yprev;
+    const double* pstats;
+    double* psums;
+    double inv_s;
+    long long* dbg;          // tools/kdn_phase_probe.py: clock64 stamps of CTA 0 around its 9th tile, or null
 };
+#define KDN_DBG(slot) do { if (p.dbg != nullptr && blockIdx.x == 0) p.dbg[slot] = clock64(); } while (0)
+constexpr int KDN_DBG_TILE = 8;
 
 __device__ __forceinline__ float transpose_reduce16(float (&v)[16], int lane) {
 #pragma unroll
@@ -94,9 +118,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kdn_kernel(const __grid_
     constexpr int A_BYTES = CIN8 ? (PLANE_BYTES + PLANE_PAD) : 2 * PLANE_BYTES;
     constexpr int B_BYTES = NMP * N * 32;                     // [mma][kc 2][N/8][8 rows][16 B]
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    constexpr int NBUF = 2;
+    // TMEM accumulator buffers: the MMAs of tile i wait for the epilogue of tile i - NBUF, and an epilogue is a LONG
+    // dependent chain (tfull wake-up, TMEM loads, global stores, TMEM zeroing: ~2400 cycles against ~1200 of MMAs), so
+    // with two buffers the tile period was (MMA + epilogue) / 2 whatever the number of epilogue warps
+    constexpr int NBUF = NCO == 8 ? VS_KDN_NBUF8 : 3;
     constexpr int BUFC = NSLOT * NCO;                         // accumulator columns per buffer (72 / 144)
-    constexpr int TMEM_COLS = NCO == 8 ? 256 : 512;
+    constexpr int TMEM_COLS = (NBUF * BUFC <= 256) ? 256 : 512;
     static_assert(STAGE_BYTES % 128 == 0, "stage alignment");
     static_assert(NBUF * BUFC <= TMEM_COLS, "TMEM budget");
 
@@ -107,7 +134,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kdn_kernel(const __grid_
     uint64_t* tfull_bar = empty_bar + NSTAGE;
     uint64_t* tempty_bar = tfull_bar + NBUF;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + NBUF);
-    float* sshift = reinterpret_cast<float*>(tmem_slot + 4);          // [16]
+    float* sshift = reinterpret_cast<float*>(tmem_slot + 4);          // [2 groups][16]
+    float* smean = sshift + 32;                                       // [2][16]  (fused norm-backward reduction)
+    float* srstd = smean + 32;                                        // [2][16]
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
@@ -127,7 +156,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kdn_kernel(const __grid_
         }
         fence_proxy_async();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == 4 * NEPI + 1) tmem_alloc(tmem_slot, TMEM_COLS);
     pdl_trigger();
     tc_fence_before();
     __syncthreads();
@@ -135,7 +164,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kdn_kernel(const __grid_
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     pdl_wait();                          // see vs_common.cuh: no global-memory access above this line
 
-    if (warp == 0) {
+    // Warp roles, lowest to highest index: 2 x 4 epilogue warps, the TMA producer, 4 MMA issuers.  The scheduler favours the
+    // highest warp index among the eligible warps of a sub-partition: the issuers (one MMA per ~100 issue cycles of
+    // descriptor arithmetic) must not queue behind the two epilogue warps they share it with.
+    if (warp == 4 * NEPI) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
@@ -150,97 +182,142 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kdn_kernel(const __grid_
                     else tma_load_5d(sa, &xmap, &full_bar[stage], ks * 16, w0 - 1, h0 - 1, d0 - 1, n);
                     if (!CIN8) tma_load_5d(sa + PLANE_BYTES, &xmap, &full_bar[stage], ks * 16 + 8, w0 - 1, h0 - 1, d0 - 1, n);
                     bulk_load(sa + A_BYTES, reinterpret_cast<const uint8_t*>(p.wpack) + (long long)ks * B_BYTES, B_BYTES, &full_bar[stage]);
+                    if (item == (int)blockIdx.x + KDN_DBG_TILE * (int)gridDim.x) KDN_DBG(0);
+                    if (item == (int)blockIdx.x + (KDN_DBG_TILE + 1) * (int)gridDim.x) KDN_DBG(1);
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
             }
         }
-    } else if (warp <= 4) {
+    } else if (warp > 4 * NEPI) {
         // ===================== MMA issuers: the (input plane, tap) list split round-robin over the 4 warps ==========
-        const int j = warp - 1;
+        const int j = warp - (4 * NEPI + 1);
         constexpr uint32_t idesc = make_idesc(N);
+        // The operand descriptors of this warp's (plane, tap) list depend on the tile only through the stage base
+        // address: they are built ONCE (relative to stage 0) and the issue loop adds the stage offset -- the ~45 uniform
+        // instructions of descriptor arithmetic per MMA were what the issuer warps spent their issue slots on
+        // (profiles/r2_fullres_ncu.txt: the four sub-partitions issued on 46 % of all cycles, shared with the epilogue).
+        constexpr int MAXI = (HD * NMP + 3) / 4;
+        uint64_t ad_rel[MAXI], bd_rel[MAXI];
+        uint32_t dcol_rel[MAXI];
+        uint32_t valid = 0u;
+        {
+            const uint32_t a0 = smem_u32(smem);
+            const uint32_t b_base = a0 + A_BYTES;
+#pragma unroll
+            for (int k = 0; k < MAXI; ++k) {
+                const int i = j + 4 * k;
+                const int q = i / NMP, m = i - q * NMP;
+                const uint32_t a_plane = a0 + (uint32_t)(q * p.bh * p.bw) * 16u;
+                if (CIN8) {
+                    const int t1 = 2 * m, t2 = (2 * m + 1 < 9) ? 2 * m + 1 : 8;
+                    const int o1 = (t1 / 3) * p.bw + t1 % 3, o2 = (t2 / 3) * p.bw + t2 % 3;
+                    const uint32_t lbo = (2 * m + 1 < 9) ? (uint32_t)(o2 - o1) * 16u : 16u;
+                    ad_rel[k] = make_desc(a_plane + (uint32_t)o1 * 16u, lbo, (uint32_t)p.bw * 16u);
+                } else {
+                    const int kh = m / 3, kw = m - kh * 3;
+                    ad_rel[k] = make_desc(a_plane + (uint32_t)(kh * p.bw + kw) * 16u, PLANE_BYTES, (uint32_t)p.bw * 16u);
+                }
+                bd_rel[k] = make_desc(b_base + m * (N * 32), N * 16, 128u);
+                dcol_rel[k] = (uint32_t)((5 - q) * NCO);                                  // slots (5-q) .. (5-q)+3
+                if (i < HD * NMP && q < p.bd) valid |= 1u << k;                          // q >= bd: plane not staged (never with D >= 4)
+            }
+        }
         uint32_t stage = 0, phase = 0, buf = 0, bphase = 0;
         for (int item = blockIdx.x; item < p.work_items; item += gridDim.x) {
+            const bool dbg_tile = j == 0 && lane == 0 && item == (int)blockIdx.x + KDN_DBG_TILE * (int)gridDim.x;
+            const bool dbg_next = j == 0 && lane == 0 && item == (int)blockIdx.x + (KDN_DBG_TILE + 1) * (int)gridDim.x;
+            if (dbg_tile) KDN_DBG(2);
             mbar_wait(&tempty_bar[buf], bphase);                 // zeroed and released by the epilogue (also initially)
             tc_fence_after();
+            if (dbg_tile) KDN_DBG(3);
+            if (dbg_next) KDN_DBG(10);
             const uint32_t dbuf = tmem_base + buf * BUFC;
             for (int ks = 0; ks < p.kslices; ++ks) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t a0 = smem_u32(smem + stage * STAGE_BYTES);
-                const uint32_t b_base = a0 + A_BYTES;
-#pragma unroll 1
-                for (int i = j; i < HD * NMP; i += 4) {
-                    const int q = i / NMP, m = i - q * NMP;
-                    if (q >= p.bd) continue;                    // plane not staged (never with D >= 4)
-                    const uint32_t a_plane = a0 + (uint32_t)(q * p.bh * p.bw) * 16u;
-                    uint64_t ad;
-                    if (CIN8) {
-                        const int t1 = 2 * m, t2 = (2 * m + 1 < 9) ? 2 * m + 1 : 8;
-                        const int o1 = (t1 / 3) * p.bw + t1 % 3, o2 = (t2 / 3) * p.bw + t2 % 3;
-                        const uint32_t lbo = (2 * m + 1 < 9) ? (uint32_t)(o2 - o1) * 16u : 16u;
-                        ad = make_desc(a_plane + (uint32_t)o1 * 16u, lbo, (uint32_t)p.bw * 16u);
-                    } else {
-                        const int kh = m / 3, kw = m - kh * 3;
-                        ad = make_desc(a_plane + (uint32_t)(kh * p.bw + kw) * 16u, PLANE_BYTES, (uint32_t)p.bw * 16u);
-                    }
-                    const uint64_t bd = make_desc(b_base + m * (N * 32), N * 16, 128u);
-                    tc_mma_elect(dbuf + (uint32_t)((5 - q) * NCO), ad, bd, idesc, 1u);      // slots (5-q) .. (5-q)+3
-                }
+                if (dbg_tile && ks == 0) KDN_DBG(4);
+                const uint64_t soff = (uint64_t)((stage * (uint32_t)STAGE_BYTES) >> 4);   // start-address field, 16-byte units
+#pragma unroll
+                for (int k = 0; k < MAXI; ++k)
+                    if (valid & (1u << k)) tc_mma_elect(dbuf + dcol_rel[k], ad_rel[k] + soff, bd_rel[k] + soff, idesc, 1u);
                 tc_commit_elect(&empty_bar[stage]);
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
             tc_commit_elect(&tfull_bar[buf]);
+            if (dbg_tile) KDN_DBG(5);
             if (++buf == NBUF) { buf = 0; bphase ^= 1; }
         }
     } else {
-        // ===================== epilogue (warps 5..8) =====================
+        // ===================== epilogue: warpgroup e = warp / 4 drains TMEM buffer e (tiles e, e+2, ...) ==========
         const int q4 = warp & 3;
-        const int et = threadIdx.x - 32 * 5;
+        const int e = warp >> 2;                                 // < NEPI
+        const int et = threadIdx.x - 128 * e;
         const int row = q4 * 32 + lane;
         const int lh = row >> 3, lw = row & 7;
-        const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
-        // both buffers start zeroed and "empty"
+        const uint32_t lane_q = tmem_base + ((uint32_t)(q4 * 32) << 16);
+        const uint32_t bar_id = 1u + (uint32_t)e;
+#define EPI_SYNC() asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory")
+        // the buffers start zeroed and "empty" (with two warpgroups each owns one buffer)
         for (int b = 0; b < NBUF; ++b) {
-            for (int c = 0; c < BUFC; c += 8) tmem_st8_zero(lane_base + b * BUFC + c);
+            if (b % NEPI != e) continue;
+            for (int c = 0; c < BUFC; c += 8) tmem_st8_zero(lane_q + b * BUFC + c);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[b]);
         }
-        uint32_t buf = 0, bphase = 0;
+        int jt = e;                                              // index of the tile among this CTA's tiles: buffer jt % NBUF, use jt / NBUF
         int stat_n = -1;
         float rs[16], rq[16], shr[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) { rs[k] = 0.f; rq[k] = 0.f; shr[k] = 0.f; }
+        const bool fused = p.psums != nullptr;
+        double* const sout = fused ? p.psums : p.stats;
         auto flush_stats = [&]() {
-            if (p.stats != nullptr && stat_n >= 0) {
+            if (sout != nullptr && stat_n >= 0) {
                 const float s1 = transpose_reduce16(rs, lane);
                 const float s2 = transpose_reduce16(rq, lane);
                 if (lane < NCO) {
-                    atomicAdd(&p.stats[((long long)stat_n * p.cout + lane) * 2], (double)s1);
-                    atomicAdd(&p.stats[((long long)stat_n * p.cout + lane) * 2 + 1], (double)s2);
+                    atomicAdd(&sout[((long long)stat_n * p.cout + lane) * 2], (double)s1);
+                    atomicAdd(&sout[((long long)stat_n * p.cout + lane) * 2 + 1], (double)s2);
                 }
 #pragma unroll
                 for (int k = 0; k < 16; ++k) { rs[k] = 0.f; rq[k] = 0.f; }
             }
         };
-        if (et < 16) sshift[et] = 0.f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        float* const my_shift = sshift + 16 * e;
+        if (et < 16) my_shift[et] = 0.f;
+        EPI_SYNC();
         const int rd = min(1, p.d - 1), rh = min(1, p.h - 1), rw = min(1, p.w - 1);
         const bool has_shift = p.shift != nullptr;
         const bool has_stats = p.stats != nullptr;
-        const uint32_t sshift_addr = smem_u32(sshift);
+        const uint32_t sshift_addr = smem_u32(my_shift);
+        const uint32_t smean_addr = smem_u32(smean + 16 * e), srstd_addr = smem_u32(srstd + 16 * e);
         const int ref_row = rh * TW + rw;
-        for (int item = blockIdx.x; item < p.work_items; item += gridDim.x) {
+        for (int item = blockIdx.x + e * (int)gridDim.x; item < p.work_items; item += NEPI * (int)gridDim.x, jt += NEPI) {
+            if (et == 0 && item == (int)blockIdx.x + (KDN_DBG_TILE + NEPI) * (int)gridDim.x) KDN_DBG(11);
+            if (et == 0 && item == (int)blockIdx.x + KDN_DBG_TILE * (int)gridDim.x) KDN_DBG(12);
             int n, d0, h0, w0;
             decode_item((unsigned)item, p, n, d0, h0, w0);
+            const int buf = jt % NBUF;
+            const uint32_t bphase = (uint32_t)(jt / NBUF) & 1u;
+            const uint32_t lane_base = lane_q + (uint32_t)(buf * BUFC);
             if (n != stat_n) {
                 flush_stats();
                 stat_n = n;
+                if (fused) {
+                    EPI_SYNC();                                  // everyone is done with the previous sample's constants
+                    if (et < NCO) {
+                        float mu, rsd;
+                        in_mean_rstd(p.pstats + ((long long)n * p.cout + et) * 2, p.inv_s, mu, rsd);
+                        smean[16 * e + et] = mu; srstd[16 * e + et] = rsd;
+                    }
+                    EPI_SYNC();
+                }
                 if (has_shift) {
                     // shift hand-off exactly as in conv3_tc.cu: the CTA owning the reference voxel (tile 0 of the sample, the
                     // first item of CTA n) publishes the fp32 accumulator of voxel (1,1,1); everyone else spins on non-zero
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    EPI_SYNC();
                     if (d0 == 0 && h0 == 0 && w0 == 0) {
                         mbar_wait(&tfull_bar[buf], bphase);
                         tc_fence_after();
@@ -250,12 +327,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kdn_kernel(const __grid_
                             for (int k = 0; k < 16; ++k) r[k] = 0u;
                             {
                                 uint32_t r8[8];
-                                tmem_ld8(lane_base + buf * BUFC + (5 - rd) * NCO, r8);
+                                tmem_ld8(lane_base + (5 - rd) * NCO, r8);
                                 tmem_ld_wait();
 #pragma unroll
                                 for (int k = 0; k < 8; ++k) r[k] = r8[k];
                                 if (NCO == 16) {
-                                    tmem_ld8(lane_base + buf * BUFC + (5 - rd) * NCO + 8, r8);
+                                    tmem_ld8(lane_base + (5 - rd) * NCO + 8, r8);
                                     tmem_ld_wait();
 #pragma unroll
                                     for (int k = 0; k < 8; ++k) r[8 + k] = r8[k];
@@ -265,7 +342,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kdn_kernel(const __grid_
 #pragma unroll
                                 for (int k = 0; k < NCO; ++k) {
                                     const uint32_t bits = r[k] | 1u;
-                                    sshift[k] = __uint_as_float(bits);
+                                    my_shift[k] = __uint_as_float(bits);
                                     *reinterpret_cast<volatile uint32_t*>(p.shift + (long long)n * p.cout + k) = bits;
                                 }
                             }
@@ -277,9 +354,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kdn_kernel(const __grid_
                             __nanosleep(64);
                             if (++spins > (1u << 23)) __trap();
                         }
-                        sshift[et] = __uint_as_float(bits);
+                        my_shift[et] = __uint_as_float(bits);
                     }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    EPI_SYNC();
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4) {
                         const float4 sh = lds128(sshift_addr + k4 * 16);
@@ -290,12 +367,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kdn_kernel(const __grid_
             const int jmax = min(TD, p.d - d0);
             const int gh = h0 + lh, gw = w0 + lw;
             const bool rc_ok = gh < p.h && gw < p.w;
+            // fused norm-backward reduction: the previous layer's raw output at this thread's voxels is fetched BEFORE
+            // waiting for the accumulators, so the global latency hides behind the MMAs of the tile
+            uint4 ypre[TD][NCO / 8];
+            if (fused) {
+#pragma unroll
+                for (int pl = 0; pl < TD; ++pl)
+#pragma unroll
+                    for (int h8 = 0; h8 < NCO / 8; ++h8) {
+                        ypre[pl][h8] = make_uint4(0u, 0u, 0u, 0u);
+                        if (pl < jmax && rc_ok)
+                            ypre[pl][h8] = __ldg(reinterpret_cast<const uint4*>(
+                                p.yprev + ((((long long)n * p.d + d0 + pl) * p.h + gh) * (long long)p.w + gw) * p.cout + h8 * 8));
+                    }
+            }
+            const bool dbg_e = et == 0 && item == (int)blockIdx.x + KDN_DBG_TILE * (int)gridDim.x;
+            if (dbg_e) KDN_DBG(6);
             mbar_wait(&tfull_bar[buf], bphase);
             tc_fence_after();
+            if (dbg_e) KDN_DBG(7);
 #pragma unroll
             for (int pl = 0; pl < TD; ++pl) {
                 if (pl >= jmax) break;
-                const uint32_t taddr = lane_base + buf * BUFC + (5 - pl) * NCO;
+                const uint32_t taddr = lane_base + (5 - pl) * NCO;
                 float v[NCO];
                 {
                     uint32_t r8[8];
@@ -323,21 +417,50 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kdn_kernel(const __grid_
 #pragma unroll
                         for (int k = 0; k < NCO; ++k) { rs[k] += v[k]; rq[k] = fmaf(v[k], v[k], rq[k]); }
                     }
+                    if (fused) {
+                        // g = this launch's output as stored (rounded to bf16); mask / xhat from the previous layer's raw
+                        // output at the same voxel -- exactly what inorm_relu_bwd_reduce_kernel computes
+#pragma unroll
+                        for (int h8 = 0; h8 < NCO / 8; ++h8) {
+                            const uint4 raw = ypre[pl][h8];
+                            const uint32_t u[4] = {raw.x, raw.y, raw.z, raw.w};
+                            float yv[8];
+#pragma unroll
+                            for (int i2 = 0; i2 < 4; ++i2) { yv[2 * i2] = __uint_as_float(u[i2] << 16); yv[2 * i2 + 1] = __uint_as_float(u[i2] & 0xffff0000u); }
+#pragma unroll
+                            for (int k4 = 0; k4 < 2; ++k4) {
+                                const float4 mu = lds128(smean_addr + (h8 * 8 + k4 * 4) * 4);
+                                const float4 rr = lds128(srstd_addr + (h8 * 8 + k4 * 4) * 4);
+                                const float mus[4] = {mu.x, mu.y, mu.z, mu.w}, rrs[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const int kk = h8 * 8 + k4 * 4 + k;
+                                    const float xh = (yv[k4 * 4 + k] - mus[k]) * rrs[k];
+                                    const float gq = __bfloat162float(__float2bfloat16_rn(v[kk]));
+                                    const float gm = xh > 0.f ? gq : 0.f;
+                                    rs[kk] += gm;
+                                    rq[kk] = fmaf(gm, xh, rq[kk]);
+                                }
+                            }
+                        }
+                    }
                 }
             }
+            if (dbg_e) KDN_DBG(8);
             // hand the buffer back ZEROED: every MMA of this kernel accumulates
-            for (int c = 0; c < BUFC; c += 8) tmem_st8_zero(lane_base + buf * BUFC + c);
+            for (int c = 0; c < BUFC; c += 8) tmem_st8_zero(lane_base + c);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[buf]);
-            if (++buf == NBUF) { buf = 0; bphase ^= 1; }
+            if (dbg_e) KDN_DBG(9);
         }
         flush_stats();
+#undef EPI_SYNC
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == 4 * NEPI + 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
@@ -352,7 +475,7 @@ template <bool CIN8, int NCO, int NSTAGE>
 int launch_kdn(const CUtensorMap& map, const KdnParams& p, cudaStream_t st) {
     constexpr int A_BYTES = CIN8 ? (PLANE_BYTES + PLANE_PAD) : 2 * PLANE_BYTES;
     constexpr int B_BYTES = (CIN8 ? 5 : 9) * 4 * NCO * 32;
-    constexpr int SMEM = NSTAGE * (A_BYTES + B_BYTES) + 128 + 8 * (2 * NSTAGE + 4) + 16 + 64 + 64;
+    constexpr int SMEM = NSTAGE * (A_BYTES + B_BYTES) + 128 + 8 * (2 * NSTAGE + 8) + 16 + 3 * 32 * 4 + 64;
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
     auto kern = conv3_tc_kdn_kernel<CIN8, NCO, NSTAGE>;
     static bool configured = false;
@@ -367,6 +490,9 @@ int launch_kdn(const CUtensorMap& map, const KdnParams& p, cudaStream_t st) {
 }
 
 }  // namespace
+
+static long long* g_kdn_dbg = nullptr;
+extern "C" void vs_debug_set_kdn_phase_buffer(void* dev_ptr) { g_kdn_dbg = (long long*)dev_ptr; }
 
 extern "C" size_t vs_conv3_tc_kdn_pack_bytes(int cin, int cout, int dgrad) {
     const int gin = dgrad ? cout : cin, gout = dgrad ? cin : cout;
@@ -386,8 +512,19 @@ extern "C" int vs_pack_conv3_weight_tc_kdn(const float* w, void* out, int cin, i
 
 // y[n,d,h,w,gout] = conv3(x[n,d,h,w,gin], wkdn); bf16 NDHWC in and out; gout in {8, 16}; D >= 4.
 // stats / shift: as vs_conv3x3x3_fprop (zeroed here unless prezeroed).
+extern "C" int vs_conv3x3x3_tc_kdn_ex(const void* x, const void* wkdn, void* y, double* stats, float* shift, int prezeroed,
+                                      const void* yprev, const double* pstats, double* psums,
+                                      int n, int d, int h, int w, int gin, int gout, void* stream);
 extern "C" int vs_conv3x3x3_tc_kdn(const void* x, const void* wkdn, void* y, double* stats, float* shift, int prezeroed,
                                    int n, int d, int h, int w, int gin, int gout, void* stream) {
+    return vs_conv3x3x3_tc_kdn_ex(x, wkdn, y, stats, shift, prezeroed, nullptr, nullptr, nullptr, n, d, h, w, gin, gout, stream);
+}
+
+// As vs_conv3x3x3_tc_kdn; psums != NULL (dgrad): also accumulates the previous layer's InstanceNorm-backward sums
+// psums[n][gout][2] += (sum g*mask, sum g*mask*xhat) from yprev / pstats (zeroed by the caller; no stats / shift then).
+extern "C" int vs_conv3x3x3_tc_kdn_ex(const void* x, const void* wkdn, void* y, double* stats, float* shift, int prezeroed,
+                                      const void* yprev, const double* pstats, double* psums,
+                                      int n, int d, int h, int w, int gin, int gout, void* stream) {
     VS_REQUIRE(x && wkdn && y, VS_ERR_SHAPE, "conv3_tc_kdn: null pointer");
     VS_REQUIRE((gin == 8 || (gin % 16 == 0 && gin >= 16)) && (gout == 8 || gout == 16) && d >= TD, VS_ERR_UNSUPPORTED,
                "conv3_tc_kdn: needs Cin = 8 or a multiple of 16, Cout in {8,16}, D >= 4 (Cin=%d Cout=%d D=%d)", gin, gout, d);
@@ -430,6 +567,13 @@ extern "C" int vs_conv3x3x3_tc_kdn(const void* x, const void* wkdn, void* y, dou
     VS_REQUIRE(items < 2147483647LL, VS_ERR_SHAPE, "conv3_tc_kdn: too many work items");
     p.work_items = (int)items;
     p.wpack = (const bf16*)wkdn; p.y = (bf16*)y; p.stats = stats; p.shift = shift;
+    p.yprev = (const bf16*)yprev; p.pstats = pstats; p.psums = psums; p.inv_s = 1.0 / ((double)d * h * w);
+    p.dbg = g_kdn_dbg;
+    if (psums != nullptr) {
+        VS_REQUIRE(yprev && pstats && stats == nullptr && shift == nullptr, VS_ERR_SHAPE,
+                   "conv3_tc_kdn: the fused norm-backward reduction needs y_prev + stats_prev and no forward statistics");
+        VS_REQUIRE(vs_aligned16(yprev), VS_ERR_ALIGN, "conv3_tc_kdn: y_prev must be 16B aligned");
+    }
     if (!prezeroed) {
         if (stats) VS_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * (size_t)n * gout, st), "conv3_tc_kdn stats memset");
         if (shift) VS_CUDA(cudaMemsetAsync(shift, 0, sizeof(float) * (size_t)n * gout, st), "conv3_tc_kdn shift memset");

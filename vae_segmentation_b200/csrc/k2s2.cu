@@ -353,7 +353,7 @@ extern "C" void vs_debug_set_k2_ksplit_max(int v) { g_k2_ksplit_max = v; }
 extern "C" int vs_k2s2_wgrad_tc(const void* coarse, const void* fine, float* dwt, int accumulate, int n, int dc, int hc,
                                 int wc, int a, int b, void* stream);
 #endif
-static int g_k2_wgrad_tc = 1;      // A/B switch: weight gradient on the tensor cores (bf16 operands) or the CUDA-core kernel
+static int g_k2_wgrad_tc = 1;      // 0: CUDA-core kernel; 1: tensor cores for the large layers; 2: tensor cores always (tests)
 extern "C" void vs_debug_set_k2_wgrad_tc(int on) { g_k2_wgrad_tc = on; }
 
 extern "C" int vs_k2s2_gather(int dtype, const void* fine, const float* wt, const float* bias, void* coarse,
@@ -418,7 +418,11 @@ extern "C" int vs_k2s2_wgrad(int dtype, const void* coarse, const void* fine, fl
     cudaStream_t st = (cudaStream_t)stream;
     bool tc = false;
 #ifdef VS_WITH_TCGEN05
-    tc = g_k2_wgrad_tc && dtype == VS_BF16 && a <= 256 && b <= 256 && (a == 8 || a % 16 == 0) && (b == 8 || b % 16 == 0);
+    // tensor cores from 24^3 coarse voxels per pair of samples up (measured, tools/k2bench.py: 108 -> 33 us at 2 x 48^3, 16
+    // channels; 55 -> 41 us at 24^3, 32 channels); below that the launch is a handful of tiles and the per-CTA atomic
+    // read-back of the TMEM accumulators costs more than the CUDA-core kernel's whole run (16 vs 40 us at 12^3)
+    tc = g_k2_wgrad_tc && dtype == VS_BF16 && a <= 256 && b <= 256 && (a == 8 || a % 16 == 0) && (b == 8 || b % 16 == 0) &&
+         (total >= 20000 || g_k2_wgrad_tc == 2);
 #endif
     if (!accumulate) {
         if (!tc) VS_CUDA(cudaMemsetAsync(dwt, 0, sizeof(float) * 8 * a * b, st), "k2s2 wgrad memset");

@@ -62,7 +62,7 @@ class _PackJob(ctypes.Structure):
     _fields_ = [("w", ctypes.c_void_p), ("wf", ctypes.c_void_p), ("wd", ctypes.c_void_p), ("tcf", ctypes.c_void_p),
                 ("tcd", ctypes.c_void_p), ("tcf_elems", ctypes.c_longlong), ("tcd_elems", ctypes.c_longlong),
                 ("cin", ctypes.c_int), ("cout", ctypes.c_int), ("cout_pad", ctypes.c_int), ("cin_pad", ctypes.c_int),
-                ("kdn", ctypes.c_void_p), ("kdn_elems", ctypes.c_longlong), ("kind", ctypes.c_int), ("reserved", ctypes.c_int)]
+                ("kdn", ctypes.c_void_p), ("kdn_elems", ctypes.c_longlong), ("kind", ctypes.c_int), ("kdn_dgrad", ctypes.c_int)]
 
 
 class PackCache(object):
@@ -156,12 +156,12 @@ class PackCache(object):
             ent["key"] = key
         return ent["tcd"]
 
-    def conv3_kdn(self, w):
-        """kd-in-N fprop pack of a 3x3x3 weight (re-packed in place, part of the batched re-pack), or None."""
-        ent, key = self._entry("kdn", w, True)
+    def conv3_kdn(self, w, dgrad=False):
+        """kd-in-N fprop (or dgrad) pack of a 3x3x3 weight (re-packed in place, part of the batched re-pack), or None."""
+        ent, key = self._entry("kdnd" if dgrad else "kdn", w, True)
         if ent["key"] != key:
             had = ent["kdn"] is not None
-            ent["kdn"] = ops.pack_conv3_weight_tc_kdn(w.detach(), dgrad=False, out=ent["kdn"])
+            ent["kdn"] = ops.pack_conv3_weight_tc_kdn(w.detach(), dgrad=dgrad, out=ent["kdn"])
             if not had:
                 self._jobs = None
             ent["tc"] = True
@@ -208,6 +208,7 @@ class PackCache(object):
                 j.kdn = e["kdn"].data_ptr() if e["kdn"] is not None else None
                 j.kdn_elems = e["kdn"].numel() if e["kdn"] is not None else 0
                 j.kind = 1 if e["kind"] == "k2s2" else 0         # k2s2: w = wt[A = shape[0]][B = shape[1]][8]
+                j.kdn_dgrad = 1 if e["kind"] == "kdnd" else 0
             host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
             self._jobs = (host.to(ents[0]["w"].device), len(ents), ents)
         ops.pack_conv3_batched(self._jobs[0], self._jobs[1])
@@ -332,7 +333,11 @@ def program_forward(layers, tensors, x, dims, dtype, cache, record=True):
             y = _sim(y, "y")
             a = _sim(ops.inorm_relu_apply(y, stats, skip), "a")
             if record:
-                tape.append((L, cur, y, stats, (n, d, h, w), (wd, wdtc)))
+                wkd = None
+                if (USE_KDN and USE_TENSOR_CORES and dtype == torch.bfloat16 and not L.in_planar and L.cin in (8, 16)
+                        and _tc_channels(L.cout) and d >= 4 and d * h * w >= 48 ** 3):
+                    wkd = cache.conv3_kdn(tensors[L.wi], dgrad=True)       # input gradient through the kd-in-N kernel too
+                tape.append((L, cur, y, stats, (n, d, h, w), (wd, wdtc, wkd)))
             cur = a
         elif L.kind == K2DOWN:
             d, h, w = d // 2, h // 2, w // 2
@@ -430,9 +435,13 @@ def program_backward(tape, g, dtype, need, grads, param_refs, need_input_grad):
                 tgt, acc = _grad_target(param_refs[L.bi], True)
                 grads[L.bi] = None if acc else torch.zeros(L.cout, device=dy.device, dtype=torch.float32)
             _grad_ready(param_refs[L.wi], param_refs[L.bi])
-            g = _sim(ops.conv3_dgrad(dy, wd[0], dims, L.cin, L.cout, dtype, out_planar=L.in_planar, wdtc=wd[1],
-                                     prev=None if L.in_planar else fuse_prev(idx, dy, L.cin, L.cout, wd[1])), "g") \
-                if want_dx else None
+            if want_dx and len(wd) > 2 and wd[2] is not None:
+                # full-resolution layers: kd-in-N kernel (GEMM input = the layer's Cout, output = its Cin in {8, 16})
+                g, _ = ops.conv3_tc_kdn(dy, wd[2], dims, L.cout, L.cin, prev=fuse_prev(idx, dy, L.cin, L.cout, wd[1]))
+            else:
+                g = _sim(ops.conv3_dgrad(dy, wd[0], dims, L.cin, L.cout, dtype, out_planar=L.in_planar, wdtc=wd[1],
+                                         prev=None if L.in_planar else fuse_prev(idx, dy, L.cin, L.cout, wd[1])), "g") \
+                    if want_dx else None
         elif L.kind == K2DOWN:
             # dims are the coarse (output) dims; g is the coarse gradient
             if need[L.wi] or need[L.bi]:

@@ -479,9 +479,10 @@ def pack_conv3_weight_tc_kdn(w, dgrad=False, out=None):
     return out
 
 
-def conv3_tc_kdn(x, wkdn, dims, gin, gout, want_stats=False, arena=None):
-    """y (bf16 NDHWC) = conv3(x, wkdn) through the experimental kd-in-N kernel; returns (y, stats or None).
-    arena: zero-filled StatsArena supplying the statistics / shift words (as conv3_fprop)."""
+def conv3_tc_kdn(x, wkdn, dims, gin, gout, want_stats=False, arena=None, prev=None):
+    """y (bf16 NDHWC) = conv3(x, wkdn) through the kd-in-N kernel; returns (y, stats or None).
+    arena: zero-filled StatsArena supplying the statistics / shift words (as conv3_fprop).  prev = (y_prev, stats_prev,
+    sums_prev) (dgrad): also accumulate the previous layer's norm-backward sums (sums pre-zeroed), as conv3_dgrad."""
     n, d, h, w = dims
     y = torch.empty(n, d, h, w, gout, device=x.device, dtype=torch.bfloat16)
     stats = shift = None
@@ -494,5 +495,7 @@ def conv3_tc_kdn(x, wkdn, dims, gin, gout, want_stats=False, arena=None):
             buf = torch.empty(stats_words(n, gout), device=x.device, dtype=torch.float64)
         stats = buf[:n * gout * 2].view(n, gout, 2)
         shift = buf[n * gout * 2:].view(torch.float32)[:n * gout].view(n, gout)
-    _cabi.call("vs_conv3x3x3_tc_kdn", _p(x), _p(wkdn), _p(y), _p(stats), _p(shift), prezeroed, n, d, h, w, gin, gout, _stream())
+    yp, sp, sums = prev if prev is not None else (None, None, None)
+    _cabi.call("vs_conv3x3x3_tc_kdn_ex", _p(x), _p(wkdn), _p(y), _p(stats), _p(shift), prezeroed, _p(yp), _p(sp), _p(sums),
+               n, d, h, w, gin, gout, _stream())
     return y, stats
