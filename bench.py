@@ -190,11 +190,20 @@ def kernel_cost(name, key):
         dt, _, _, _, n, d, h, w, cin, cout = key
         vox = n * d * h * w
         return 2.0 * 27 * cin * cout * vox, vox * (cin + cout) * size[dt]
+    if name in ("vs_conv3x3x3_tc_kdn", "vs_conv3x3x3_tc_kdn_ex"):
+        # kd-in-N tensor-core convolution (fprop or dgrad): bf16 in and out, GEMM input gin / output gout channels
+        n, d, h, w, gin, gout = key[-6:]
+        vox = n * d * h * w
+        return 2.0 * 27 * gin * gout * vox, vox * (gin + gout) * 2
     if name in ("vs_k2s2_gather", "vs_k2s2_scatter", "vs_k2s2_wgrad"):
         dt = key[0]
         n, dc, hc, wc, a, b = key[-6:]
         vox = n * dc * hc * wc
         return 2.0 * 8 * a * b * vox, vox * (a + 8 * b) * size[dt]
+    if name in ("vs_k2s2_gather_tc", "vs_k2s2_scatter_tc"):
+        n, dc, hc, wc, a, b = key[-6:]
+        vox = n * dc * hc * wc
+        return 2.0 * 8 * a * b * vox, vox * (a + 8 * b) * 2
     if name == "vs_inorm_relu_apply":
         dt, n, s, c = key
         return 0.0, 2.0 * n * s * c * size[dt]

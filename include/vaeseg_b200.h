@@ -42,6 +42,11 @@ int vs_has_tcgen05(void);
  * of at most `max_ctas` CTAs may be scheduled while their predecessor in the stream drains (the prologue overlaps the
  * predecessor's tail; the kernel waits before touching global memory).  0 disables.  Returns the previous setting. */
 int vs_set_pdl(int max_ctas);
+/* 1: the kd-in-N convolution issues its accumulating MMAs from one warp in a fixed order, which makes the forward pass
+ * bit-reproducible from run to run (with 0 four warps issue concurrently and the fp32 accumulation order, hence the
+ * last bit of some outputs, varies).  The reference has no equivalent switch; torch.use_deterministic_algorithms is
+ * the nearest notion.  Statistics and weight gradients still use atomics (order differences ~1e-16 / ~1e-7). */
+void vs_set_kdn_ordered(int on);
 
 /* ---- weight repacking (derived caches of the fp32 master weights) ------------------- */
 /* Conv3d 3x3x3 weight [Cout,Cin,27] -> wf[27][Cin][Cout] (fprop) and, when wd != NULL,

@@ -171,9 +171,21 @@ KDN_CASES = [(1, 4, 16, 8, 8, 8), (2, 5, 17, 9, 8, 8), (1, 8, 18, 10, 16, 8), (1
              (1, 12, 24, 24, 32, 16)]
 
 
+@pytest.mark.parametrize("ordered", [0, 1])
 @pytest.mark.parametrize("case", KDN_CASES)
-def test_tc_kdn_fprop_and_dgrad(case):
-    """Experimental kd-in-N convolution against torch (same bf16 operands) and against the production kernel."""
+def test_tc_kdn_fprop_and_dgrad(case, ordered):
+    """kd-in-N convolution against torch (same bf16 operands) and against the tap-per-MMA kernel; ordered = 1 is the
+    single-issuer mode (vs_set_kdn_ordered), which must also give identical bits on a second run."""
+    import os
+    import vae_segmentation_b200._cabi as cabi
+    cabi.lib().vs_set_kdn_ordered(ordered)
+    try:
+        _tc_kdn_case(case, ordered)
+    finally:
+        cabi.lib().vs_set_kdn_ordered(int(os.environ.get("VAESEG_KDN_ORDERED", cabi.KDN_ORDERED_DEFAULT)))
+
+
+def _tc_kdn_case(case, ordered):
     n, d, h, w, cin, cout = case
     torch.manual_seed(sum(case) + 7)
     x = torch.randn(n, cin, d, h, w).bfloat16().float()
@@ -193,6 +205,9 @@ def test_tc_kdn_fprop_and_dgrad(case):
     assert torch.allclose(stats.cpu(), s_ref, rtol=5e-3, atol=5e-3 * s_ref.abs().max().item())
     # plain (no shift / statistics) == the production kernel on the same operands
     y2, _ = ops.conv3_tc_kdn(to_ndhwc(x), wk, dims, cin, cout, want_stats=False)
+    if ordered:
+        y2b, _ = ops.conv3_tc_kdn(to_ndhwc(x), wk, dims, cin, cout, want_stats=False)
+        assert torch.equal(y2, y2b)
     wf, _ = ops.pack_conv3_weight(wd)
     y3, _ = ops.conv3_fprop(to_ndhwc(x), wf, None, dims, cin, cout, torch.bfloat16, shifted=False, want_stats=False,
                             wtc=ops.pack_conv3_weight_tc(wd, dgrad=False))

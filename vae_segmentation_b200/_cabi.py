@@ -22,6 +22,7 @@ _SIGNATURES = {
     "vs_version": [],
     "vs_has_tcgen05": [],
     "vs_set_pdl": [_I],
+    "vs_set_kdn_ordered": [_I],
     "vs_pack_conv3_weight": [_P, _P, _P, _I, _I, _P],
     "vs_conv3_tc_pack_bytes": [_I, _I, _I],
     "vs_pack_conv3_weight_tc": [_P, _P, _I, _I, _I, _P],
@@ -74,12 +75,14 @@ _SIGNATURES = {
     "vs_joint_target_finish": [_P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _I, _I, _I, _P, _P, _P],
 }
 _RESTYPES = {"vs_last_error_string": c_char_p, "vs_conv3_wgrad_workspace_bytes": c_size_t,
-             "vs_conv3_tc_pack_bytes": c_size_t, "vs_conv3_tc_kdn_pack_bytes": c_size_t, "vs_k2s2_tc_pack_bytes": c_size_t}
+             "vs_conv3_tc_pack_bytes": c_size_t, "vs_conv3_tc_kdn_pack_bytes": c_size_t, "vs_k2s2_tc_pack_bytes": c_size_t,
+             "vs_set_kdn_ordered": None}
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
 _lib = None
 PDL_DEFAULT = "0"
+KDN_ORDERED_DEFAULT = "0"
 
 
 def lib():
@@ -97,6 +100,7 @@ def lib():
             fn.restype = _RESTYPES.get(name, c_int)
         # programmatic dependent launch for launches of at most VAESEG_PDL CTAs (include/vaeseg_b200.h: vs_set_pdl); 0 disables
         handle.vs_set_pdl(int(os.environ.get("VAESEG_PDL", PDL_DEFAULT)))
+        handle.vs_set_kdn_ordered(int(os.environ.get("VAESEG_KDN_ORDERED", KDN_ORDERED_DEFAULT)))
         if os.environ.get("VAESEG_CONV3_KSPLIT", "1") == "0":          # A/B switch (tools): K split over the conv issuer warps
             handle.vs_debug_set_conv3_ksplit(0)
         _lib = handle

@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
     if (threadIdx.x == 0) TC_DBG(0);
 
     if (threadIdx.x == 0) {
+        prefetch_tensormap(&xmap);
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], TD); }
         for (int b = 0; b < NBUF; ++b) { mbar_init(&tfull_bar[b], TD); mbar_init(&tempty_bar[b], 4); }
         fence_barrier_init();

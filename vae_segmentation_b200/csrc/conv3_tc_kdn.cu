@@ -67,6 +67,7 @@ struct KdnParams {
     const double* pstats;
     double* psums;
     double inv_s;
+    int ordered;             // 1: one issuer warp issues the whole (plane, tap) list in a fixed order (bit-reproducible sums)
     long long* dbg;          // tools/kdn_phase_probe.py: clock64 stamps of CTA 0 around its 9th tile, or null
 };
 #define KDN_DBG(slot) do { if (p.dbg != nullptr && blockIdx.x == 0) p.dbg[slot] = clock64(); } while (0)
@@ -137,11 +138,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kdn_kernel(const __grid_
     float* sshift = reinterpret_cast<float*>(tmem_slot + 4);          // [2 groups][16]
     float* smean = sshift + 32;                                       // [2][16]  (fused norm-backward reduction)
     float* srstd = smean + 32;                                        // [2][16]
+    uint64_t* tab_a = reinterpret_cast<uint64_t*>(srstd + 32);        // [HD * NMP] operand descriptors relative to stage 0 (ordered mode)
+    uint64_t* tab_b = tab_a + HD * 9;
+    uint32_t* tab_d = reinterpret_cast<uint32_t*>(tab_b + HD * 9);
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
+        prefetch_tensormap(&xmap);
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 4); }
         for (int b = 0; b < NBUF; ++b) { mbar_init(&tfull_bar[b], 4); mbar_init(&tempty_bar[b], 4); }
         fence_barrier_init();
@@ -220,8 +225,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kdn_kernel(const __grid_
                 bd_rel[k] = make_desc(b_base + m * (N * 32), N * 16, 128u);
                 dcol_rel[k] = (uint32_t)((5 - q) * NCO);                                  // slots (5-q) .. (5-q)+3
                 if (i < HD * NMP && q < p.bd) valid |= 1u << k;                          // q >= bd: plane not staged (never with D >= 4)
+                if (p.ordered && lane == 0 && i < HD * NMP) { tab_a[i] = ad_rel[k]; tab_b[i] = bd_rel[k]; tab_d[i] = dcol_rel[k]; }
             }
         }
+        // Ordered mode: accumulating MMAs issued by different warps into the same TMEM columns add in ISSUE order, which
+        // varies from run to run (fp32 rounding of y moves, a few bf16 roundings flip).  Here warp j = 0 alone issues the
+        // whole list, in list order, from the descriptor table the four warps just filled; the other three only keep the
+        // barrier protocol going (their commits track no MMAs and arrive at once).
+        if (p.ordered) asm volatile("bar.sync 8, 128;" ::: "memory");
         uint32_t stage = 0, phase = 0, buf = 0, bphase = 0;
         for (int item = blockIdx.x; item < p.work_items; item += gridDim.x) {
             const bool dbg_tile = j == 0 && lane == 0 && item == (int)blockIdx.x + KDN_DBG_TILE * (int)gridDim.x;
@@ -237,9 +248,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kdn_kernel(const __grid_
                 tc_fence_after();
                 if (dbg_tile && ks == 0) KDN_DBG(4);
                 const uint64_t soff = (uint64_t)((stage * (uint32_t)STAGE_BYTES) >> 4);   // start-address field, 16-byte units
+                if (p.ordered) {
+                    if (j == 0) {
+#pragma unroll 6
+                        for (int i = 0; i < HD * NMP; ++i)
+                            if (i / NMP < p.bd) tc_mma_elect(dbuf + tab_d[i], tab_a[i] + soff, tab_b[i] + soff, idesc, 1u);
+                    }
+                } else {
 #pragma unroll
-                for (int k = 0; k < MAXI; ++k)
-                    if (valid & (1u << k)) tc_mma_elect(dbuf + dcol_rel[k], ad_rel[k] + soff, bd_rel[k] + soff, idesc, 1u);
+                    for (int k = 0; k < MAXI; ++k)
+                        if (valid & (1u << k)) tc_mma_elect(dbuf + dcol_rel[k], ad_rel[k] + soff, bd_rel[k] + soff, idesc, 1u);
+                }
                 tc_commit_elect(&empty_bar[stage]);
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
@@ -475,7 +494,7 @@ template <bool CIN8, int NCO, int NSTAGE>
 int launch_kdn(const CUtensorMap& map, const KdnParams& p, cudaStream_t st) {
     constexpr int A_BYTES = CIN8 ? (PLANE_BYTES + PLANE_PAD) : 2 * PLANE_BYTES;
     constexpr int B_BYTES = (CIN8 ? 5 : 9) * 4 * NCO * 32;
-    constexpr int SMEM = NSTAGE * (A_BYTES + B_BYTES) + 128 + 8 * (2 * NSTAGE + 8) + 16 + 3 * 32 * 4 + 64;
+    constexpr int SMEM = NSTAGE * (A_BYTES + B_BYTES) + 128 + 8 * (2 * NSTAGE + 8) + 16 + 3 * 32 * 4 + 64 + HD * 9 * 20 + 16;
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
     auto kern = conv3_tc_kdn_kernel<CIN8, NCO, NSTAGE>;
     static bool configured = false;
@@ -492,6 +511,9 @@ int launch_kdn(const CUtensorMap& map, const KdnParams& p, cudaStream_t st) {
 }  // namespace
 
 static long long* g_kdn_dbg = nullptr;
+static int g_kdn_ordered = 0;
+// 1 = bit-reproducible accumulation order in the kd-in-N kernel (one issuer warp); see the kernel's issuer section
+extern "C" void vs_set_kdn_ordered(int on) { g_kdn_ordered = on ? 1 : 0; }
 extern "C" void vs_debug_set_kdn_phase_buffer(void* dev_ptr) { g_kdn_dbg = (long long*)dev_ptr; }
 
 extern "C" size_t vs_conv3_tc_kdn_pack_bytes(int cin, int cout, int dgrad) {
@@ -569,6 +591,7 @@ extern "C" int vs_conv3x3x3_tc_kdn_ex(const void* x, const void* wkdn, void* y, 
     p.wpack = (const bf16*)wkdn; p.y = (bf16*)y; p.stats = stats; p.shift = shift;
     p.yprev = (const bf16*)yprev; p.pstats = pstats; p.psums = psums; p.inv_s = 1.0 / ((double)d * h * w);
     p.dbg = g_kdn_dbg;
+    p.ordered = g_kdn_ordered;
     if (psums != nullptr) {
         VS_REQUIRE(yprev && pstats && stats == nullptr && shift == nullptr, VS_ERR_SHAPE,
                    "conv3_tc_kdn: the fused norm-backward reduction needs y_prev + stats_prev and no forward statistics");

@@ -81,6 +81,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_wgrad_tc_kernel(const __gri
     const int mc = blockIdx.y / p.kslices;                    // 64-channel chunk of co
 
     if (threadIdx.x == 0) {
+        prefetch_tensormap(&xmap);
+        prefetch_tensormap(&dymap);
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 4); }
         mbar_init(done_bar, 4);
         fence_barrier_init();
@@ -286,6 +288,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_wgrad_dsh_kernel(const __gr
     const int ks = blockIdx.y;                                // 16-channel slice of ci (0 for Cin = 8)
 
     if (threadIdx.x == 0) {
+        prefetch_tensormap(&xmap);
+        prefetch_tensormap(&dymap);
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 4); }
         mbar_init(done_bar, 4);
         fence_barrier_init();

@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(128 + 128 * NEPI, 1) k2s2_tc_kernel(const __gr
     const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
+        prefetch_tensormap(&xmap);
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int b = 0; b < NBUF; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
         fence_barrier_init();

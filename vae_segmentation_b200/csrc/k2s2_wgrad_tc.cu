@@ -61,6 +61,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k2s2_wgrad_tc_kernel(const __gr
     const int tmem_cols = p.cpc * p.npad <= 32 ? 32 : p.cpc * p.npad <= 64 ? 64 : p.cpc * p.npad <= 128 ? 128 : p.cpc * p.npad <= 256 ? 256 : 512;
 
     if (threadIdx.x == 0) {
+        prefetch_tensormap(&fmap);
+        prefetch_tensormap(&cmap);
         for (int s = 0; s < p.nstage; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(done_bar, 1);
         fence_barrier_init();
