@@ -195,6 +195,11 @@ def kernel_cost(name, key):
         n, d, h, w, gin, gout = key[-6:]
         vox = n * d * h * w
         return 2.0 * 27 * gin * gout * vox, vox * (gin + gout) * 2
+    if name == "vs_conv3x3x3_tc_kdn_planar":
+        # 8-output-channel kd-in-N convolution storing channels 0..1 as planar fp32 (2-class head / in-block dgrad)
+        _, n, d, h, w, gin = key[-6:]
+        vox = n * d * h * w
+        return 2.0 * 27 * gin * 8 * vox, vox * (gin * 2 + 8)
     if name in ("vs_k2s2_gather", "vs_k2s2_scatter", "vs_k2s2_wgrad"):
         dt = key[0]
         n, dc, hc, wc, a, b = key[-6:]

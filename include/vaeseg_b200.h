@@ -126,6 +126,16 @@ int vs_conv3x3x3_tc_kdn(const void* x, const void* wkdn, void* y, double* stats,
 int vs_conv3x3x3_tc_kdn_ex(const void* x, const void* wkdn, void* y, double* stats, float* shift, int prezeroed,
                            const void* yprev, const double* pstats, double* psums,
                            int n, int d, int h, int w, int gin, int gout, void* stream);
+/* kd-in-N pack of a layer whose channels are zero-padded to cin_pad x cout_pad (w is [cout][cin][27]): the 2-class head
+ * (cout 2 -> 8) and the 2-channel in-block's input gradient (cin 2 -> 8).  Size: vs_conv3_tc_kdn_pack_bytes(cin_pad, cout_pad, dgrad). */
+int vs_pack_conv3_weight_tc_kdn_padded(const float* w, void* out, int cin, int cout, int cin_pad, int cout_pad, int dgrad,
+                                       void* stream);
+/* Planar fp32 output out[N][2][D][H][W] of GEMM output channels 0..1 of an 8-output-channel kd-in-N convolution:
+ * mode 1 = the 2-class head, softmax_c(conv3(x, w) + bias) in one launch (as vs_head_conv_softmax2_fwd;
+ * joint_model.py:224-225,366-367); mode 2 = plain values (the planar 2-channel input gradient of the VAE in-block,
+ * as vs_conv3x3x3_dgrad with out_planar = 1).  x bf16 NDHWC with gin = 8 or a multiple of 16 channels, D >= 4. */
+int vs_conv3x3x3_tc_kdn_planar(const void* x, const void* wkdn8, float* out, const float* bias, int mode,
+                               int n, int d, int h, int w, int gin, void* stream);
 /* dw[Cout,Cin,27] (+)= sum_v dy[v,co] * x[v+tap,ci]; db[Cout] (+)= sum_v dy (db may be NULL).
  * x may be planar fp32 (in_planar=1).  accumulate=0 overwrites.  workspace: fp32
  * vs_conv3_wgrad_workspace_bytes() bytes (partial sums).                                 */

@@ -44,6 +44,8 @@ def _disk_get(key):
 
 
 def _disk_put(key, value):
+    if key[1] < 20:          # short recipes (the golden check of the recipe itself) are cheaper to redo than to ship
+        return
     try:
         os.makedirs(_DISK, exist_ok=True)
         torch.save(value, os.path.join(_DISK, "_".join(str(k) for k in key) + ".pt"))

@@ -167,6 +167,70 @@ def test_tc_inblock2_planar_dgrad(case):
     assert (dx.cpu() - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("case", [(2, 5, 17, 9, 8), (1, 8, 16, 8, 16), (1, 7, 20, 19, 8), (1, 4, 33, 12, 16)])
+def test_tc_kdn_planar_head_and_inblock_dgrad(case):
+    """kd-in-N kernel with the planar fp32 epilogue: mode 1 = 2-class head (weights zero-padded to 8 output channels,
+    bias + softmax fused), mode 2 = the 2-channel planar input gradient of an in-block (input channels padded to 8);
+    plus the head's 8-channel dgrad through the padded dgrad pack.  All against torch on the same bf16 operands."""
+    n, d, h, w, cin = case
+    torch.manual_seed(sum(case) + 11)
+    x = torch.randn(n, cin, d, h, w).bfloat16().float()
+    wt = torch.randn(2, cin, 3, 3, 3) * 0.2
+    b = torch.randn(2)
+    ref = F.softmax(F.conv3d(x, wt.bfloat16().float(), b, padding=1), dim=1)
+    wk8 = ops.pack_conv3_weight_tc_kdn_padded(wt.to(DEV), cin, 8, dgrad=False)
+    assert wk8 is not None
+    probs = ops.conv3_tc_kdn_planar(to_ndhwc(x), wk8, (n, d, h, w), cin, 1, bias=b.to(DEV))
+    torch.cuda.synchronize()
+    assert probs.shape == ref.shape and probs.dtype == torch.float32
+    assert (probs.cpu() - ref).abs().max().item() < 2e-3
+    assert (probs.cpu().argmax(1) == ref.argmax(1)).float().mean().item() > 0.999
+    # head dgrad: 8-channel padded logit gradient (channels 2..7 arbitrary: their weights are zero) -> Cin channels
+    gl = torch.randn(n, 8, d, h, w).bfloat16().float()
+    dref = F.conv_transpose3d(gl[:, :2], wt.bfloat16().float(), None, padding=1)
+    wkd8 = ops.pack_conv3_weight_tc_kdn_padded(wt.to(DEV), cin, 8, dgrad=True)
+    assert wkd8 is not None
+    dx, _ = ops.conv3_tc_kdn(to_ndhwc(gl), wkd8, (n, d, h, w), 8, cin)
+    torch.cuda.synchronize()
+    assert (from_ndhwc(dx) - dref).abs().max().item() < 1e-2 * dref.abs().max().item()
+    if cin == 8:
+        # in-block 2 -> 8: planar 2-channel input gradient
+        wi = torch.randn(8, 2, 3, 3, 3) * 0.2
+        gy = torch.randn(n, 8, d, h, w).bfloat16().float()
+        iref = F.conv_transpose3d(gy, wi.bfloat16().float(), None, padding=1)
+        wki = ops.pack_conv3_weight_tc_kdn_padded(wi.to(DEV), 8, 8, dgrad=True)
+        dxi = ops.conv3_tc_kdn_planar(to_ndhwc(gy), wki, (n, d, h, w), 8, 2)
+        torch.cuda.synchronize()
+        assert dxi.shape == iref.shape and dxi.dtype == torch.float32
+        assert (dxi.cpu() - iref).abs().max().item() < 2e-3 * iref.abs().max().item()
+
+
+def test_batched_repack_matches_per_layer_packs():
+    """engine.PackCache.repack_all (one launch for every derived pack, incl. the padded kd-in-N packs of the head and the
+    2-channel in-block) writes exactly what the per-layer pack entry points write."""
+    from vae_segmentation_b200 import engine
+    torch.manual_seed(5)
+    cache = engine.PackCache()
+    w_head = (torch.randn(2, 8, 3, 3, 3) * 0.3).to(DEV)
+    w_in = (torch.randn(8, 2, 3, 3, 3) * 0.3).to(DEV)
+    w_c = (torch.randn(16, 8, 3, 3, 3) * 0.3).to(DEV)
+    first = {"hk": cache.head_kdn(w_head), "ht": cache.head_tc(w_head), "ik": cache.inblock2_dgrad_kdn(w_in),
+             "it": cache.inblock2_dgrad_tc(w_in), "ck": cache.conv3_kdn(w_c), "ckd": cache.conv3_kdn(w_c, dgrad=True)}
+    flat = lambda d: [t for v in d.values() for t in (v if isinstance(v, tuple) else (v,))]
+    assert all(t is not None for t in flat(first))
+    before = [t.clone() for t in flat(first)]
+    for wt in (w_head, w_in, w_c):
+        wt.mul_(-1.5)                                  # new weights, same storage
+    cache.repack_all()
+    torch.cuda.synchronize()
+    fresh = engine.PackCache()
+    want = {"hk": fresh.head_kdn(w_head), "ht": fresh.head_tc(w_head), "ik": fresh.inblock2_dgrad_kdn(w_in),
+            "it": fresh.inblock2_dgrad_tc(w_in), "ck": fresh.conv3_kdn(w_c), "ckd": fresh.conv3_kdn(w_c, dgrad=True)}
+    for got, exp, old in zip(flat(first), flat(want), before):
+        assert torch.equal(got, exp)
+        assert not torch.equal(got, old)
+
+
 KDN_CASES = [(1, 4, 16, 8, 8, 8), (2, 5, 17, 9, 8, 8), (1, 8, 18, 10, 16, 8), (1, 7, 20, 19, 8, 16), (2, 6, 9, 11, 16, 16),
              (1, 12, 24, 24, 32, 16)]
 

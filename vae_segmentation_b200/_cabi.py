@@ -31,6 +31,8 @@ _SIGNATURES = {
     "vs_head_conv_softmax2_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "vs_conv3_tc_kdn_pack_bytes": [_I, _I, _I],
     "vs_pack_conv3_weight_tc_kdn": [_P, _P, _I, _I, _I, _P],
+    "vs_pack_conv3_weight_tc_kdn_padded": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "vs_conv3x3x3_tc_kdn_planar": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "vs_conv3x3x3_tc_kdn": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "vs_conv3x3x3_tc_kdn_ex": [_P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "vs_conv3x3x3_fprop": [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],

@@ -675,7 +675,7 @@ __global__ void __launch_bounds__(256) pack_batched_kernel(const vs_pack_job* __
     }
     if (j.kdn != nullptr) {
         bf16* o = (bf16*)j.kdn;
-        for (long long i = t0; i < j.kdn_elems; i += stride) o[i] = __float2bfloat16_rn(pack_kdn_elem(w, i, cin, cout, j.kdn_dgrad));
+        for (long long i = t0; i < j.kdn_elems; i += stride) o[i] = __float2bfloat16_rn(pack_kdn_elem(w, i, cinpad, cpad, j.kdn_dgrad, cin, cout));
     }
 }
 

@@ -67,6 +67,11 @@ struct KdnParams {
     const double* pstats;
     double* psums;
     double inv_s;
+    // planar fp32 output of GEMM output channels 0..1 instead of the bf16 NDHWC store (NCO = 8; see conv3_tc.cu TcParams):
+    // 1 = 2-class head, probs = softmax(acc + bias); 2 = plain values (2-channel planar input gradient)
+    int planar_mode;
+    float* yplanar;
+    const float* bias;
     int ordered;             // 1: one issuer warp issues the whole (plane, tap) list in a fixed order (bit-reproducible sums)
     long long* dbg;          // tools/kdn_phase_probe.py: clock64 stamps of CTA 0 around its 9th tile, or null
 };
@@ -311,6 +316,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kdn_kernel(const __grid_
         const bool has_shift = p.shift != nullptr;
         const bool has_stats = p.stats != nullptr;
         const uint32_t sshift_addr = smem_u32(my_shift);
+        float hb0 = 0.f, hb1 = 0.f;
+        if (p.planar_mode == 1 && p.bias != nullptr) { hb0 = p.bias[0]; hb1 = p.bias[1]; }
+        const long long vol = (long long)p.d * p.h * p.w;
         const uint32_t smean_addr = smem_u32(smean + 16 * e), srstd_addr = smem_u32(srstd + 16 * e);
         const int ref_row = rh * TW + rw;
         for (int item = blockIdx.x + e * (int)gridDim.x; item < p.work_items; item += NEPI * (int)gridDim.x, jt += NEPI) {
@@ -423,7 +431,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kdn_kernel(const __grid_
                         for (int k = 0; k < 8; ++k) v[NCO == 16 ? 8 + k : k] = __uint_as_float(r8[k]) - shr[8 + k];
                     }
                 }
-                if (rc_ok) {
+                if (p.planar_mode != 0) {
+                    if (rc_ok) {
+                        float o0 = v[0] + hb0, o1 = v[1] + hb1;
+                        if (p.planar_mode == 1) {
+                            const float mx = fmaxf(o0, o1);
+                            const float e0 = expf(o0 - mx), e1 = expf(o1 - mx);
+                            const float inv = 1.f / (e0 + e1);
+                            o0 = e0 * inv; o1 = e1 * inv;
+                        }
+                        float* pp = p.yplanar + (long long)n * 2 * vol + ((long long)(d0 + pl) * p.h + gh) * p.w + gw;
+                        pp[0] = o0;
+                        pp[vol] = o1;
+                    }
+                } else if (rc_ok) {
                     bf16* py = p.y + ((((long long)n * p.d + d0 + pl) * p.h + gh) * (long long)p.w + gw) * p.cout;
 #pragma unroll
                     for (int h8 = 0; h8 < NCO / 8; ++h8) {
@@ -485,9 +506,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kdn_kernel(const __grid_
     }
 }
 
-__global__ void pack_kdn_kernel(const float* __restrict__ w, bf16* __restrict__ out, int cin, int cout, int dgrad, long long total) {
+__global__ void pack_kdn_kernel(const float* __restrict__ w, bf16* __restrict__ out, int cin, int cout, int dgrad, long long total,
+                                int cin_real, int cout_real) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
-        out[i] = __float2bfloat16_rn(pack_kdn_elem(w, i, cin, cout, dgrad));
+        out[i] = __float2bfloat16_rn(pack_kdn_elem(w, i, cin, cout, dgrad, cin_real, cout_real));
 }
 
 template <bool CIN8, int NCO, int NSTAGE>
@@ -523,13 +545,21 @@ extern "C" size_t vs_conv3_tc_kdn_pack_bytes(int cin, int cout, int dgrad) {
     return (size_t)kslices * (gin == 8 ? 5 : 9) * 4 * gout * 32;
 }
 
-extern "C" int vs_pack_conv3_weight_tc_kdn(const float* w, void* out, int cin, int cout, int dgrad, void* stream) {
-    const size_t bytes = vs_conv3_tc_kdn_pack_bytes(cin, cout, dgrad);
-    VS_REQUIRE(w && out && bytes > 0, VS_ERR_UNSUPPORTED, "pack_conv3_weight_tc_kdn: unsupported shape Cin=%d Cout=%d", cin, cout);
+// w[cout][cin][27] fp32 -> kd-in-N pack of a layer with cin_pad x cout_pad channels (the missing ones zero); the pack
+// has vs_conv3_tc_kdn_pack_bytes(cin_pad, cout_pad, dgrad) bytes.
+extern "C" int vs_pack_conv3_weight_tc_kdn_padded(const float* w, void* out, int cin, int cout, int cin_pad, int cout_pad,
+                                                  int dgrad, void* stream) {
+    VS_REQUIRE(cin_pad >= cin && cout_pad >= cout, VS_ERR_SHAPE, "pack_conv3_weight_tc_kdn: padded channel counts below the real ones");
+    const size_t bytes = vs_conv3_tc_kdn_pack_bytes(cin_pad, cout_pad, dgrad);
+    VS_REQUIRE(w && out && bytes > 0, VS_ERR_UNSUPPORTED, "pack_conv3_weight_tc_kdn: unsupported shape Cin=%d Cout=%d", cin_pad, cout_pad);
     const long long total = (long long)(bytes / 2);
-    pack_kdn_kernel<<<(unsigned)min(1024LL, (total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, (bf16*)out, cin, cout, dgrad, total);
+    pack_kdn_kernel<<<(unsigned)min(1024LL, (total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, (bf16*)out, cin_pad, cout_pad,
+                                                                                                  dgrad, total, cin, cout);
     VS_CHECK_LAUNCH("pack_kdn_kernel");
     return VS_OK;
+}
+extern "C" int vs_pack_conv3_weight_tc_kdn(const float* w, void* out, int cin, int cout, int dgrad, void* stream) {
+    return vs_pack_conv3_weight_tc_kdn_padded(w, out, cin, cout, cin, cout, dgrad, stream);
 }
 
 // y[n,d,h,w,gout] = conv3(x[n,d,h,w,gin], wkdn); bf16 NDHWC in and out; gout in {8, 16}; D >= 4.
@@ -544,10 +574,12 @@ extern "C" int vs_conv3x3x3_tc_kdn(const void* x, const void* wkdn, void* y, dou
 
 // As vs_conv3x3x3_tc_kdn; psums != NULL (dgrad): also accumulates the previous layer's InstanceNorm-backward sums
 // psums[n][gout][2] += (sum g*mask, sum g*mask*xhat) from yprev / pstats (zeroed by the caller; no stats / shift then).
-extern "C" int vs_conv3x3x3_tc_kdn_ex(const void* x, const void* wkdn, void* y, double* stats, float* shift, int prezeroed,
-                                      const void* yprev, const double* pstats, double* psums,
-                                      int n, int d, int h, int w, int gin, int gout, void* stream) {
-    VS_REQUIRE(x && wkdn && y, VS_ERR_SHAPE, "conv3_tc_kdn: null pointer");
+static int run_kdn(const void* x, const void* wkdn, void* y, double* stats, float* shift, int prezeroed,
+                   const void* yprev, const double* pstats, double* psums, int planar_mode, float* yplanar, const float* bias,
+                   int n, int d, int h, int w, int gin, int gout, void* stream) {
+    VS_REQUIRE(x && wkdn && (y || planar_mode), VS_ERR_SHAPE, "conv3_tc_kdn: null pointer");
+    if (planar_mode) VS_REQUIRE(yplanar && gout == 8 && !stats && !shift && !psums, VS_ERR_SHAPE,
+                                "conv3_tc_kdn: planar output needs Cout padded to 8 and no statistics");
     VS_REQUIRE((gin == 8 || (gin % 16 == 0 && gin >= 16)) && (gout == 8 || gout == 16) && d >= TD, VS_ERR_UNSUPPORTED,
                "conv3_tc_kdn: needs Cin = 8 or a multiple of 16, Cout in {8,16}, D >= 4 (Cin=%d Cout=%d D=%d)", gin, gout, d);
     VS_REQUIRE(vs_aligned16(x) && vs_aligned16(y) && vs_aligned16(wkdn), VS_ERR_ALIGN, "conv3_tc_kdn: pointers must be 16B aligned");
@@ -590,6 +622,7 @@ extern "C" int vs_conv3x3x3_tc_kdn_ex(const void* x, const void* wkdn, void* y, 
     p.work_items = (int)items;
     p.wpack = (const bf16*)wkdn; p.y = (bf16*)y; p.stats = stats; p.shift = shift;
     p.yprev = (const bf16*)yprev; p.pstats = pstats; p.psums = psums; p.inv_s = 1.0 / ((double)d * h * w);
+    p.planar_mode = planar_mode; p.yplanar = yplanar; p.bias = bias;
     p.dbg = g_kdn_dbg;
     p.ordered = g_kdn_ordered;
     if (psums != nullptr) {
@@ -607,4 +640,20 @@ extern "C" int vs_conv3x3x3_tc_kdn_ex(const void* x, const void* wkdn, void* y, 
     }
     if (gout == 8) return launch_kdn<false, 8, 4>(map, p, st);
     return launch_kdn<false, 16, 4>(map, p, st);
+}
+
+extern "C" int vs_conv3x3x3_tc_kdn_ex(const void* x, const void* wkdn, void* y, double* stats, float* shift, int prezeroed,
+                                      const void* yprev, const double* pstats, double* psums,
+                                      int n, int d, int h, int w, int gin, int gout, void* stream) {
+    return run_kdn(x, wkdn, y, stats, shift, prezeroed, yprev, pstats, psums, 0, nullptr, nullptr, n, d, h, w, gin, gout, stream);
+}
+
+// Planar fp32 output of GEMM output channels 0..1 of an 8-channel kd-in-N convolution (pack built with
+// vs_pack_conv3_weight_tc_kdn_padded): mode 1 = the 2-class head, out[N][2][D][H][W] = softmax(conv + bias)
+// (joint_model.py:224-225,366-367); mode 2 = plain values (the VAE in-block's 2-channel planar input gradient).
+extern "C" int vs_conv3x3x3_tc_kdn_planar(const void* x, const void* wkdn8, float* out, const float* bias, int mode,
+                                          int n, int d, int h, int w, int gin, void* stream) {
+    VS_REQUIRE(mode == 1 || mode == 2, VS_ERR_SHAPE, "conv3_tc_kdn_planar: mode must be 1 (softmax head) or 2 (plain)");
+    return run_kdn(x, wkdn8, nullptr, nullptr, nullptr, 1, nullptr, nullptr, nullptr, mode, out, mode == 1 ? bias : nullptr,
+                   n, d, h, w, gin, 8, stream);
 }

@@ -54,7 +54,12 @@ __device__ __forceinline__ float pack_tc_elem(const float* __restrict__ w, long 
 //   m  -> in-plane tap(s): Cin = 8: taps 2m (kc 0) and 2m+1 (kc 1) of the 9 (kh,kw) taps, the 10th is zero;
 //                          else   : tap m = kh*3 + kw, kc selects channels 0-7 / 8-15 of the slice
 // dgrad = same contraction with (ci,co) swapped and taps flipped.
-__device__ __forceinline__ float pack_kdn_elem(const float* __restrict__ w, long long i, int cin_l, int cout_l, int dgrad) {
+// cin_real / cout_real < cin_l / cout_l: the master weight is [cout_real][cin_real][27] and the missing channels are zero
+// (2-class head padded to 8 output channels, 2-channel in-block padded to 8 input channels).
+__device__ __forceinline__ float pack_kdn_elem(const float* __restrict__ w, long long i, int cin_l, int cout_l, int dgrad,
+                                               int cin_real = -1, int cout_real = -1) {
+    if (cin_real < 0) cin_real = cin_l;
+    if (cout_real < 0) cout_real = cout_l;
     const int gin = dgrad ? cout_l : cin_l, gout = dgrad ? cin_l : cout_l;
     const bool cin8 = gin == 8;
     const int nmp = cin8 ? 5 : 9, ngroups = 4 * gout / 8;
@@ -71,8 +76,12 @@ __device__ __forceinline__ float pack_kdn_elem(const float* __restrict__ w, long
     else { gi = ks * 16 + kc * 8 + ch8; t = m; }
     if (kdp > 2 || t < 0 || gi >= gin) return 0.f;
     const int tap = kdp * 9 + t;                              // (kd', kh, kw) in the GEMM's (input-side) orientation
-    if (dgrad) return w[((long long)gi * cin_l + go) * 27 + (26 - tap)];      // w[co = gi][ci = go][flipped tap]
-    return w[((long long)go * cin_l + gi) * 27 + tap];
+    if (dgrad) {                                              // w[co = gi][ci = go][flipped tap]
+        if (gi >= cout_real || go >= cin_real) return 0.f;
+        return w[((long long)gi * cin_real + go) * 27 + (26 - tap)];
+    }
+    if (go >= cout_real || gi >= cin_real) return 0.f;
+    return w[((long long)go * cin_real + gi) * 27 + tap];
 }
 
 

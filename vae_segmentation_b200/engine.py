@@ -28,6 +28,7 @@ C3IN, K2DOWN, K2UP, HEAD = "c3in", "k2down", "k2up", "head"
 USE_TENSOR_CORES = os.environ.get("VAESEG_NO_TC", "0") != "1"
 # VAESEG_NO_FUSE_REDUCE=1 keeps the InstanceNorm-backward reduction a separate pass (A/B measurements, parity tests)
 FUSE_BWD_REDUCE = os.environ.get("VAESEG_NO_FUSE_REDUCE", "0") != "1"
+FUSE_BWD_REDUCE_MAX_VOX = int(os.environ.get("VAESEG_FUSE_REDUCE_MAX_VOX", "0"))      # 0 = no limit (voxels per sample)
 HEAD_DIRECT = os.environ.get("VAESEG_HEAD_DIRECT", "0") == "1"
 # The forward 3x3x3 convolutions with 8 / 16 output channels at >= 48^3 run through the kd-in-N kernel
 # (csrc/conv3_tc_kdn.cu: the three kd taps folded into the MMA's N, halving the A-operand shared-memory traffic).
@@ -156,6 +157,31 @@ class PackCache(object):
             ent["key"] = key
         return ent["tcd"]
 
+    def _kdn_padded(self, kind, w, cin_pad, cout_pad, dgrad):
+        ent, key = self._entry(kind, w, True)
+        if ent["key"] != key:
+            had = ent["kdn"] is not None
+            ent["kdn"] = ops.pack_conv3_weight_tc_kdn_padded(w.detach(), cin_pad, cout_pad, dgrad=dgrad, out=ent["kdn"])
+            if not had:
+                self._jobs = None
+            ent["tc"] = True
+            ent["key"] = key
+        return ent["kdn"]
+
+    def head_kdn(self, w):
+        """kd-in-N (fprop, dgrad) packs of the head weight [n_class,Cin,3,3,3] zero-padded to 8 output channels (the
+        full-resolution head through the kd-in-N kernel), entries None where that kernel does not take the shape."""
+        if not (USE_TENSOR_CORES and USE_KDN):
+            return None, None
+        cin = w.shape[1]
+        return (self._kdn_padded("head8kdn", w, cin, 8, False), self._kdn_padded("head8kdnd", w, cin, 8, True))
+
+    def inblock2_dgrad_kdn(self, w):
+        """kd-in-N dgrad pack of a 2-input-channel in-block weight with the input channels zero-padded to 8, or None."""
+        if not (USE_TENSOR_CORES and USE_KDN):
+            return None
+        return self._kdn_padded("inblk8kdnd", w, 8, w.shape[0], True)
+
     def conv3_kdn(self, w, dgrad=False):
         """kd-in-N fprop (or dgrad) pack of a 3x3x3 weight (re-packed in place, part of the batched re-pack), or None."""
         ent, key = self._entry("kdnd" if dgrad else "kdn", w, True)
@@ -197,8 +223,8 @@ class PackCache(object):
                 w = e["w"].detach()
                 j.w = w.data_ptr()
                 j.cout, j.cin = w.shape[0], w.shape[1]
-                j.cout_pad = 8 if e["kind"] == "head8" else w.shape[0]
-                j.cin_pad = 8 if e["kind"] == "inblk8" else 0
+                j.cout_pad = 8 if e["kind"] in ("head8", "head8kdn", "head8kdnd") else w.shape[0]
+                j.cin_pad = 8 if e["kind"] in ("inblk8", "inblk8kdnd") else 0
                 j.wf = e["wf"].data_ptr() if e["wf"] is not None else None
                 j.wd = e["wd"].data_ptr() if e["wd"] is not None else None
                 j.tcf = e["tcf"].data_ptr() if e["tcf"] is not None else None
@@ -208,7 +234,7 @@ class PackCache(object):
                 j.kdn = e["kdn"].data_ptr() if e["kdn"] is not None else None
                 j.kdn_elems = e["kdn"].numel() if e["kdn"] is not None else 0
                 j.kind = 1 if e["kind"] == "k2s2" else 0         # k2s2: w = wt[A = shape[0]][B = shape[1]][8]
-                j.kdn_dgrad = 1 if e["kind"] == "kdnd" else 0
+                j.kdn_dgrad = 1 if e["kind"] in ("kdnd", "head8kdnd", "inblk8kdnd") else 0
             host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
             self._jobs = (host.to(ents[0]["w"].device), len(ents), ents)
         ops.pack_conv3_batched(self._jobs[0], self._jobs[1])
@@ -317,8 +343,11 @@ def program_forward(layers, tensors, x, dims, dtype, cache, record=True):
     for L in layers:
         if L.kind == C3IN:
             wf, wd, wtc, wdtc = cache.conv3(tensors[L.wi], tc=(dtype == torch.bfloat16))
+            wkd_in = None
             if L.in_planar and L.cin == 2 and record and dtype == torch.bfloat16 and L.cout % 8 == 0:
                 wdtc = cache.inblock2_dgrad_tc(tensors[L.wi])      # planar 2-channel input gradient on the tensor cores
+                if L.cout == 8 and d >= 4 and d * h * w >= 48 ** 3:
+                    wkd_in = cache.inblock2_dgrad_kdn(tensors[L.wi])       # ... through the kd-in-N kernel at full resolution
             # the conv bias is a no-op ahead of InstanceNorm(affine=False): skipped
             wk = None
             if (USE_KDN and USE_TENSOR_CORES and dtype == torch.bfloat16 and not L.in_planar and L.cout in (8, 16)
@@ -337,7 +366,7 @@ def program_forward(layers, tensors, x, dims, dtype, cache, record=True):
                 if (USE_KDN and USE_TENSOR_CORES and dtype == torch.bfloat16 and not L.in_planar and L.cin in (8, 16)
                         and _tc_channels(L.cout) and d >= 4 and d * h * w >= 48 ** 3):
                     wkd = cache.conv3_kdn(tensors[L.wi], dgrad=True)       # input gradient through the kd-in-N kernel too
-                tape.append((L, cur, y, stats, (n, d, h, w), (wd, wdtc, wkd)))
+                tape.append((L, cur, y, stats, (n, d, h, w), (wd, wdtc, wkd, wkd_in)))
             cur = a
         elif L.kind == K2DOWN:
             d, h, w = d // 2, h // 2, w // 2
@@ -359,7 +388,14 @@ def program_forward(layers, tensors, x, dims, dtype, cache, record=True):
                 wtc8, wdtc = cache.head_tc(tensors[L.wi])
                 if HEAD_DIRECT:          # A/B switch: fp32-weight CUDA-core head forward (backward stays on the tensor cores)
                     wtc8 = None
-            if wtc8 is not None:
+            wk8 = wkd8 = None
+            if wtc8 is not None and USE_KDN and d >= 4 and d * h * w >= 48 ** 3:
+                wk8, wkd8 = cache.head_kdn(tensors[L.wi])
+            if wk8 is not None:
+                # conv + bias + softmax + planar store in ONE kd-in-N launch
+                wd = None
+                probs = ops.conv3_tc_kdn_planar(cur, wk8, (n, d, h, w), L.cin, 1, bias=tensors[L.bi].detach())
+            elif wtc8 is not None:
                 # conv + bias + softmax + planar store in ONE tensor-core launch
                 wd = None
                 probs = ops.head_conv_softmax2(cur, wtc8, tensors[L.bi].detach(), (n, d, h, w), L.cin)
@@ -369,7 +405,7 @@ def program_forward(layers, tensors, x, dims, dtype, cache, record=True):
                                             in_planar=L.in_planar, want_stats=False)
                 probs = ops.softmax2_fwd(logits, (n, d, h, w))
             if record:
-                tape.append((L, cur, probs, None, (n, d, h, w), (wd, wdtc)))
+                tape.append((L, cur, probs, None, (n, d, h, w), (wd, wdtc, wkd8)))
             cur = probs
         else:
             raise RuntimeError("unknown layer kind %r" % (L.kind,))
@@ -396,6 +432,9 @@ def program_backward(tape, g, dtype, need, grads, param_refs, need_input_grad):
             return None
         Lp = tape[idx - 1][0]
         if Lp.kind != C3IN or (Lp.save_as is not None and Lp.save_as in pending):
+            return None
+        dd = tape[idx][4]
+        if FUSE_BWD_REDUCE_MAX_VOX and dd[1] * dd[2] * dd[3] > FUSE_BWD_REDUCE_MAX_VOX:
             return None
         if not ops.dgrad_can_fuse_reduce(dy_like, cin, cout, dtype, False, wdtc, tape[idx][4]):
             return None
@@ -438,6 +477,8 @@ def program_backward(tape, g, dtype, need, grads, param_refs, need_input_grad):
             if want_dx and len(wd) > 2 and wd[2] is not None:
                 # full-resolution layers: kd-in-N kernel (GEMM input = the layer's Cout, output = its Cin in {8, 16})
                 g, _ = ops.conv3_tc_kdn(dy, wd[2], dims, L.cout, L.cin, prev=fuse_prev(idx, dy, L.cin, L.cout, wd[1]))
+            elif want_dx and len(wd) > 3 and wd[3] is not None and not SIMULATE_BF16:
+                g = ops.conv3_tc_kdn_planar(dy, wd[3], dims, L.cout, 2)        # planar 2-channel input gradient (VAE in-block)
             else:
                 g = _sim(ops.conv3_dgrad(dy, wd[0], dims, L.cin, L.cout, dtype, out_planar=L.in_planar, wdtc=wd[1],
                                          prev=None if L.in_planar else fuse_prev(idx, dy, L.cin, L.cout, wd[1])), "g") \
@@ -482,8 +523,11 @@ def program_backward(tape, g, dtype, need, grads, param_refs, need_input_grad):
                 if need[L.wi] or need[L.bi]:
                     _hand_back(grads, need, L.wi, L.bi, tw, tb, acc)
                 _grad_ready(param_refs[L.wi], param_refs[L.bi])
-                g = ops.conv3_dgrad(dl8, None, dims, L.cin, 8, dtype, wdtc=wd[1],
-                                    prev=fuse_prev(idx, dl8, L.cin, 8, wd[1])) if want_dx else None
+                if want_dx and len(wd) > 2 and wd[2] is not None and L.cin in (8, 16):
+                    g, _ = ops.conv3_tc_kdn(dl8, wd[2], dims, 8, L.cin, prev=fuse_prev(idx, dl8, L.cin, 8, wd[1]))
+                else:
+                    g = ops.conv3_dgrad(dl8, None, dims, L.cin, 8, dtype, wdtc=wd[1],
+                                        prev=fuse_prev(idx, dl8, L.cin, 8, wd[1])) if want_dx else None
                 continue
             dlogits = _sim(ops.softmax2_bwd(g, probs, dims, dtype), "dy")
             if need[L.wi] or need[L.bi]:

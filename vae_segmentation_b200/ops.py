@@ -479,6 +479,32 @@ def pack_conv3_weight_tc_kdn(w, dgrad=False, out=None):
     return out
 
 
+def pack_conv3_weight_tc_kdn_padded(w, cin_pad, cout_pad, dgrad=False, out=None):
+    """kd-in-N pack of w [Cout,Cin,3,3,3] with the channels zero-padded to cin_pad x cout_pad (2-class head, 2-channel
+    in-block input gradient), or None when the kernel does not take the padded shape.  `out` re-packs in place."""
+    cout, cin = w.shape[0], w.shape[1]
+    nbytes = _cabi.lib().vs_conv3_tc_kdn_pack_bytes(cin_pad, cout_pad, int(dgrad))
+    if nbytes == 0:
+        return None
+    if out is None:
+        out = torch.empty(nbytes // 2, device=w.device, dtype=torch.bfloat16)
+    _cabi.call("vs_pack_conv3_weight_tc_kdn_padded", _p(_f32(w, "weight")), _p(out), cin, cout, cin_pad, cout_pad, int(dgrad),
+               _stream())
+    return out
+
+
+def conv3_tc_kdn_planar(x, wkdn8, dims, gin, mode, bias=None):
+    """out [N,2,D,H,W] fp32 = channels 0..1 of an 8-output-channel kd-in-N convolution: mode 1 softmax(conv + bias) (the
+    2-class head), mode 2 plain values (planar 2-channel input gradient)."""
+    n, d, h, w = dims
+    if x.dtype != torch.bfloat16:
+        raise RuntimeError("vaeseg_b200: conv3_tc_kdn_planar takes bf16 NDHWC activations")
+    out = torch.empty(n, 2, d, h, w, device=x.device, dtype=torch.float32)
+    _cabi.call("vs_conv3x3x3_tc_kdn_planar", _p(x), _p(wkdn8), _p(out), _p(_f32(bias, "bias") if bias is not None else None),
+               int(mode), n, d, h, w, gin, _stream())
+    return out
+
+
 def conv3_tc_kdn(x, wkdn, dims, gin, gout, want_stats=False, arena=None, prev=None):
     """y (bf16 NDHWC) = conv3(x, wkdn) through the kd-in-N kernel; returns (y, stats or None).
     arena: zero-filled StatsArena supplying the statistics / shift words (as conv3_fprop).  prev = (y_prev, stats_prev,
