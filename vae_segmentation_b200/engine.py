@@ -34,6 +34,12 @@ HEAD_DIRECT = os.environ.get("VAESEG_HEAD_DIRECT", "0") == "1"
 # (csrc/conv3_tc_kdn.cu: the three kd taps folded into the MMA's N, halving the A-operand shared-memory traffic).
 # Measured on B200, joint step 2 x 96^3: 345.3 vs 327.2 vol/s.  VAESEG_KDN=0 falls back to the tap-per-MMA kernel.
 USE_KDN = os.environ.get("VAESEG_KDN", "1") == "1"
+# Full-resolution 2-channel in-block (the VAE's: planar fp32 probabilities in): convert the input once to 8 zero-padded
+# bf16 channels and run the kd-in-N kernel instead of the CUDA-core in-block kernel (91 us -> 14 + 40 us at 2 x 96^3); the
+# converted input is reused by the weight gradient.  Not for the 1-channel image in-block of Segmentation: rounding the
+# IMAGE to bf16 moved the conditioned-fixture gradients of the 12^3 level from 4.x e-2 to 5.05e-2 of the floored norm
+# (north-star bound 5e-2) for 11 us.  VAESEG_INBLOCK_TC=0 keeps the CUDA-core kernel everywhere.
+INBLOCK_TC = os.environ.get("VAESEG_INBLOCK_TC", "1") == "1"
 # 2x2x2 stride-2 convolutions / transposed convolutions (forward and input gradient) on the tensor cores
 # (csrc/k2s2_tc.cu); VAESEG_K2_TC=0 keeps the CUDA-core kernels of csrc/k2s2.cu (A/B measurements).
 USE_K2_TC = os.environ.get("VAESEG_K2_TC", "1") == "1"
@@ -176,6 +182,12 @@ class PackCache(object):
         cin = w.shape[1]
         return (self._kdn_padded("head8kdn", w, cin, 8, False), self._kdn_padded("head8kdnd", w, cin, 8, True))
 
+    def inblock_kdn(self, w):
+        """kd-in-N fprop pack of an in-block weight [Cout,Cin<=2,3,3,3] with the input channels zero-padded to 8, or None."""
+        if not (USE_TENSOR_CORES and USE_KDN):
+            return None
+        return self._kdn_padded("inblk8kdn", w, 8, w.shape[0], False)
+
     def inblock2_dgrad_kdn(self, w):
         """kd-in-N dgrad pack of a 2-input-channel in-block weight with the input channels zero-padded to 8, or None."""
         if not (USE_TENSOR_CORES and USE_KDN):
@@ -224,7 +236,7 @@ class PackCache(object):
                 j.w = w.data_ptr()
                 j.cout, j.cin = w.shape[0], w.shape[1]
                 j.cout_pad = 8 if e["kind"] in ("head8", "head8kdn", "head8kdnd") else w.shape[0]
-                j.cin_pad = 8 if e["kind"] in ("inblk8", "inblk8kdnd") else 0
+                j.cin_pad = 8 if e["kind"] in ("inblk8", "inblk8kdn", "inblk8kdnd") else 0
                 j.wf = e["wf"].data_ptr() if e["wf"] is not None else None
                 j.wd = e["wd"].data_ptr() if e["wd"] is not None else None
                 j.tcf = e["tcf"].data_ptr() if e["tcf"] is not None else None
@@ -350,10 +362,18 @@ def program_forward(layers, tensors, x, dims, dtype, cache, record=True):
                     wkd_in = cache.inblock2_dgrad_kdn(tensors[L.wi])       # ... through the kd-in-N kernel at full resolution
             # the conv bias is a no-op ahead of InstanceNorm(affine=False): skipped
             wk = None
+            x8 = None
             if (USE_KDN and USE_TENSOR_CORES and dtype == torch.bfloat16 and not L.in_planar and L.cout in (8, 16)
                     and _tc_channels(L.cin) and d >= 4 and d * h * w >= 48 ** 3):
                 wk = cache.conv3_kdn(tensors[L.wi])
-            if wk is not None:
+            elif (USE_KDN and USE_TENSOR_CORES and INBLOCK_TC and dtype == torch.bfloat16 and L.in_planar and L.cin == 2
+                    and L.cout in (8, 16) and d >= 4 and d * h * w >= 48 ** 3 and not SIMULATE_BF16):
+                wk = cache.inblock_kdn(tensors[L.wi])
+                if wk is not None:
+                    x8 = ops.planar_to_ndhwc8(cur)
+            if x8 is not None:
+                y, stats = ops.conv3_tc_kdn(x8, wk, (n, d, h, w), 8, L.cout, want_stats=True, arena=arena)
+            elif wk is not None:
                 y, stats = ops.conv3_tc_kdn(cur, wk, (n, d, h, w), L.cin, L.cout, want_stats=True, arena=arena)
             else:
                 y, stats = ops.conv3_fprop(cur, wf, None, (n, d, h, w), L.cin, L.cout, dtype, in_planar=L.in_planar,
@@ -366,7 +386,7 @@ def program_forward(layers, tensors, x, dims, dtype, cache, record=True):
                 if (USE_KDN and USE_TENSOR_CORES and dtype == torch.bfloat16 and not L.in_planar and L.cin in (8, 16)
                         and _tc_channels(L.cout) and d >= 4 and d * h * w >= 48 ** 3):
                     wkd = cache.conv3_kdn(tensors[L.wi], dgrad=True)       # input gradient through the kd-in-N kernel too
-                tape.append((L, cur, y, stats, (n, d, h, w), (wd, wdtc, wkd, wkd_in)))
+                tape.append((L, cur, y, stats, (n, d, h, w), (wd, wdtc, wkd, wkd_in, x8)))
             cur = a
         elif L.kind == K2DOWN:
             d, h, w = d // 2, h // 2, w // 2
@@ -456,18 +476,19 @@ def program_backward(tape, g, dtype, need, grads, param_refs, need_input_grad):
             dy = _sim(ops.inorm_relu_bwd(g, y, stats, sums=sums_of[idx], reduced=idx in fused), "dy")
             if need[L.wi]:
                 tgt, acc = _grad_target(param_refs[L.wi], True)
-                def run_wgrad(L=L, x_in=x_in, dy=dy, dims=dims, tgt=tgt, acc=acc):
+                def run_wgrad(L=L, x_in=x_in, dy=dy, dims=dims, tgt=tgt, acc=acc, wd=wd):
                     if L.in_planar and dtype == torch.bfloat16 and USE_TENSOR_CORES and L.cin < 8 and L.cout % 8 == 0:
                         # in-block (Cin 1 or 2, planar fp32 input): pad the input to 8 bf16 channels and take the
                         # tensor-core wgrad; the padded input channels give zero rows that are dropped
-                        dw8, _ = ops.conv3_wgrad(ops.planar_to_ndhwc8(x_in), dy, dims, 8, L.cout)
+                        x8 = wd[4] if len(wd) > 4 and wd[4] is not None else ops.planar_to_ndhwc8(x_in)
+                        dw8, _ = ops.conv3_wgrad(x8, dy, dims, 8, L.cout)
                         if acc:
                             ops.atomic_add_rows(tgt, dw8, L.cout, L.cin * 27, 8 * 27)      # += dw8[:, :cin]; atomics:
                             # other per-sample backward chains may be adding onto the same .grad concurrently
                             return tgt
                         return dw8[:, :L.cin].contiguous()
                     return ops.conv3_wgrad(x_in, dy, dims, L.cin, L.cout, dw=tgt, in_planar=L.in_planar, accumulate=acc)[0]
-                dw = _wgrad_async(run_wgrad, acc, x_in, dy)
+                dw = _wgrad_async(run_wgrad, acc, x_in, dy, wd[4] if len(wd) > 4 else None)
                 grads[L.wi] = None if acc else dw
             if need[L.bi]:
                 # exactly zero: the bias cancels in InstanceNorm
