@@ -126,6 +126,17 @@ int vs_conv3x3x3_tc_kdn(const void* x, const void* wkdn, void* y, double* stats,
 int vs_conv3x3x3_tc_kdn_ex(const void* x, const void* wkdn, void* y, double* stats, float* shift, int prezeroed,
                            const void* yprev, const double* pstats, double* psums,
                            int n, int d, int h, int w, int gin, int gout, void* stream);
+/* Conv3d(3, padding 1) -> InstanceNorm3d(eps 1e-5, biased, no affine) -> ReLU (+ skip add) in ONE launch
+ * (joint_model.py:40-46,106 `Conv` / `DoubleConv`): the kernel is launched cooperatively, accumulates the statistics,
+ * passes a grid barrier and then turns the raw outputs it just stored (still in L2) into the activation
+ * a = relu((y - mean) * rstd) + skip -- the separate vs_inorm_relu_apply pass disappears.  y (raw, shifted; kept for the
+ * backward pass), a and skip are bf16 NDHWC [N,D,H,W,gout]; stats [N][gout][2] fp64, shift [N][gout] fp32 and the
+ * 32-bit word gbar must be ZERO on entry.  _tc_: tap-per-MMA kernel (pack of vs_pack_conv3_weight_tc); _tc_kdn_: kd-in-N
+ * kernel (pack of vs_pack_conv3_weight_tc_kdn; gout 8 or 16, D >= 4).  Same channel constraints as those kernels. */
+int vs_conv3x3x3_tc_in_relu(const void* x, const void* wtc, void* y, void* a, const void* skip, double* stats, float* shift,
+                            unsigned* gbar, int n, int d, int h, int w, int gin, int gout, void* stream);
+int vs_conv3x3x3_tc_kdn_in_relu(const void* x, const void* wkdn, void* y, void* a, const void* skip, double* stats,
+                                float* shift, unsigned* gbar, int n, int d, int h, int w, int gin, int gout, void* stream);
 /* kd-in-N pack of a layer whose channels are zero-padded to cin_pad x cout_pad (w is [cout][cin][27]): the 2-class head
  * (cout 2 -> 8) and the 2-channel in-block's input gradient (cin 2 -> 8).  Size: vs_conv3_tc_kdn_pack_bytes(cin_pad, cout_pad, dgrad). */
 int vs_pack_conv3_weight_tc_kdn_padded(const float* w, void* out, int cin, int cout, int cin_pad, int cout_pad, int dgrad,

@@ -231,6 +231,53 @@ def test_batched_repack_matches_per_layer_packs():
         assert not torch.equal(got, old)
 
 
+FUSED_CASES = [(2, 5, 17, 9, 8, 8, True), (1, 8, 18, 10, 16, 8, True), (2, 6, 9, 11, 16, 16, True), (1, 12, 24, 24, 32, 16, True),
+               (2, 5, 17, 9, 8, 8, False), (2, 6, 6, 6, 128, 128, False), (1, 12, 12, 12, 64, 32, False), (2, 3, 3, 3, 256, 64, False),
+               (1, 24, 24, 24, 32, 32, False), (1, 48, 40, 56, 8, 8, True)]
+
+
+@pytest.mark.parametrize("with_skip", [False, True])
+@pytest.mark.parametrize("case", FUSED_CASES)
+def test_tc_conv_instance_norm_relu_in_one_launch(case, with_skip):
+    """Conv3d -> InstanceNorm3d -> ReLU (+ skip) as ONE cooperative launch with an in-kernel grid barrier
+    (vs_conv3x3x3_tc[_kdn]_in_relu) against torch on the same bf16 operands and against conv + separate apply pass."""
+    n, d, h, w, cin, cout, kdn = case
+    torch.manual_seed(sum(case[:6]) + 23)
+    x = torch.randn(n, cin, d, h, w).bfloat16().float()
+    wt = torch.randn(cout, cin, 3, 3, 3) * 0.1
+    skip = torch.randn(n, cout, d, h, w).bfloat16().float() if with_skip else None
+    ref = F.relu(F.instance_norm(F.conv3d(x, wt.bfloat16().float(), None, padding=1), eps=1e-5))
+    if skip is not None:
+        ref = ref + skip
+    wd = wt.to(DEV)
+    dims = (n, d, h, w)
+    wpack = ops.pack_conv3_weight_tc_kdn(wd, dgrad=False) if kdn else ops.pack_conv3_weight_tc(wd, dgrad=False)
+    assert wpack is not None
+    skd = to_ndhwc(skip) if skip is not None else None
+    arena = ops.StatsArena(ops.stats_words(n, cout), DEV)
+    y, stats, a = ops.conv3_in_relu(to_ndhwc(x), wpack, dims, cin, cout, arena, skip=skd, kdn=kdn)
+    torch.cuda.synchronize()
+    assert (from_ndhwc(a) - ref).abs().max().item() < 3e-2 * max(1.0, ref.abs().max().item())
+    # the two-launch path on the same operands: same raw output and statistics (up to summation order), same activation
+    arena2 = ops.StatsArena(ops.stats_words(n, cout), DEV)
+    if kdn:
+        y2, stats2 = ops.conv3_tc_kdn(to_ndhwc(x), wpack, dims, cin, cout, want_stats=True, arena=arena2)
+    else:
+        wf, _ = ops.pack_conv3_weight(wd)
+        y2, stats2 = ops.conv3_fprop(to_ndhwc(x), wf, None, dims, cin, cout, torch.bfloat16, wtc=wpack, arena=arena2)
+    a2 = ops.inorm_relu_apply(y2, stats2, skd)
+    torch.cuda.synchronize()
+    scale = y2.float().abs().max().item()
+    assert (y.float() - y2.float()).abs().max().item() <= 1e-2 * scale           # kd-in-N issue order: a bf16 ulp at most
+    assert torch.allclose(stats, stats2, rtol=1e-3, atol=1e-3 * stats2.abs().max().item())
+    assert (a.float() - a2.float()).abs().max().item() <= 2e-2 * max(1.0, a2.float().abs().max().item())
+    # a second launch reusing nothing: the barrier word is consumed per launch
+    arena3 = ops.StatsArena(ops.stats_words(n, cout), DEV)
+    _, _, a3 = ops.conv3_in_relu(to_ndhwc(x), wpack, dims, cin, cout, arena3, skip=skd, kdn=kdn)
+    torch.cuda.synchronize()
+    assert (a3.float() - a.float()).abs().max().item() <= 2e-2 * max(1.0, a2.float().abs().max().item())
+
+
 KDN_CASES = [(1, 4, 16, 8, 8, 8), (2, 5, 17, 9, 8, 8), (1, 8, 18, 10, 16, 8), (1, 7, 20, 19, 8, 16), (2, 6, 9, 11, 16, 16),
              (1, 12, 24, 24, 32, 16)]
 

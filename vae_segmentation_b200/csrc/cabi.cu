@@ -119,6 +119,14 @@ extern "C" int vs_pack_conv3_weight_tc_kdn(const float*, void*, int, int, int, v
 extern "C" int vs_conv3x3x3_tc_kdn(const void*, const void*, void*, double*, float*, int, int, int, int, int, int, int, void*) {
     VS_FAIL(VS_ERR_UNSUPPORTED, "library built without the tcgen05 kernels");
 }
+extern "C" int vs_conv3x3x3_tc_in_relu(const void*, const void*, void*, void*, const void*, double*, float*, unsigned*, int, int,
+                                       int, int, int, int, void*) {
+    VS_FAIL(VS_ERR_UNSUPPORTED, "library built without the tcgen05 kernels");
+}
+extern "C" int vs_conv3x3x3_tc_kdn_in_relu(const void*, const void*, void*, void*, const void*, double*, float*, unsigned*, int,
+                                           int, int, int, int, int, void*) {
+    VS_FAIL(VS_ERR_UNSUPPORTED, "library built without the tcgen05 kernels");
+}
 extern "C" int vs_pack_conv3_weight_tc_kdn_padded(const float*, void*, int, int, int, int, int, void*) {
     VS_FAIL(VS_ERR_UNSUPPORTED, "library built without the tcgen05 kernels");
 }

@@ -67,6 +67,11 @@ struct TcParams {
     int planar_mode;
     float* yplanar;
     const float* bias;      // [2] or null (mode 1)
+    // fused InstanceNorm + ReLU (+ skip): a = relu((y - mean) * rstd) + skip written by the same launch after a grid
+    // barrier (cooperative launch); needs stats; gbar = zero-initialised counter
+    bf16* a_out;
+    const bf16* skip;
+    unsigned* gbar;
     long long* dbg;         // tools/tc_phase_probe.py: clock64 of CTA 0 at the phases of its first work item, or null
 };
 #define TC_DBG(slot) do { if (p.dbg != nullptr && blockIdx.x == 0) p.dbg[slot] = clock64(); } while (0)
@@ -549,6 +554,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
+    if (p.a_out != nullptr) {
+        // ---- fused InstanceNorm + ReLU (+ skip); see conv3_tc_kdn.cu ---------------------------------------------------
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) vs_grid_barrier(p.gbar);
+        __syncthreads();
+        float* tab = reinterpret_cast<float*>(smem);                          // [n * cout][2] = (mean, rstd)
+        for (int i = threadIdx.x; i < p.n * p.cout; i += NTHREADS) {
+            float m1, r1;
+            in_mean_rstd_cg(p.stats + (long long)i * 2, p.inv_s, m1, r1);
+            tab[2 * i] = m1; tab[2 * i + 1] = r1;
+        }
+        __syncthreads();
+        constexpr int NW = NTHREADS / 32;
+        int it = 0;
+        for (long long item = blockIdx.x; item < p.work_items; item += gridDim.x, ++it) {
+            if (it % NW != warp) continue;
+            int n, d0, h0, w0, chunk;
+            decode_work(item, p, n, d0, h0, w0, chunk);
+            in_relu_apply_tile<NC / 8, 4>(p.y, p.skip, p.a_out, tab, lane, n, d0, h0, w0, chunk * NC, min(p.td, p.d - d0),
+                                          p.d, p.h, p.w, p.cout);
+        }
+    }
     if (threadIdx.x == 0) TC_DBG(10);
 }
 
@@ -581,7 +609,10 @@ int launch_tc(const CUtensorMap& map, const TcParams& p, cudaStream_t st) {
         configured = true;
     }
     const long long grid = p.work_items < (long long)vs_sm_count() ? p.work_items : (long long)vs_sm_count();
-    VS_CUDA(vs_launch(kern, dim3((unsigned)grid), dim3(NTHREADS), SMEM, st, map, p), "conv3_tc_kernel launch");
+    if (p.a_out != nullptr)
+        VS_CUDA(vs_launch_coop(kern, dim3((unsigned)grid), dim3(NTHREADS), SMEM, st, map, p), "conv3_tc_kernel cooperative launch");
+    else
+        VS_CUDA(vs_launch(kern, dim3((unsigned)grid), dim3(NTHREADS), SMEM, st, map, p), "conv3_tc_kernel launch");
     VS_CHECK_LAUNCH("conv3_tc_kernel");
     return VS_OK;
 }
@@ -680,10 +711,30 @@ __global__ void __launch_bounds__(256) pack_batched_kernel(const vs_pack_job* __
 }
 
 // y[n,d,h,w,gout] = conv3(x[n,d,h,w,gin], wtc) on the tensor cores; bf16 NDHWC in and out.
+static int run_conv3_tc(const void* x, const void* wtc, void* y, double* stats, float* shift, int prezeroed,
+                        const void* yprev, const double* pstats, double* psums, int planar_mode,
+                        float* yplanar, const float* bias, int n, int d,
+                        int h, int w, int gin, int gout, void* stream, void* a_out, const void* skip, unsigned* gbar);
 extern "C" int vs_conv3x3x3_tc(const void* x, const void* wtc, void* y, double* stats, float* shift, int prezeroed,
                                const void* yprev, const double* pstats, double* psums, int planar_mode,
                                float* yplanar, const float* bias, int n, int d,
                                int h, int w, int gin, int gout, void* stream) {
+    return run_conv3_tc(x, wtc, y, stats, shift, prezeroed, yprev, pstats, psums, planar_mode, yplanar, bias, n, d, h, w, gin, gout,
+                        stream, nullptr, nullptr, nullptr);
+}
+// conv3 + InstanceNorm3d(eps 1e-5, biased) + ReLU (+ skip add) in ONE cooperative launch (joint_model.py:40-46,106):
+// y = raw conv output (shifted), a = relu((y - mean) * rstd) + skip.  stats / shift / gbar zeroed by the caller.
+extern "C" int vs_conv3x3x3_tc_in_relu(const void* x, const void* wtc, void* y, void* a, const void* skip, double* stats,
+                                       float* shift, unsigned* gbar, int n, int d, int h, int w, int gin, int gout, void* stream) {
+    VS_REQUIRE(a && stats && gbar && vs_aligned16(a) && vs_aligned16(skip) && (long long)n * gout * 8 <= 64 * 1024, VS_ERR_SHAPE,
+               "conv3_tc_in_relu: needs the activation output, pre-zeroed statistics and a barrier word");
+    return run_conv3_tc(x, wtc, y, stats, shift, 1, nullptr, nullptr, nullptr, 0, nullptr, nullptr, n, d, h, w, gin, gout, stream,
+                        a, skip, gbar);
+}
+static int run_conv3_tc(const void* x, const void* wtc, void* y, double* stats, float* shift, int prezeroed,
+                        const void* yprev, const double* pstats, double* psums, int planar_mode,
+                        float* yplanar, const float* bias, int n, int d,
+                        int h, int w, int gin, int gout, void* stream, void* a_out, const void* skip, unsigned* gbar) {
     VS_REQUIRE(x && wtc && (y || planar_mode), VS_ERR_SHAPE, "conv3_tc: null pointer");
     if (planar_mode) VS_REQUIRE(yplanar && gout == 8 && !stats && !shift && !psums, VS_ERR_SHAPE, "conv3_tc: planar output needs Cout padded to 8 and no statistics");
     VS_REQUIRE((gin == 8 || (gin % 16 == 0 && gin >= 16)) && gout % 8 == 0 && gout >= 8, VS_ERR_UNSUPPORTED,
@@ -744,6 +795,7 @@ extern "C" int vs_conv3x3x3_tc(const void* x, const void* wtc, void* y, double* 
     p.wpack = (const bf16*)wtc; p.y = (bf16*)y; p.stats = stats; p.shift = shift;
     p.yprev = (const bf16*)yprev; p.pstats = pstats; p.psums = psums; p.inv_s = 1.0 / ((double)d * h * w);
     p.planar_mode = planar_mode; p.yplanar = yplanar; p.bias = bias;
+    p.a_out = (bf16*)a_out; p.skip = (const bf16*)skip; p.gbar = gbar;
     p.dbg = g_tc_dbg;
     if (psums != nullptr) {
         VS_REQUIRE(yprev && pstats && stats == nullptr && shift == nullptr, VS_ERR_SHAPE,

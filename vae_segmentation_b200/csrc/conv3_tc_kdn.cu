@@ -72,6 +72,11 @@ struct KdnParams {
     int planar_mode;
     float* yplanar;
     const float* bias;
+    // fused InstanceNorm + ReLU (+ skip): a = relu((y - mean) * rstd) + skip written by the same launch after a grid
+    // barrier (cooperative launch); needs stats; gbar = zero-initialised counter
+    bf16* a_out;
+    const bf16* skip;
+    unsigned* gbar;
     int ordered;             // 1: one issuer warp issues the whole (plane, tap) list in a fixed order (bit-reproducible sums)
     long long* dbg;          // tools/kdn_phase_probe.py: clock64 stamps of CTA 0 around its 9th tile, or null
 };
@@ -504,6 +509,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kdn_kernel(const __grid_
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
+    if (p.a_out != nullptr) {
+        // ---- fused InstanceNorm + ReLU (+ skip) ----------------------------------------------------------------------
+        // The statistics are complete once every CTA has flushed: grid barrier (the launch is cooperative: all CTAs are
+        // co-resident), then ALL warps of the CTA -- the pipeline roles are over, the stage buffers are free -- turn the
+        // tiles this CTA stored (read back from L2) into the activation.  The separate apply pass (a launch + a read of
+        // y from HBM) disappears.
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) vs_grid_barrier(p.gbar);
+        __syncthreads();
+        float* tab = reinterpret_cast<float*>(smem);                          // [n * cout][2] = (mean, rstd)
+        for (int i = threadIdx.x; i < p.n * p.cout; i += NTHREADS) {
+            float m1, r1;
+            in_mean_rstd_cg(p.stats + (long long)i * 2, p.inv_s, m1, r1);
+            tab[2 * i] = m1; tab[2 * i + 1] = r1;
+        }
+        __syncthreads();
+        constexpr int NW = NTHREADS / 32;
+        int it = 0;
+        for (int item = blockIdx.x; item < p.work_items; item += gridDim.x, ++it) {
+            if (it % NW != warp) continue;
+            int n, d0, h0, w0;
+            decode_item((unsigned)item, p, n, d0, h0, w0);
+            in_relu_apply_tile<NCO / 8, 8>(p.y, p.skip, p.a_out, tab, lane, n, d0, h0, w0, 0, min(TD, p.d - d0), p.d, p.h, p.w, p.cout);
+        }
+    }
 }
 
 __global__ void pack_kdn_kernel(const float* __restrict__ w, bf16* __restrict__ out, int cin, int cout, int dgrad, long long total,
@@ -525,7 +556,10 @@ int launch_kdn(const CUtensorMap& map, const KdnParams& p, cudaStream_t st) {
         configured = true;
     }
     const int grid = p.work_items < vs_sm_count() ? p.work_items : vs_sm_count();
-    VS_CUDA(vs_launch(kern, dim3((unsigned)grid), dim3(NTHREADS), SMEM, st, map, p), "conv3_tc_kdn_kernel launch");
+    if (p.a_out != nullptr)
+        VS_CUDA(vs_launch_coop(kern, dim3((unsigned)grid), dim3(NTHREADS), SMEM, st, map, p), "conv3_tc_kdn_kernel cooperative launch");
+    else
+        VS_CUDA(vs_launch(kern, dim3((unsigned)grid), dim3(NTHREADS), SMEM, st, map, p), "conv3_tc_kdn_kernel launch");
     VS_CHECK_LAUNCH("conv3_tc_kdn_kernel");
     return VS_OK;
 }
@@ -576,7 +610,8 @@ extern "C" int vs_conv3x3x3_tc_kdn(const void* x, const void* wkdn, void* y, dou
 // psums[n][gout][2] += (sum g*mask, sum g*mask*xhat) from yprev / pstats (zeroed by the caller; no stats / shift then).
 static int run_kdn(const void* x, const void* wkdn, void* y, double* stats, float* shift, int prezeroed,
                    const void* yprev, const double* pstats, double* psums, int planar_mode, float* yplanar, const float* bias,
-                   int n, int d, int h, int w, int gin, int gout, void* stream) {
+                   int n, int d, int h, int w, int gin, int gout, void* stream,
+                   void* a_out = nullptr, const void* skip = nullptr, unsigned* gbar = nullptr) {
     VS_REQUIRE(x && wkdn && (y || planar_mode), VS_ERR_SHAPE, "conv3_tc_kdn: null pointer");
     if (planar_mode) VS_REQUIRE(yplanar && gout == 8 && !stats && !shift && !psums, VS_ERR_SHAPE,
                                 "conv3_tc_kdn: planar output needs Cout padded to 8 and no statistics");
@@ -623,6 +658,11 @@ static int run_kdn(const void* x, const void* wkdn, void* y, double* stats, floa
     p.wpack = (const bf16*)wkdn; p.y = (bf16*)y; p.stats = stats; p.shift = shift;
     p.yprev = (const bf16*)yprev; p.pstats = pstats; p.psums = psums; p.inv_s = 1.0 / ((double)d * h * w);
     p.planar_mode = planar_mode; p.yplanar = yplanar; p.bias = bias;
+    p.a_out = (bf16*)a_out; p.skip = (const bf16*)skip; p.gbar = gbar;
+    if (a_out != nullptr)
+        VS_REQUIRE(stats && gbar && prezeroed && !planar_mode && !psums && vs_aligned16(a_out) && vs_aligned16(skip) &&
+                   (long long)n * gout * 8 <= 64 * 1024, VS_ERR_SHAPE,
+                   "conv3_tc_kdn: the fused InstanceNorm+ReLU needs pre-zeroed statistics and a barrier word");
     p.dbg = g_kdn_dbg;
     p.ordered = g_kdn_ordered;
     if (psums != nullptr) {
@@ -656,4 +696,15 @@ extern "C" int vs_conv3x3x3_tc_kdn_planar(const void* x, const void* wkdn8, floa
     VS_REQUIRE(mode == 1 || mode == 2, VS_ERR_SHAPE, "conv3_tc_kdn_planar: mode must be 1 (softmax head) or 2 (plain)");
     return run_kdn(x, wkdn8, nullptr, nullptr, nullptr, 1, nullptr, nullptr, nullptr, mode, out, mode == 1 ? bias : nullptr,
                    n, d, h, w, gin, 8, stream);
+}
+
+// conv3 + InstanceNorm3d(eps 1e-5, biased) + ReLU (+ skip add) in ONE cooperative launch of the kd-in-N kernel
+// (joint_model.py:40-46,106: Conv3d -> InstanceNorm3d -> ReLU): y = raw conv output (shifted, as vs_conv3x3x3_tc_kdn),
+// a = relu((y - mean) * rstd) + skip.  stats / shift / gbar (one 32-bit word) must be zeroed by the caller.
+extern "C" int vs_conv3x3x3_tc_kdn_in_relu(const void* x, const void* wkdn, void* y, void* a, const void* skip, double* stats,
+                                           float* shift, unsigned* gbar, int n, int d, int h, int w, int gin, int gout,
+                                           void* stream) {
+    VS_REQUIRE(a != nullptr, VS_ERR_SHAPE, "conv3_tc_kdn_in_relu: null activation output");
+    return run_kdn(x, wkdn, y, stats, shift, 1, nullptr, nullptr, nullptr, 0, nullptr, nullptr, n, d, h, w, gin, gout, stream,
+                   a, skip, gbar);
 }

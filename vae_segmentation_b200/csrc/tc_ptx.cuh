@@ -193,4 +193,54 @@ EncodeTiledFn get_encode_fn() {
 }
 
 
+
+// ---- fused InstanceNorm + ReLU (+ skip) phase of the convolution kernels (after their grid barrier) -------------------
+// One WARP turns one output tile [npl d-planes][16 h][8 w] x [NCV 8-channel vectors] at (n, d0, h0, w0), channels from
+// co0, of the raw conv output y into the activation a = relu((y - mean) * rstd) + skip.  tab = shared-memory table
+// [N * C][2] of (mean, rstd).  UNROLL independent 16-byte loads are in flight per lane (the pass is pure memory
+// latency: y was written by this kernel a few microseconds ago and is read back from L2).
+template <int NCV, int UNROLL>
+__device__ __forceinline__ void in_relu_apply_tile(const bf16* __restrict__ y, const bf16* __restrict__ skip, bf16* __restrict__ a,
+                                                   const float* tab, int lane, int n, int d0, int h0, int w0, int co0, int npl,
+                                                   int D, int H, int W, int C) {
+    const int nvec = npl * 128 * NCV;
+    const uint32_t tab_addr = smem_u32(tab + ((long long)n * C + co0) * 2);
+    for (int v0 = lane; v0 < nvec; v0 += 32 * UNROLL) {
+        uint4 raw[UNROLL], sk[UNROLL];
+        long long off[UNROLL];
+        bool ok[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int v = v0 + 32 * u;
+            const int c8 = v % NCV, r = (v / NCV) & 127, pl = v / (NCV * 128);
+            const int gh = h0 + (r >> 3), gw = w0 + (r & 7);
+            ok[u] = v < nvec && gh < H && gw < W && co0 + c8 * 8 < C;
+            off[u] = ((((long long)n * D + d0 + pl) * H + gh) * (long long)W + gw) * C + co0 + c8 * 8;
+            raw[u] = make_uint4(0u, 0u, 0u, 0u);
+            sk[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (ok[u]) {
+                raw[u] = __ldcg(reinterpret_cast<const uint4*>(y + off[u]));
+                if (skip != nullptr) sk[u] = __ldg(reinterpret_cast<const uint4*>(skip + off[u]));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            if (!ok[u]) continue;
+            const int c8 = (v0 + 32 * u) % NCV;
+            const uint32_t yu[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+            const uint32_t su[4] = {sk[u].x, sk[u].y, sk[u].z, sk[u].w};
+            float o[8];
+#pragma unroll
+            for (int i2 = 0; i2 < 4; ++i2) {
+                // (mean, rstd) pairs of channels 2*i2 and 2*i2+1 of this vector
+                const float4 mr = lds128(tab_addr + (uint32_t)(c8 * 8 + 2 * i2) * 8u);
+                const float y0 = __uint_as_float(yu[i2] << 16), y1 = __uint_as_float(yu[i2] & 0xffff0000u);
+                o[2 * i2] = fmaxf((y0 - mr.x) * mr.y, 0.f) + __uint_as_float(su[i2] << 16);
+                o[2 * i2 + 1] = fmaxf((y1 - mr.z) * mr.w, 0.f) + __uint_as_float(su[i2] & 0xffff0000u);
+            }
+            Store<bf16>::st8(a + off[u], o);
+        }
+    }
+}
+
 }  // namespace

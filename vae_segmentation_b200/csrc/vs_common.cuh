@@ -44,6 +44,33 @@ static inline cudaError_t vs_launch(void (*kern)(KArgs...), dim3 grid, dim3 bloc
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
+// Cooperative launch: every CTA of the grid is co-resident (the driver gang-schedules the grid, also against kernels of
+// other streams and inside captured graphs -- tools/coop_probe.cu), which is what makes an in-kernel grid barrier
+// (vs_grid_barrier) safe.  The grid must fit the device at once (<= SMs x resident CTAs per SM) or the launch fails.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t vs_launch_coop(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+// One thread per CTA calls this after the CTA's own threads have fenced and synchronised: arrive on a zero-initialised
+// counter and wait for the whole grid.  Only under vs_launch_coop.  Traps instead of hanging on a protocol bug.
+__device__ __forceinline__ void vs_grid_barrier(unsigned* counter) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned spins = 0;
+    while (*reinterpret_cast<volatile unsigned*>(counter) < gridDim.x * gridDim.y * gridDim.z) {
+        __nanosleep(64);
+        if (++spins > (1u << 23)) __trap();
+    }
+    __threadfence();
+}
+
 static inline bool vs_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 int vs_sm_count();
 __device__ __forceinline__ bool vs_aligned16_dev(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -99,6 +126,14 @@ __device__ __forceinline__ double warp_sum(double v) {
 // mean / rstd of InstanceNorm3d (biased variance, eps 1e-5) from (sum, sumsq) over s voxels.
 // The sums are fp64: E[x^2]-E[x]^2 cancels catastrophically in fp32 when |mean| >> sigma
 // (e.g. the VAE in_block on a mostly-constant mask), and B200 has full-rate-enough FP64.
+// _cg: the sums were accumulated by atomics of THIS kernel (other CTAs): read them from L2
+__device__ __forceinline__ void in_mean_rstd_cg(const double* st, double inv_s, float& mean, float& rstd) {
+    const double s0 = __ldcg(st), s1 = __ldcg(st + 1);
+    const double m = s0 * inv_s;
+    const double var = fmax(s1 * inv_s - m * m, 0.0);
+    mean = (float)m;
+    rstd = (float)(1.0 / sqrt(var + 1e-5));
+}
 __device__ __forceinline__ void in_mean_rstd(const double* st, double inv_s, float& mean, float& rstd) {
     const double m = st[0] * inv_s;
     const double var = fmax(st[1] * inv_s - m * m, 0.0);

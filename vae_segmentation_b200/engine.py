@@ -40,6 +40,13 @@ USE_KDN = os.environ.get("VAESEG_KDN", "1") == "1"
 # IMAGE to bf16 moved the conditioned-fixture gradients of the 12^3 level from 4.x e-2 to 5.05e-2 of the floored norm
 # (north-star bound 5e-2) for 11 us.  VAESEG_INBLOCK_TC=0 keeps the CUDA-core kernel everywhere.
 INBLOCK_TC = os.environ.get("VAESEG_INBLOCK_TC", "1") == "1"
+# Conv -> InstanceNorm -> ReLU (+ skip) of the tensor-core layers as ONE cooperative launch with an in-kernel grid barrier
+# (ops.conv3_in_relu) instead of conv + a separate apply pass.  Correct (tests/test_conv3_tc_gpu.py) and measured SLOWER:
+# joint step 316 vs 385 vol/s, seg 826 vs 864, vae 971 vs 1006 (profiles/r2_fused_apply_ab.txt).  A cooperative grid is
+# gang-scheduled -- it starts only when ALL of its CTAs fit at once, so it cannot slide into the SMs a kernel of another
+# stream (teacher forward, weight gradients) frees one by one, and the in-kernel pass (fence + grid barrier + L2 re-read
+# on one CTA per SM) is no faster than the stand-alone apply kernel at full occupancy (16 vs 14 us at 2 x 96^3).  Opt-in.
+FUSE_APPLY = os.environ.get("VAESEG_FUSE_APPLY", "0") == "1"
 # 2x2x2 stride-2 convolutions / transposed convolutions (forward and input gradient) on the tensor cores
 # (csrc/k2s2_tc.cu); VAESEG_K2_TC=0 keeps the CUDA-core kernels of csrc/k2s2.cu (A/B measurements).
 USE_K2_TC = os.environ.get("VAESEG_K2_TC", "1") == "1"
@@ -371,16 +378,25 @@ def program_forward(layers, tensors, x, dims, dtype, cache, record=True):
                 wk = cache.inblock_kdn(tensors[L.wi])
                 if wk is not None:
                     x8 = ops.planar_to_ndhwc8(cur)
-            if x8 is not None:
+            skip = slots[L.skip_from] if L.skip_from is not None else None
+            fuse = FUSE_APPLY and USE_TENSOR_CORES and dtype == torch.bfloat16 and arena is not None and not SIMULATE_BF16
+            a = None
+            if x8 is not None and fuse:
+                y, stats, a = ops.conv3_in_relu(x8, wk, (n, d, h, w), 8, L.cout, arena, skip=skip, kdn=True)
+            elif x8 is not None:
                 y, stats = ops.conv3_tc_kdn(x8, wk, (n, d, h, w), 8, L.cout, want_stats=True, arena=arena)
+            elif wk is not None and fuse:
+                y, stats, a = ops.conv3_in_relu(cur, wk, (n, d, h, w), L.cin, L.cout, arena, skip=skip, kdn=True)
             elif wk is not None:
                 y, stats = ops.conv3_tc_kdn(cur, wk, (n, d, h, w), L.cin, L.cout, want_stats=True, arena=arena)
+            elif fuse and not L.in_planar and wtc is not None and _tc_channels(L.cin) and L.cout % 8 == 0:
+                y, stats, a = ops.conv3_in_relu(cur, wtc, (n, d, h, w), L.cin, L.cout, arena, skip=skip, kdn=False)
             else:
                 y, stats = ops.conv3_fprop(cur, wf, None, (n, d, h, w), L.cin, L.cout, dtype, in_planar=L.in_planar,
                                            wtc=None if L.in_planar else wtc, arena=arena)
-            skip = slots[L.skip_from] if L.skip_from is not None else None
             y = _sim(y, "y")
-            a = _sim(ops.inorm_relu_apply(y, stats, skip), "a")
+            if a is None:
+                a = _sim(ops.inorm_relu_apply(y, stats, skip), "a")
             if record:
                 wkd = None
                 if (USE_KDN and USE_TENSOR_CORES and dtype == torch.bfloat16 and not L.in_planar and L.cin in (8, 16)

@@ -97,8 +97,9 @@ def pack_conv3_batched(jobs_dev, njobs):
 
 
 def stats_words(n, cout):
-    """fp64 words of one layer's statistics + shift block (see conv3_fprop / StatsArena)."""
-    return n * cout * 2 + (n * cout + 1) // 2
+    """fp64 words of one layer's statistics + shift block (see conv3_fprop / StatsArena) + one word whose first 32 bits
+    are the grid-barrier counter of the fused conv + InstanceNorm + ReLU launch (conv3_in_relu)."""
+    return n * cout * 2 + (n * cout + 1) // 2 + 1
 
 
 class StatsArena(object):
@@ -503,6 +504,22 @@ def conv3_tc_kdn_planar(x, wkdn8, dims, gin, mode, bias=None):
     _cabi.call("vs_conv3x3x3_tc_kdn_planar", _p(x), _p(wkdn8), _p(out), _p(_f32(bias, "bias") if bias is not None else None),
                int(mode), n, d, h, w, gin, _stream())
     return out
+
+
+def conv3_in_relu(x, wpack, dims, gin, gout, arena, skip=None, kdn=False):
+    """(y, stats, a): Conv3d(3, padding 1) -> InstanceNorm3d -> ReLU (+ skip) in ONE cooperative tensor-core launch
+    (vs_conv3x3x3_tc[_kdn]_in_relu): y = raw conv output (kept for backward), a = the activation.  bf16 NDHWC.
+    `arena`: zero-filled StatsArena supplying statistics, shift and the barrier word."""
+    n, d, h, w = dims
+    y = torch.empty(n, d, h, w, gout, device=x.device, dtype=torch.bfloat16)
+    a = torch.empty_like(y)
+    buf = arena.take(stats_words(n, gout))
+    stats = buf[:n * gout * 2].view(n, gout, 2)
+    shift = buf[n * gout * 2:].view(torch.float32)[:n * gout].view(n, gout)
+    gbar = buf[-1:]
+    _cabi.call("vs_conv3x3x3_tc_kdn_in_relu" if kdn else "vs_conv3x3x3_tc_in_relu", _p(x), _p(wpack), _p(y), _p(a), _p(skip),
+               _p(stats), _p(shift), _p(gbar), n, d, h, w, gin, gout, _stream())
+    return y, stats, a
 
 
 def conv3_tc_kdn(x, wkdn, dims, gin, gout, want_stats=False, arena=None, prev=None):
