@@ -47,6 +47,7 @@ INBLOCK_TC = os.environ.get("VAESEG_INBLOCK_TC", "1") == "1"
 # stream (teacher forward, weight gradients) frees one by one, and the in-kernel pass (fence + grid barrier + L2 re-read
 # on one CTA per SM) is no faster than the stand-alone apply kernel at full occupancy (16 vs 14 us at 2 x 96^3).  Opt-in.
 FUSE_APPLY = os.environ.get("VAESEG_FUSE_APPLY", "0") == "1"
+FUSE_APPLY_MAX_VOX = int(os.environ.get("VAESEG_FUSE_APPLY_MAX_VOX", "0"))        # 0 = every size (voxels per sample)
 # 2x2x2 stride-2 convolutions / transposed convolutions (forward and input gradient) on the tensor cores
 # (csrc/k2s2_tc.cu); VAESEG_K2_TC=0 keeps the CUDA-core kernels of csrc/k2s2.cu (A/B measurements).
 USE_K2_TC = os.environ.get("VAESEG_K2_TC", "1") == "1"
@@ -379,7 +380,8 @@ def program_forward(layers, tensors, x, dims, dtype, cache, record=True):
                 if wk is not None:
                     x8 = ops.planar_to_ndhwc8(cur)
             skip = slots[L.skip_from] if L.skip_from is not None else None
-            fuse = FUSE_APPLY and USE_TENSOR_CORES and dtype == torch.bfloat16 and arena is not None and not SIMULATE_BF16
+            fuse = (FUSE_APPLY and USE_TENSOR_CORES and dtype == torch.bfloat16 and arena is not None and not SIMULATE_BF16
+                    and (FUSE_APPLY_MAX_VOX == 0 or d * h * w <= FUSE_APPLY_MAX_VOX))
             a = None
             if x8 is not None and fuse:
                 y, stats, a = ops.conv3_in_relu(x8, wk, (n, d, h, w), 8, L.cout, arena, skip=skip, kdn=True)
