@@ -260,7 +260,7 @@ def main():
     ap.add_argument("--patch", type=int, default=0, help="patch edge (default: the mode's)")
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH)
     ap.add_argument("--loss-type", type=int, default=0)
-    ap.add_argument("--ttt-cases", type=int, default=2, help="joint_ttt: validation cases per rank in the TTT leg")
+    ap.add_argument("--ttt-cases", type=int, default=8, help="joint_ttt: validation cases per rank in the TTT leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the CUDA-graph-captured step")
     ap.add_argument("--no-roofline", action="store_true", help="skip the per-kernel event pass (sweeps)")
@@ -472,7 +472,7 @@ def main():
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         ttt = {"cases": ncase * world, "cases_per_s": ncase * world / dt.item(), "s_per_case_per_gpu": dt.item() / ncase,
                "val_finetune": 1, "dsc": out["dsc"], "dsc_noft": out["dsc_noft"],
-               "timing": "host wall clock around validate() incl. its final host sync, max over ranks (eager launches)"}
+               "timing": "host wall clock around validate() incl. its final host sync, max over ranks (one captured graph replay per case; VAESEG_VAL_GRAPH=0 for eager launches)"}
 
     # ---- the dominant kernel, CUDA events around each of its launches over the same K steps (eager launches:
     #      events cannot be recorded inside a replayed graph) ---------------------------------------

@@ -124,6 +124,8 @@ def load_checkpoint(path, model, trainer=None, strict=True, map_location="cpu"):
         # the trainer re-homed the parameters into its arena: load_state_dict copied INTO those views, so the arena
         # is current; only the derived packs and the optimiser moments remain
         trainer.opt.arena.module.repack_packs()
+        if hasattr(trainer, "release_graph"):
+            trainer.release_graph()                  # captured graphs may hold lazily re-packed state of the old weights
         if osd.get("state"):
             opt = trainer.opt
             all_params, trained = list(model.parameters()), opt.arena.params

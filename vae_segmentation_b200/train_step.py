@@ -319,6 +319,7 @@ class JointTrainer(object):
         self._bucketer = None
         self._grads_reduced = False
         self._graphs = {}                        # slot -> (captured CUDA graph, monitored terms), see capture()
+        self._val_graphs = {}                    # validation: (shape, TTT setting) -> captured per-case graph
         self._graph = self._graph_mon = None
         # the step's own (critical) chain runs at high priority; the teacher forward and the weight gradients, which
         # only have to finish by the loss / the optimiser step, fill in behind it at the default priority
@@ -512,6 +513,7 @@ class JointTrainer(object):
         self._graph = None
         self._graph_mon = None
         self._graphs = {}
+        self._val_graphs = {}
         torch.cuda.synchronize()
 
     def step_graphed(self, update_teacher=False, slot=0):
@@ -549,7 +551,46 @@ class JointTrainer(object):
             p1 = finetune.Seg.predict(img)
         return p0, p1
 
-    def validate(self, cases, finetune=None, val_finetune=0, lr_finetune=1e-2):
+    def _case_scores(self, finetune, img, label, val_finetune, lr_finetune):
+        """One validation case: optional TTT, inference, (finetuned, student) binary Dice as a 2-vector on the device."""
+        if val_finetune and finetune is not None:
+            p0, p1 = self.test_time_train(finetune, img, label, iters=val_finetune, lr_finetune=lr_finetune)
+        else:
+            with torch.no_grad():
+                p0 = self.student.Seg.predict(img)
+            p1 = p0
+        onehot = ev.one_hot(label, p0.shape[1])
+        top = p0.shape[1]
+        s0 = ev.avg_dsc({"p": p0, "t": onehot}, "p", "t", binary=True, botindex=1, topindex=top).reshape(())
+        s1 = s0 if p1 is p0 else ev.avg_dsc({"p": p1, "t": onehot}, "p", "t", binary=True, botindex=1, topindex=top).reshape(())
+        return torch.stack([s1, s0])
+
+    def _case_graph(self, finetune, img, label, val_finetune, lr_finetune):
+        """The per-case validation work captured ONCE per (case shape, TTT setting) on static input buffers: every case
+        of a validation pass has the same patch shape, and a case is ~600 launches (weight copy, teacher + finetune
+        forward, backward, SGD, re-pack, two inferences, Dice) that the host cannot issue as fast as the GPU runs them
+        (eager: 25 cases/s at 128^3).  Replay: copy the case into the static buffers, launch the graph."""
+        key = (id(finetune), tuple(img.shape), str(img.dtype), int(val_finetune), float(lr_finetune), self.loss_type,
+               float(self.lambda_vae) if not torch.is_tensor(self.lambda_vae) else -1.0)
+        ent = self._val_graphs.get(key)
+        if ent is None:
+            s_img, s_label = img.clone(), label.clone()
+            cur = torch.cuda.current_stream()
+            side = self.stream
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for _ in range(2):                         # allocations, pack-cache entries, the finetune arena
+                    self._case_scores(finetune, s_img, s_label, val_finetune, lr_finetune)
+            cur.wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                out = self._case_scores(finetune, s_img, s_label, val_finetune, lr_finetune)
+            self._val_graphs = {key: (graph, s_img, s_label, out)}      # one at a time: a graph pins GBs of activations
+            ent = self._val_graphs[key]
+        return ent
+
+    def validate(self, cases, finetune=None, val_finetune=0, lr_finetune=1e-2, graphed=None):
         """The validation pass of main_target.py:795-960 (method 'domain_adaptation') over `cases`, an iterable of
         (img [1,1,D,H,W], label [1,1,D,H,W]) CUDA tensors: per case optionally `val_finetune` test-time-training
         iterations on a private copy of the student (:807-900), then no-grad inference and the binary (argmax) Dice of
@@ -560,21 +601,22 @@ class JointTrainer(object):
         cases[rank::world] and the two sums are all-reduced -- cases are independent, nothing else is exchanged."""
         world = _world()
         rank = dist.get_rank() if world > 1 else 0
+        if graphed is None:
+            graphed = os.environ.get("VAESEG_VAL_GRAPH", "1") == "1"
         scores, scores_noft = [], []
         for idx, (img, label) in enumerate(cases):
             if idx % world != rank:
                 continue
-            if val_finetune and finetune is not None:
-                p0, p1 = self.test_time_train(finetune, img, label, iters=val_finetune, lr_finetune=lr_finetune)
+            if graphed:
+                graph, s_img, s_label, out = self._case_graph(finetune, img, label, val_finetune, lr_finetune)
+                s_img.copy_(img, non_blocking=True)
+                s_label.copy_(label, non_blocking=True)
+                graph.replay()
+                both = out.clone()
             else:
-                with torch.no_grad():
-                    p0 = self.student.Seg.predict(img)
-                p1 = p0
-            onehot = ev.one_hot(label, p0.shape[1])
-            top = p0.shape[1]
-            scores_noft.append(ev.avg_dsc({"p": p0, "t": onehot}, "p", "t", binary=True, botindex=1, topindex=top).reshape(()))
-            scores.append(scores_noft[-1] if p1 is p0 else
-                          ev.avg_dsc({"p": p1, "t": onehot}, "p", "t", binary=True, botindex=1, topindex=top).reshape(()))
+                both = self._case_scores(finetune, img, label, val_finetune, lr_finetune)
+            scores.append(both[0])
+            scores_noft.append(both[1])
         dev = self.arena.data.device
         local = torch.stack([torch.stack(scores).sum() if scores else torch.zeros((), device=dev),
                              torch.stack(scores_noft).sum() if scores_noft else torch.zeros((), device=dev),
