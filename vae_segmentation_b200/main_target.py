@@ -83,6 +83,7 @@ def build_parser():
     p.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     p.add_argument("--save_root", default="checkpoints", help="the reference's save_root_path")
     p.add_argument("--max_iters", type=int, default=0, help="stop after this many training iterations (smoke runs)")
+    p.add_argument("--no_graph", action="store_true", help="eager launches instead of CUDA-graph replay of the train step")
     return p
 
 
@@ -217,10 +218,13 @@ def main(argv=None):
     say("train volumes per epoch %d, per-GPU batch %d x %d GPU(s), %d validation cases" % (len(train_names), B, world, len(val_names)))
 
     best, iters, lambda_vae = 0.0, 0, args.lambda_vae
+    static = None                      # (image, label) buffers of the captured train step + the lambda it was captured with
     with torch.cuda.stream(trainer.stream):
         for epoch in range(start_epoch, args.max_epoch // args.eval_epoch):
             if not args.test_only and epoch > 0:                                          # :506 `if epoch == 0: continue`
-                perm = torch.randperm(len(train_names)).tolist()
+                shuffle = torch.Generator()                  # own generator: the order must not depend on how many draws
+                shuffle.manual_seed(1000 + epoch)            # the model code made (graph capture warms the step up twice)
+                perm = torch.randperm(len(train_names), generator=shuffle).tolist()
                 for idx in range(steps_per_epoch):
                     update = False
                     if args.pseudo_save_epoch != 0 and epoch % max(args.pseudo_save_epoch // args.eval_epoch, 1) == 0:
@@ -232,7 +236,18 @@ def main(argv=None):
                     pairs = [train_set.load(train_names[i]) for i in pick]
                     img = torch.cat([p[0] for p in pairs]).contiguous()
                     label = torch.cat([p[1] for p in pairs]).contiguous()
-                    mon = trainer.step(img, label, update_teacher=update)
+                    if args.no_graph:
+                        mon = trainer.step(img, label, update_teacher=update)
+                    else:
+                        # ~600 launches per step: the host cannot issue them as fast as the GPU runs them, so the step
+                        # (zero_grad + forwards + losses + backward) is captured once per (batch shape, lambda) and replayed
+                        if static is None or static[0].shape != img.shape or static[2] != lambda_vae:
+                            trainer.release_graph()
+                            static = (img.clone(), label.clone(), lambda_vae)
+                            trainer.capture(static[0], static[1])
+                        static[0].copy_(img)
+                        static[1].copy_(label)
+                        mon = trainer.step_graphed(update_teacher=update)
                     iters += 1
                     if idx % 10 == 0:
                         say("epoch %d iter %d: " % (epoch, idx) + " ".join("%s %.4f" % (k, v.item()) for k, v in mon.items()))
