@@ -1,5 +1,6 @@
 #!/bin/bash
-# final round-2 evidence set on one GPU
+# The one-GPU evidence set of profiles/ (sanitizer, bench lines of every BASELINE config, ncu launch list, CUPTI timeline):
+#   gpurun --timeout 3000 -- "bash tools/measure_all.sh"; results land in gpurun_out/
 mkdir -p gpurun_out
 bash tools/sanitize.sh
 for m in joint seg vae; do
