@@ -41,3 +41,42 @@ def test_no_cuda_is_an_error_not_a_fallback():
         pytest.skip("GPU present")
     with pytest.raises(SystemExit, match="no CUDA device"):
         cli.main(shlex.split(DH_FT1) + ["--synthetic", "2"])
+
+
+# ---- main_source.py (scripts/source/*.bash) ---------------------------------------------------------------------------
+REF_SOURCE_SCRIPTS = "/root/reference/scripts/source"
+SEG_NIH = ("seg_nih -G 0 --method seg_train --train_list NIH_train --val_list NIH_val --data_root X --val_data_root X "
+           "--data_path data/Multi_all.json --eval_epoch 20 --save_epoch 800 --max_epoch 2400")
+
+
+def test_source_parser_accepts_the_shipped_preset():
+    from vae_segmentation_b200 import main_source as src
+    a = src.build_parser().parse_args(shlex.split(SEG_NIH))
+    assert a.method == "seg_train" and a.eval_epoch == 20 and a.save_epoch == 800 and a.max_epoch == 2400 and a.lr_seg == 1e-2
+    d = src.build_parser().parse_args(["p"])
+    assert d.method == "vae_train" and d.batch_size == 4 and d.lr_vae == 0          # main_source.py:29,35,49 defaults
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SOURCE_SCRIPTS), reason="reference tree not present")
+def test_source_parser_accepts_every_reference_source_script():
+    from vae_segmentation_b200 import main_source as src
+    scripts = sorted(glob.glob(os.path.join(REF_SOURCE_SCRIPTS, "*.bash")))
+    assert len(scripts) == 2
+    methods = set()
+    for path in scripts:
+        text = open(path).read().replace("\\\n", " ").rstrip("\\ \n")          # the scripts end in a dangling backslash
+        line = [l for l in text.splitlines() if "main_source.py" in l][0]
+        argv = shlex.split(line.replace("$1", "0"))
+        argv = [("X" if (t.startswith("<") and t.endswith(">")) else t) for t in argv[argv.index("main_source.py") + 1:]]
+        methods.add(src.build_parser().parse_args(argv).method)
+    assert methods == {"seg_train", "vae_train"}
+
+
+def test_source_unwired_method_and_missing_gpu_are_errors():
+    import torch
+    from vae_segmentation_b200 import main_source as src
+    with pytest.raises(SystemExit, match="not wired"):
+        src.main(["p", "--method", "joint_train", "--synthetic", "2"])
+    if not torch.cuda.is_available():
+        with pytest.raises(SystemExit, match="no CUDA device"):
+            src.main(shlex.split(SEG_NIH) + ["--synthetic", "2"])
