@@ -194,6 +194,20 @@ int vs_inorm_relu_bwd_apply(int dtype, const void* g, const void* y, const doubl
                             void* dy, int n, long long s, int c, void* stream);
 /* dst += src (gradient fan-in at the additive skips, joint_model.py:381,383)               */
 int vs_add_inplace(int dtype, void* dst, const void* src, long long count, void* stream);
+/* ---- per-(n,c) affine + ReLU passes: BatchNorm3d(affine, running statistics) + ReLU, joint_model.py:12-13 -------
+ * The statistics of BatchNorm are pooled over the batch, which the host does on the [N][C] outputs of the convolution
+ * kernels (a few hundred numbers); gamma / beta / the stored shift are folded into per-(n,c) coefficient tables and
+ * these kernels do the tensor passes.  y, skip, a, g, dy: NDHWC [N,S,C] of `dtype`, C a power of two in [8,256].
+ *   apply:       a  = relu(k*y + b) + skip                    kb   [N][C][2] fp32 = (k, b); skip may be NULL
+ *   bwd_reduce:  sums[n][c] = (sum gm, sum gm*xhat)           gm = g*[k*y+b > 0], xhat = k2*y + b2; k2b2 [N][C][2];
+ *                                                              sums [N][C][2] fp64, zeroed by the call
+ *   bwd_apply:   dy = c0*gm + c1 + c2*y                        coef [N][C][3] fp32                                  */
+int vs_affine_relu_apply(int dtype, const void* y, const float* kb, const void* skip, void* a, int n, long long s, int c,
+                         void* stream);
+int vs_affine_relu_bwd_reduce(int dtype, const void* g, const void* y, const float* kb, const float* k2b2, double* sums,
+                              int n, long long s, int c, void* stream);
+int vs_affine_relu_bwd_apply(int dtype, const void* g, const void* y, const float* kb, const float* coef, void* dy,
+                             int n, long long s, int c, void* stream);
 
 /* ---- softmax over n_class=2 (joint_model.py:225,367) ---------------------------------- */
 /* logits: NDHWC fp32 [N][S][2]; probs: planar fp32 [N][2][S]                               */

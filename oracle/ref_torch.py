@@ -99,6 +99,9 @@ def init_vae_state(n_class=2, dim=128, patch=128):
     return sd
 
 
+# BatchNorm layers (norm_type 2) use running statistics when True (module.eval()); see conv_in_relu
+BN_EVAL = False
+
 # ----------------------------------------------------------------------------------
 # blocks
 # ----------------------------------------------------------------------------------
@@ -106,7 +109,15 @@ def conv_in_relu(sd, name, x):
     """Conv3d(3,p=1) -> InstanceNorm3d(affine=False, eps=1e-5, biased var) -> ReLU
     (joint_model.py:101-112 and each third of :35-52)."""
     y = F.conv3d(x, sd[name + ".weight"], sd[name + ".bias"], padding=1)
-    y = F.instance_norm(y, eps=IN_EPS)
+    head, _, last = name.rpartition(".")
+    norm = "%s.%d" % (head, int(last) + 1)
+    if norm + ".running_mean" in sd:
+        # norm_type 2: nn.BatchNorm3d(C, momentum=0.1) at the next Sequential index (joint_model.py:12-13).  Training mode
+        # (batch statistics; the running buffers of `sd` are updated in place like the module's) unless BN_EVAL is set.
+        y = F.batch_norm(y, sd[norm + ".running_mean"], sd[norm + ".running_var"], sd[norm + ".weight"], sd[norm + ".bias"],
+                         training=not BN_EVAL, momentum=0.1, eps=IN_EPS)
+    else:
+        y = F.instance_norm(y, eps=IN_EPS)
     return F.relu(y)
 
 
@@ -306,8 +317,17 @@ def compose_target_loss(recon_loss, dsc_loss_fake, klloss, lambda_vae=1.0, loss_
 # ----------------------------------------------------------------------------------
 # train steps
 # ----------------------------------------------------------------------------------
+_BN_BUFFERS = ("running_mean", "running_var", "num_batches_tracked")
+
+
 def _leafify(sd, requires_grad=True, dtype=None):
-    return OrderedDict((k, v.detach().clone().to(dtype or v.dtype).requires_grad_(requires_grad)) for k, v in sd.items())
+    out = OrderedDict()
+    for k, v in sd.items():
+        if k.rsplit(".", 1)[-1] in _BN_BUFFERS:          # BatchNorm buffers (norm_type 2): no gradient, updated in place
+            out[k] = v.detach().clone().to(dtype if (dtype is not None and v.is_floating_point()) else v.dtype)
+        else:
+            out[k] = v.detach().clone().to(dtype or v.dtype).requires_grad_(requires_grad)
+    return out
 
 
 def sgd_step(sd, grads, bufs, lr=1e-2, momentum=0.9):

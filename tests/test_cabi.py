@@ -52,4 +52,4 @@ def test_cpu_tensors_are_rejected():
     with pytest.raises(RuntimeError, match="CUDA"):
         evaluation.avg_dsc({"a": torch.zeros(1, 2, 4, 4, 4), "b": torch.zeros(1, 2, 4, 4, 4)}, "a", "b")
     with pytest.raises(NotImplementedError):
-        joint_model.Segmentation(1, 2, norm_type=2)
+        joint_model.Segmentation(1, 2, norm_type=3)          # GSNorm3d: the one normalisation that is not implemented

@@ -82,3 +82,25 @@ def test_variant_modules_state_dict_matches_the_real_reference():
                             joint_model.Fusion(1, 2, 2, norm_type=1)])
     rm = rjm.Embed([rjm.Encoder(1, 128, norm_type=1), rjm.VAE(2, 2, norm_type=1, dim=128), rjm.Fusion(1, 2, 2, norm_type=1)])
     assert list(em.state_dict().keys()) == list(rm.state_dict().keys())
+
+
+def test_batchnorm_variant_state_dict_matches_reference():
+    """norm_type=2 (the constructors' default): same keys, shapes, dtypes and initial values as the reference's
+    nn.BatchNorm3d-based modules, and reference state loads strictly."""
+    import os
+    import pytest
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("reference tree not present")
+    from oracle import reference_shim
+    rjm, _ = reference_shim.load()
+    torch.manual_seed(3)
+    for ours, ref in ((joint_model.Segmentation(1, 2), rjm.Segmentation(1, 2)),
+                      (joint_model.VAE(2, 2, dim=128), rjm.VAE(2, 2, dim=128))):
+        a, b = ours.state_dict(), ref.state_dict()
+        assert list(a.keys()) == list(b.keys())
+        for k in a:
+            assert a[k].shape == b[k].shape and a[k].dtype == b[k].dtype, k
+            if k.rsplit(".", 1)[-1] in ("running_mean", "running_var", "num_batches_tracked") or \
+                    (k.rsplit(".", 2)[-2] in ("1", "4", "7") and "conv" in k):
+                assert torch.equal(a[k], b[k]), k                                  # BatchNorm init: ones / zeros / 0
+        ours.load_state_dict(b, strict=True)

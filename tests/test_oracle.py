@@ -2,6 +2,7 @@
 REAL reference (tests/golden/, oracle/make_golden.py) and, when /root/reference is present
 (authoring container), against the real reference modules executed live."""
 import os
+from collections import OrderedDict
 
 import numpy as np
 import pytest
@@ -207,3 +208,41 @@ def test_oracle_equals_real_reference_encoder_and_fusion():
     img, mask = torch.randn(1, 1, 32, 32, 32), R.one_hot((torch.rand(1, 1, 32, 32, 32) > 0.9).float())
     with torch.no_grad():
         assert torch.equal(fus({"i": img, "m": mask}, "i", "m", "o")["o"], R.fusion_forward(fus.state_dict(), img, mask))
+
+
+@needs_ref
+def test_oracle_batchnorm_path_equals_real_reference():
+    """norm_type=2: the oracle's F.batch_norm branch against the reference's nn.BatchNorm3d-based Segmentation, training
+    mode (forward, every gradient, running-statistics update) and eval mode (forward)."""
+    jm, ev = reference_shim.load()
+    torch.manual_seed(5)
+    m = jm.Segmentation(1, 2, norm_type=2)
+    with torch.no_grad():
+        for k, p in m.named_parameters():
+            if k.rsplit(".", 2)[-2] in ("1", "4", "7") and "conv" in k:          # BatchNorm affine parameters
+                p.copy_(0.5 + torch.rand_like(p) if k.endswith("weight") else 0.2 * torch.randn_like(p))
+    sd = OrderedDict((k, v.clone()) for k, v in m.state_dict().items())
+    x, lab = torch.randn(2, 1, 32, 32, 32), (torch.rand(2, 1, 32, 32, 32) > 0.7).float()
+    m.train()
+    pred = m({"img": x}, "img", "pred")["pred"]
+    onehot = R.one_hot(lab)
+    loss = 1 - ev.avg_dsc({"p": pred, "t": onehot}, source_key="p", target_key="t", botindex=1, topindex=2)
+    loss.backward()
+    rsd = R._leafify(sd)
+    pred_o = R.seg_forward(rsd, x)
+    loss_o = 1 - R.avg_dsc(pred_o, onehot, botindex=1, topindex=2)
+    loss_o.backward()
+    assert torch.equal(pred, pred_o) and torch.equal(loss, loss_o)
+    for k, p in m.named_parameters():
+        assert torch.allclose(p.grad, rsd[k].grad, rtol=1e-6, atol=1e-9), k
+    new = m.state_dict()
+    for k in sd:
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            assert torch.equal(new[k], rsd[k].detach()), k
+    m.eval()
+    R.BN_EVAL = True
+    try:
+        with torch.no_grad():
+            assert torch.equal(m({"img": x}, "img", "pred")["pred"], R.seg_forward(R._leafify(new, requires_grad=False), x))
+    finally:
+        R.BN_EVAL = False

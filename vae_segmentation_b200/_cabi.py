@@ -52,6 +52,9 @@ _SIGNATURES = {
     "vs_inorm_relu_bwd_reduce": [_I, _P, _P, _P, _P, _I, _L, _I, _I, _P],
     "vs_inorm_relu_bwd_apply": [_I, _P, _P, _P, _P, _P, _I, _L, _I, _P],
     "vs_add_inplace": [_I, _P, _P, _L, _P],
+    "vs_affine_relu_apply": [_I, _P, _P, _P, _P, _I, _L, _I, _P],
+    "vs_affine_relu_bwd_reduce": [_I, _P, _P, _P, _P, _P, _I, _L, _I, _P],
+    "vs_affine_relu_bwd_apply": [_I, _P, _P, _P, _P, _P, _I, _L, _I, _P],
     "vs_softmax2_fwd": [_P, _P, _I, _L, _P],
     "vs_softmax2_bwd": [_I, _P, _P, _P, _I, _L, _P],
     "vs_softmax2_bwd_pad8": [_P, _P, _P, _P, _I, _L, _P],

@@ -4,7 +4,7 @@ set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="${VS_EXTRA_FLAGS:-} -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Xcompiler -fvisibility=default"
-SRCS="cabi.cu conv3_direct.cu k2s2.cu norm_act.cu losses.cu fc.cu optim.cu resize.cu"
+SRCS="cabi.cu conv3_direct.cu k2s2.cu norm_act.cu affine_act.cu losses.cu fc.cu optim.cu resize.cu"
 if [ -f conv3_tc.cu ]; then SRCS="$SRCS conv3_tc.cu conv3_wgrad_tc.cu conv3_tc_kdn.cu k2s2_tc.cu k2s2_wgrad_tc.cu"; FLAGS="$FLAGS -DVS_WITH_TCGEN05"; fi
 mkdir -p build
 pids=()

@@ -64,12 +64,15 @@ def _sim(t, what):
 
 
 class Layer(object):
-    __slots__ = ("kind", "name", "cin", "cout", "wi", "bi", "save_as", "skip_from", "in_planar")
+    __slots__ = ("kind", "name", "cin", "cout", "wi", "bi", "save_as", "skip_from", "in_planar", "bn", "gi", "bti")
 
-    def __init__(self, kind, name, cin, cout, wi, bi, save_as=None, skip_from=None, in_planar=False):
+    def __init__(self, kind, name, cin, cout, wi, bi, save_as=None, skip_from=None, in_planar=False, bn=None, gi=None, bti=None):
         self.kind, self.name, self.cin, self.cout = kind, name, cin, cout
         self.wi, self.bi = wi, bi
         self.save_as, self.skip_from, self.in_planar = save_as, skip_from, in_planar
+        # BatchNorm3d instead of InstanceNorm3d behind the conv (norm_type 2): the parameter-holding module (running
+        # statistics, momentum, eps, .training) and the indices of its weight (gamma) / bias (beta) in `tensors`
+        self.bn, self.gi, self.bti = bn, gi, bti
 
 
 class _PackJob(ctypes.Structure):
@@ -351,6 +354,76 @@ def _hand_back(grads, need, wi, bi, tw, tb, acc):
     grads[bi] = tb if (need[bi] and not acc) else None
 
 
+def _bn_forward_tables(L, tensors, stats, shift, S):
+    """BatchNorm3d (joint_model.py:12-13: momentum 0.1, eps 1e-5, affine, running statistics) on top of the per-(n,c)
+    outputs of the convolution kernel: stats [N,C,2] = (sum, sum of squares) of the STORED output y_s = conv - shift[n,c]
+    (no bias: it cancels in training mode and is folded in below in eval mode).  Returns the coefficient tables of the
+    affine kernels -- kb: a = relu(k*y_s + b); k2b2: xhat = k2*y_s + b2 -- and (k [C], rstd [C]) in fp64.  A few hundred
+    numbers: plain torch ops, fp64."""
+    bn = L.bn
+    n, c = stats.shape[0], stats.shape[1]
+    gamma = tensors[L.gi].detach().double()
+    beta = tensors[L.bti].detach().double()
+    bias = tensors[L.bi].detach().double()
+    sh = shift.double()
+    if bn.training:
+        m_n = sh + stats[..., 0] / S                                  # per-sample mean of the bias-free conv output
+        v_n = stats[..., 1] / S - (stats[..., 0] / S) ** 2            # per-sample biased variance
+        mean = m_n.mean(0)
+        var = ((v_n + m_n ** 2).mean(0) - mean ** 2).clamp_min(0.0)   # biased variance over (N, D, H, W)
+        with torch.no_grad():
+            cnt = float(n * S)
+            mom = bn.momentum
+            bn.running_mean.mul_(1.0 - mom).add_((mean + bias).float(), alpha=mom)        # BN sees conv + bias
+            bn.running_var.mul_(1.0 - mom).add_((var * (cnt / max(cnt - 1.0, 1.0))).float(), alpha=mom)
+            bn.num_batches_tracked.add_(1)
+    else:
+        mean = bn.running_mean.double() - bias
+        var = bn.running_var.double()
+    rstd = torch.rsqrt(var + bn.eps)
+    k = gamma * rstd
+    b = beta[None] - k[None] * (mean[None] - sh)
+    kb = torch.stack([k[None].expand(n, c), b], -1).float().contiguous()
+    k2b2 = torch.stack([rstd[None].expand(n, c), (sh - mean[None]) * rstd[None]], -1).float().contiguous()
+    return kb, k2b2, (k, rstd)
+
+
+def _bn_backward_tables(L, sums, kb, k2b2, aux, S, training):
+    """From the per-(n,c) sums (sum gm, sum gm*xhat): dgamma, dbeta, the conv-bias gradient and the coefficients of
+    dy = c0*gm + c1 + c2*y_s (BatchNorm backward in training mode; a plain scale in eval mode)."""
+    k, rstd = aux
+    n, c = sums.shape[0], sums.shape[1]
+    g0, g1 = sums[..., 0].sum(0), sums[..., 1].sum(0)                 # [C]
+    dgamma, dbeta = g1.float(), g0.float()
+    k2, b2 = k2b2[..., 0].double(), k2b2[..., 1].double()
+    if training:
+        cnt = float(n * S)
+        m0, m1 = g0 / cnt, g1 / cnt
+        c0 = k[None].expand(n, c)
+        c1 = -k[None] * m0[None] - k[None] * m1[None] * b2
+        c2 = -k[None] * m1[None] * k2
+        dbias = torch.zeros(c, device=sums.device, dtype=torch.float32)   # cancels in the batch statistics
+    else:
+        c0 = k[None].expand(n, c)
+        c1 = torch.zeros(n, c, device=sums.device, dtype=torch.float64)
+        c2 = c1
+        dbias = (k * g0).float()
+    coef = torch.stack([c0, c1, c2], -1).float().contiguous()
+    return coef, dgamma, dbeta, dbias
+
+
+def _accumulate_small(param_refs, need, grads, i, value):
+    """Hands a small parameter gradient (BatchNorm gamma / beta, conv bias) to its .grad buffer or back to autograd."""
+    if i is None or not need[i]:
+        return
+    tgt, acc = _grad_target(param_refs[i], True)
+    if acc:
+        tgt.add_(value.reshape(tgt.shape))
+        grads[i] = None
+    else:
+        grads[i] = value.reshape(param_refs[i].shape).clone()
+
+
 def program_forward(layers, tensors, x, dims, dtype, cache, record=True):
     """x: NDHWC `dtype` tensor (planar fp32 when layers[0].in_planar).  dims=(N,D,H,W) of x.
     Returns (out, out_dims, tape)."""
@@ -361,7 +434,19 @@ def program_forward(layers, tensors, x, dims, dtype, cache, record=True):
     # statistics + shift words of every Conv+InstanceNorm layer, zeroed by ONE launch (not one memset per layer)
     arena = ops.StatsArena(sum(ops.stats_words(n, L.cout) for L in layers if L.kind == C3IN), x.device)
     for L in layers:
-        if L.kind == C3IN:
+        if L.kind == C3IN and L.bn is not None:
+            # Conv3d -> BatchNorm3d -> ReLU (norm_type 2): same convolution kernels (tap-per-MMA / CUDA-core), batch
+            # statistics pooled on the host side of the launch stream, affine + ReLU kernels of affine_act.cu
+            wf, wd, wtc, wdtc = cache.conv3(tensors[L.wi], tc=(dtype == torch.bfloat16))
+            y, stats, shift = ops.conv3_fprop(cur, wf, None, (n, d, h, w), L.cin, L.cout, dtype, in_planar=L.in_planar,
+                                              wtc=None if L.in_planar else wtc, return_shift=True)
+            skip = slots[L.skip_from] if L.skip_from is not None else None
+            kb, k2b2, aux = _bn_forward_tables(L, tensors, stats, shift, float(d * h * w))
+            a = ops.affine_relu_apply(y, kb, skip)
+            if record:
+                tape.append((L, cur, y, (kb, k2b2, aux, bool(L.bn.training)), (n, d, h, w), (wd, wdtc)))
+            cur = a
+        elif L.kind == C3IN:
             wf, wd, wtc, wdtc = cache.conv3(tensors[L.wi], tc=(dtype == torch.bfloat16))
             wkd_in = None
             if L.in_planar and L.cin == 2 and record and dtype == torch.bfloat16 and L.cout % 8 == 0:
@@ -469,7 +554,7 @@ def program_backward(tape, g, dtype, need, grads, param_refs, need_input_grad):
         if idx == 0 or SIMULATE_BF16 or not FUSE_BWD_REDUCE:
             return None
         Lp = tape[idx - 1][0]
-        if Lp.kind != C3IN or (Lp.save_as is not None and Lp.save_as in pending):
+        if Lp.kind != C3IN or Lp.bn is not None or (Lp.save_as is not None and Lp.save_as in pending):
             return None
         dd = tape[idx][4]
         if FUSE_BWD_REDUCE_MAX_VOX and dd[1] * dd[2] * dd[3] > FUSE_BWD_REDUCE_MAX_VOX:
@@ -488,7 +573,24 @@ def program_backward(tape, g, dtype, need, grads, param_refs, need_input_grad):
         want_dx = (not first) or need_input_grad
         if L.save_as is not None and L.save_as in pending:
             g = ops.add_inplace(g, pending.pop(L.save_as))
-        if L.kind == C3IN:
+        if L.kind == C3IN and L.bn is not None:
+            if L.skip_from is not None:
+                pending[L.skip_from] = g
+            kb, k2b2, aux, was_training = stats
+            S = float(dims[1] * dims[2] * dims[3])
+            sums = ops.affine_relu_bwd_reduce(g, y, kb, k2b2)
+            coef, dgamma, dbeta, dbias = _bn_backward_tables(L, sums, kb, k2b2, aux, S, was_training)
+            dy = ops.affine_relu_bwd_apply(g, y, kb, coef)
+            _accumulate_small(param_refs, need, grads, L.gi, dgamma)
+            _accumulate_small(param_refs, need, grads, L.bti, dbeta)
+            _accumulate_small(param_refs, need, grads, L.bi, dbias)
+            if need[L.wi]:
+                tgt, acc = _grad_target(param_refs[L.wi], True)
+                dw = ops.conv3_wgrad(x_in, dy, dims, L.cin, L.cout, dw=tgt, in_planar=L.in_planar, accumulate=acc)[0]
+                grads[L.wi] = None if acc else dw
+            _grad_ready(param_refs[L.wi], param_refs[L.bi], param_refs[L.gi], param_refs[L.bti])
+            g = ops.conv3_dgrad(dy, wd[0], dims, L.cin, L.cout, dtype, out_planar=L.in_planar, wdtc=wd[1]) if want_dx else None
+        elif L.kind == C3IN:
             if L.skip_from is not None:
                 pending[L.skip_from] = g
             dy = _sim(ops.inorm_relu_bwd(g, y, stats, sums=sums_of[idx], reduced=idx in fused), "dy")

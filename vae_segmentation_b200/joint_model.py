@@ -10,8 +10,9 @@ hand-written sm_100a kernels of libvaeseg_b200.so through `engine`.  There is no
 compute and no CPU fallback: CPU tensors raise.
 
 Differences, all explicit:
-  * only norm_type=1 (InstanceNorm3d), the configuration every shipped script uses, is
-    implemented; 2/3 raise NotImplementedError.
+  * norm_type=1 (InstanceNorm3d, the configuration every shipped script uses) and norm_type=2
+    (BatchNorm3d, the constructors' default) are implemented; 3 (GSNorm3d) raises
+    NotImplementedError.
   * VAE takes an extra keyword `patch` (default 128): the reference hard-codes the 128^3
     flat dimension 16384 (joint_model.py:216-218,241,253); flat = 256*(patch/32)^3 here.
   * dropout probabilities other than 0 raise (every shipped preset uses 0).
@@ -82,11 +83,31 @@ class _Fused(nn.Module):
         return self.what + " (fused)"
 
 
+class _BatchNormParams(nn.Module):
+    """Parameters and running statistics of nn.BatchNorm3d(C, momentum=0.1) (joint_model.py:12-13), same state_dict keys
+    (weight, bias, running_mean, running_var, num_batches_tracked); the arithmetic is fused into the neighbouring kernels
+    (engine._bn_forward_tables + csrc/affine_act.cu).  .train() / .eval() select batch / running statistics."""
+
+    def __init__(self, num_features, eps=1e-5, momentum=0.1):
+        super().__init__()
+        self.num_features, self.eps, self.momentum = num_features, eps, momentum
+        self.weight = nn.Parameter(torch.ones(num_features))
+        self.bias = nn.Parameter(torch.zeros(num_features))
+        self.register_buffer("running_mean", torch.zeros(num_features))
+        self.register_buffer("running_var", torch.ones(num_features))
+        self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+
+    def extra_repr(self):
+        return "%d, eps=%g, momentum=%g, affine=True, track_running_stats=True (fused)" % (self.num_features, self.eps, self.momentum)
+
+
 def Normalization(norm_type, out_channels, num_group=1):
     if norm_type == 1:
         return _Fused("InstanceNorm3d(%d, eps=1e-05, affine=False)" % out_channels)
-    raise NotImplementedError("vaeseg_b200 implements norm_type=1 (InstanceNorm3d) only; got norm_type=%r "
-                              "(BatchNorm3d / GSNorm3d are not used by any shipped script)" % (norm_type,))
+    if norm_type == 2:
+        return _BatchNormParams(out_channels)
+    raise NotImplementedError("vaeseg_b200 implements norm_type=1 (InstanceNorm3d) and 2 (BatchNorm3d); got norm_type=%r "
+                              "(GSNorm3d is not used by any shipped script)" % (norm_type,))
 
 
 # ---- program building --------------------------------------------------------------------
@@ -103,6 +124,13 @@ def _j(prefix, name):
 
 
 def _conv_layers(idx, prefix, cin, cout, in_planar=False, **kw):
+    # the normalisation sits at the next nn.Sequential index (joint_model.py:40-46,106); a _BatchNormParams there
+    # switches the layer to the BatchNorm path of the engine
+    head, _, last = prefix.rpartition(".")
+    norm_name = (head + "." if head else "") + str(int(last) + 1)
+    bn = idx.get("__modules__", {}).get(norm_name)
+    if isinstance(bn, _BatchNormParams):
+        kw = dict(kw, bn=bn, gi=idx[norm_name + ".weight"], bti=idx[norm_name + ".bias"])
     return [Layer(C3IN, prefix, cin, cout, idx[prefix + ".weight"], idx[prefix + ".bias"], in_planar=in_planar, **kw)]
 
 
@@ -168,6 +196,7 @@ class _Engineered(nn.Module):
     def _prog(self):
         if self._program is None:
             idx, params = _index(self)
+            idx["__modules__"] = dict(self.named_modules())
             self._program = (self._build(idx), params)
         return self._program
 
@@ -219,7 +248,7 @@ class Conv(_Engineered):
         self._engine_init()
 
     def _build(self, idx):
-        return [Layer(C3IN, "conv.0", self.in_ch, self.out_ch, idx["conv.0.weight"], idx["conv.0.bias"])]
+        return _conv_layers(idx, "conv.0", self.in_ch, self.out_ch)
 
     def forward(self, x):
         _check_input(x, "Conv")

@@ -187,7 +187,9 @@ def main(argv=None):
                     if args.max_iters and iters >= args.max_iters:
                         break
             # ---- validation ----
+            model.eval()                                                                   # main_source.py:690
             dsc = validate(method, model, val_set, val_names, world, rank, dev)
+            model.train()                                                                  # :822
             say("epoch %d validation result: %f, best result %f." % (epoch + 1, dsc, best))
             if args.test_only or (args.max_iters and iters >= args.max_iters):
                 break

@@ -192,6 +192,11 @@ def main(argv=None):
     for m in (model, model_fix, model_finetune):
         if m is not None:
             m.to(dev).set_precision(args.precision)
+    # main_target.py:336,399,433 (no effect on the InstanceNorm models the driver builds; kept for the same module state)
+    model.Vae.eval()
+    model_fix.eval()
+    if model_finetune is not None:
+        model_finetune.Vae.eval()
     trainer = ts.JointTrainer(model, model_fix, lr=args.lr_seg, momentum=0.9, lambda_vae=args.lambda_vae,
                               loss_type=args.domain_loss_type, kl=args.kl, confident=args.use_confident_binarize,
                               only_pseudo=args.only_pseudo, alpha=args.alpha, adam=args.adam)
@@ -255,7 +260,10 @@ def main(argv=None):
                         break
             # ---- validation (:795-960) ----
             cases = (val_set.load(n) for n in val_names)
+            model.eval()                                                                  # :756
             out = trainer.validate(cases, finetune=model_finetune, val_finetune=args.val_finetune, lr_finetune=args.lr_finetune)
+            model.train()                                                                 # :1041-1043
+            model.Vae.eval()
             say("epoch %d validation result: %f, best result %f." % (epoch + 1, out["dsc"], best) +
                 (" (no finetune: %f)" % out["dsc_noft"] if args.val_finetune else ""))
             if args.test_only or (args.max_iters and iters >= args.max_iters):

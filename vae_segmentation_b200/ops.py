@@ -119,7 +119,7 @@ class StatsArena(object):
 
 
 def conv3_fprop(x, wf, bias, dims, cin, cout, out_dtype, in_planar=False, out_planar=False, want_stats=True,
-                shifted=None, wtc=None, arena=None):
+                shifted=None, wtc=None, arena=None, return_shift=False):
     """dims = (N, D, H, W).  Returns (y, stats).  `shifted` (default: same as want_stats) subtracts the
     per-(n,co) reference-voxel value from the output (InstanceNorm-invariant, see the header).  `arena`: a
     zero-filled StatsArena that supplies the statistics / shift words (the call then skips its memset)."""
@@ -149,6 +149,8 @@ def conv3_fprop(x, wf, bias, dims, cin, cout, out_dtype, in_planar=False, out_pl
         shift = torch.empty(n, cout, device=dev, dtype=torch.float32)
     _cabi.call("vs_conv3x3x3_fprop", _dt(x), _dt(y), int(in_planar), int(out_planar), flags, _p(x), _p(_f32(wf, "wf")), _p(wtc),
                _p(_f32(bias, "bias")), _p(y), _p(stats), _p(shift), n, d, h, w, cin, cout, _stream())
+    if return_shift:
+        return y, stats, shift
     return y, stats
 
 
@@ -258,6 +260,36 @@ def inorm_relu_bwd(g, y, stats, sums=None, reduced=False):
         _cabi.call("vs_inorm_relu_bwd_reduce", _dt(y), _p(g), _p(y), _p(stats), _p(sums), n, s, c, flags, _stream())
     dy = torch.empty_like(y)
     _cabi.call("vs_inorm_relu_bwd_apply", _dt(y), _p(g), _p(y), _p(stats), _p(sums), _p(dy), n, s, c, _stream())
+    return dy
+
+
+# ---- per-(n,c) affine + ReLU (BatchNorm path) -------------------------------------------------------------------------
+def affine_relu_apply(y, kb, skip=None):
+    """a = relu(k*y + b) (+ skip); kb [N,C,2] fp32."""
+    n, c = y.shape[0], y.shape[-1]
+    s = y.numel() // (n * c)
+    a = torch.empty_like(y)
+    _cabi.call("vs_affine_relu_apply", _dt(y), _p(y), _p(_f32(kb, "kb")), _p(skip), _p(a), n, s, c, _stream())
+    return a
+
+
+def affine_relu_bwd_reduce(g, y, kb, k2b2):
+    """sums [N,C,2] fp64 = (sum gm, sum gm*xhat) with gm = g*[k*y+b > 0], xhat = k2*y + b2."""
+    n, c = y.shape[0], y.shape[-1]
+    s = y.numel() // (n * c)
+    sums = torch.empty(n, c, 2, device=y.device, dtype=torch.float64)
+    _cabi.call("vs_affine_relu_bwd_reduce", _dt(y), _p(g), _p(y), _p(_f32(kb, "kb")), _p(_f32(k2b2, "k2b2")), _p(sums), n, s, c,
+               _stream())
+    return sums
+
+
+def affine_relu_bwd_apply(g, y, kb, coef):
+    """dy = c0*gm + c1 + c2*y; coef [N,C,3] fp32."""
+    n, c = y.shape[0], y.shape[-1]
+    s = y.numel() // (n * c)
+    dy = torch.empty_like(y)
+    _cabi.call("vs_affine_relu_bwd_apply", _dt(y), _p(g), _p(y), _p(_f32(kb, "kb")), _p(_f32(coef, "coef")), _p(dy), n, s, c,
+               _stream())
     return dy
 
 

@@ -333,8 +333,15 @@ class JointTrainer(object):
         self.wgrad_stream = [torch.cuda.Stream() for _ in range(max(1, int(os.environ.get("VAESEG_WGRAD_STREAMS", "1"))))]
 
     def ema_teacher(self):
-        # main_target.py:512-516 on the Seg state_dict
+        # main_target.py:512-516 on the Seg state_dict: parameters through the flat arenas, buffers (the running
+        # statistics of a norm_type=2 model; none with InstanceNorm) one by one
         ops.ema_update(self.teacher_arena.data, self.arena.data, self.alpha)
+        with torch.no_grad():
+            for tb, sb in zip(self.teacher.Seg.buffers(), self.student.Seg.buffers()):
+                if tb.is_floating_point():
+                    tb.mul_(self.alpha).add_(sb, alpha=1.0 - self.alpha)
+                else:                                   # num_batches_tracked: the reference's float result is cast back on load
+                    tb.copy_((self.alpha * tb.double() + (1.0 - self.alpha) * sb.double()).to(tb.dtype))
         self.teacher.repack_packs()
 
     def losses(self, img, label, student=None, sync=True):
@@ -539,6 +546,8 @@ class JointTrainer(object):
             for dst, src in zip(finetune.Vae.parameters(), self.student.Vae.parameters()):   # Joint state is loaded
                 if dst.data_ptr() != src.data_ptr():
                     dst.copy_(src)
+            for dst, src in zip(finetune.buffers(), self.student.buffers()):         # BatchNorm running statistics, if any
+                dst.copy_(src)
         finetune.repack_packs()
         for _ in range(iters):
             ft.zero_grad()
