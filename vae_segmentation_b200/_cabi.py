@@ -108,6 +108,8 @@ def lib():
         # programmatic dependent launch for launches of at most VAESEG_PDL CTAs (include/vaeseg_b200.h: vs_set_pdl); 0 disables
         handle.vs_set_pdl(int(os.environ.get("VAESEG_PDL", PDL_DEFAULT)))
         handle.vs_set_kdn_ordered(int(os.environ.get("VAESEG_KDN_ORDERED", KDN_ORDERED_DEFAULT)))
+        if os.environ.get("VAESEG_NORM_VPT"):                            # A/B switch (tools): grid sizing of the apply passes
+            handle.vs_debug_set_norm_vpt(int(os.environ["VAESEG_NORM_VPT"]))
         if os.environ.get("VAESEG_CONV3_KSPLIT", "1") == "0":          # A/B switch (tools): K split over the conv issuer warps
             handle.vs_debug_set_conv3_ksplit(0)
         _lib = handle

@@ -206,6 +206,7 @@ __global__ void __launch_bounds__(NT) planar_to_ndhwc8_kernel(const float* __res
     }
 }
 
+int g_norm_vpt = 4;      // 16-byte vectors per thread that size the grids of the apply passes (vs_debug_set_norm_vpt)
 int stream_grid(long long work_items) {
     long long blocks = (work_items + NT - 1) / NT;
     long long cap = (long long)vs_sm_count() * 8;
@@ -225,7 +226,7 @@ extern "C" int vs_inorm_relu_apply(int dtype, const void* y, const double* stats
                                    int n, long long s, int c, void* stream) {
     int rc = check_norm(y, a, n, s, c, "inorm_relu_apply");
     if (rc) return rc;
-    dim3 grid(stream_grid(s * (c / 8) / 4 + 1), n);
+    dim3 grid(stream_grid(s * (c / 8) / g_norm_vpt + 1), n);
     VS_DISPATCH_DTYPE(dtype, T, { VS_CUDA(vs_launch(inorm_relu_apply_kernel<T>, grid, dim3(NT), 0, (cudaStream_t)stream,
         (const T*)y, stats, (const T*)skip, (T*)a, s, c), "inorm_relu_apply launch"); });
     VS_CHECK_LAUNCH("inorm_relu_apply_kernel");
@@ -251,7 +252,7 @@ extern "C" int vs_inorm_relu_bwd_apply(int dtype, const void* g, const void* y, 
                                        void* dy, int n, long long s, int c, void* stream) {
     int rc = check_norm(g, dy, n, s, c, "inorm_relu_bwd_apply");
     if (rc) return rc;
-    dim3 grid(stream_grid(s * (c / 8) / 4 + 1), n);
+    dim3 grid(stream_grid(s * (c / 8) / g_norm_vpt + 1), n);
     VS_DISPATCH_DTYPE(dtype, T, { VS_CUDA(vs_launch(inorm_relu_bwd_apply_kernel<T>, grid, dim3(NT), 0, (cudaStream_t)stream,
         (const T*)g, (const T*)y, stats, sums, (T*)dy, s, c), "inorm_relu_bwd_apply launch"); });
     VS_CHECK_LAUNCH("inorm_relu_bwd_apply_kernel");
@@ -262,7 +263,7 @@ extern "C" int vs_add_inplace(int dtype, void* dst, const void* src, long long c
     VS_REQUIRE(dst && src && count > 0 && count % 8 == 0, VS_ERR_SHAPE, "add_inplace: count must be a positive multiple of 8");
     VS_REQUIRE(vs_aligned16(dst) && vs_aligned16(src), VS_ERR_ALIGN, "add_inplace: pointers must be 16B aligned");
     const long long nvec = count / 8;
-    VS_DISPATCH_DTYPE(dtype, T, { VS_CUDA(vs_launch(add_inplace_kernel<T>, dim3(stream_grid(nvec / 4 + 1)), dim3(NT), 0,
+    VS_DISPATCH_DTYPE(dtype, T, { VS_CUDA(vs_launch(add_inplace_kernel<T>, dim3(stream_grid(nvec / g_norm_vpt + 1)), dim3(NT), 0,
         (cudaStream_t)stream, (T*)dst, (const T*)src, nvec), "add_inplace launch"); });
     VS_CHECK_LAUNCH("add_inplace_kernel");
     return VS_OK;
@@ -303,3 +304,5 @@ extern "C" int vs_planar_to_ndhwc8(const float* x, void* out, int n, int c, long
     VS_CHECK_LAUNCH("planar_to_ndhwc8_kernel");
     return VS_OK;
 }
+
+extern "C" void vs_debug_set_norm_vpt(int vpt) { g_norm_vpt = vpt > 0 ? vpt : 4; }
