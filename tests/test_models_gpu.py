@@ -700,8 +700,11 @@ def test_main_source_cli_shim_synthetic_run(tmp_path, method):
         assert cli.main(argv) == 0
     text = buf.getvalue()
     losses = [float(l.split("loss:")[1].split(",")[0]) for l in text.splitlines() if "loss:" in l]
-    assert len(losses) >= 2 and losses[-1] < losses[0], text
-    assert text.count("validation result") == 3
+    vals = [float(l.split("validation result:")[1].split(",")[0]) for l in text.splitlines() if "validation result:" in l]
+    # lr 0.1 from random weights is a bumpy ride (the last printed loss of four identical runs: 0.93 / 0.76 / 0.80 / 0.54
+    # after 0.96 at the first step): the loss must have gone down at some print and the validation Dice must have improved
+    assert len(losses) >= 2 and min(losses[1:]) < losses[0], text
+    assert len(vals) == 3 and max(vals[1:]) > vals[0], text
     ckpt = torch.load(os.path.join(root, "srctest", "model_epoch12.ckpt"))
     assert set(ckpt) == {"epoch", "model_state_dict", "optimizer_state_dict"} and ckpt["epoch"] == 12
     fresh = jm.Segmentation(1, 2, norm_type=1) if method == "seg_train" else jm.VAE(2, 2, norm_type=1, dim=128, patch=64)
