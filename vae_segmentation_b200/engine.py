@@ -52,7 +52,7 @@ FUSE_APPLY_MAX_VOX = int(os.environ.get("VAESEG_FUSE_APPLY_MAX_VOX", "0"))      
 # (csrc/k2s2_tc.cu); VAESEG_K2_TC=0 keeps the CUDA-core kernels of csrc/k2s2.cu (A/B measurements).
 USE_K2_TC = os.environ.get("VAESEG_K2_TC", "1") == "1"
 
-# tools/precision_probe*.py only: names of tensor classes to round through bf16 while running the fp32
+# tools/precision_attrib.py and the calibration of tests/test_models_gpu.py only: names of tensor classes to round through bf16 while running the fp32
 # check mode ("y", "a", "g", "dy", "k2"), to attribute bf16-mode error to a storage point.  Empty in production.
 SIMULATE_BF16 = set()
 
