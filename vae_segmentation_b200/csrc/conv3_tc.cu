@@ -127,7 +127,11 @@ __device__ __forceinline__ void decode_work(long long item64, const TcParams& p,
 // ---------------------------------------------------------------------------------------------
 // H8 (NC = 16 only): the layer has 8 output channels -- the epilogue touches accumulator columns 0..7 only (the MMA
 // still runs at N = 16, its minimum at M = 128; columns 8..15 hold the zero-padded weights' zeros).
-template <int NC, bool CIN8, int NSTAGE, bool H8 = false>
+// FEAT: compile-time feature set (planar epilogue, fused InstanceNorm pass, fused norm-backward reduction): the rarely used
+// paths get their own instantiations so the default body stays small (see conv3_tc_kdn.cu: compiled into one body they
+// cost the hot kernel 30 % through registers and instruction-cache footprint).
+constexpr int TC_PLANAR = 1, TC_APPLY = 2, TC_REDUCE = 8;
+template <int NC, bool CIN8, int NSTAGE, bool H8, int FEAT>
 __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_constant__ CUtensorMap xmap, TcParams p) {
     static_assert(!H8 || NC == 16, "H8 is a variant of the 16-column kernel");
     constexpr int NV = H8 ? 8 : 16;                           // accumulator columns the epilogue processes per 16-column group
@@ -282,7 +286,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
         for (int c = 0; c < NC / 16; ++c)
 #pragma unroll
             for (int k = 0; k < 16; ++k) { rs[c][k] = 0.f; rq[c][k] = 0.f; }
-        const bool fused = p.psums != nullptr;
+        const bool fused = (FEAT & TC_REDUCE) && p.psums != nullptr;
         double* const sout = fused ? p.psums : p.stats;
         auto flush_stats = [&]() {
             if (sout != nullptr && stat_n >= 0) {
@@ -310,7 +314,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
         // (decode_work), a producing item never waits, and the hardware dispatches CTAs in index order -- so whenever
         // a waiter is resident, the CTA it waits on already is, independent of what else occupies the GPU.
         float hb0 = 0.f, hb1 = 0.f;
-        if (p.planar_mode == 1 && p.bias != nullptr) { hb0 = p.bias[0]; hb1 = p.bias[1]; }
+        if ((FEAT & TC_PLANAR) && p.planar_mode == 1 && p.bias != nullptr) { hb0 = p.bias[0]; hb1 = p.bias[1]; }
         const long long vol = (long long)p.d * p.h * p.w;
         const int rd = min(1, p.d - 1), rh = min(1, p.h - 1), rw = min(1, p.w - 1);
         const bool has_shift = p.shift != nullptr;
@@ -476,7 +480,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
 #pragma unroll
                         for (int k = 0; k < NV; ++k) v[k] = 0.f;
                     }
-                    if (p.planar_mode != 0) {
+                    if ((FEAT & TC_PLANAR) && p.planar_mode != 0) {
                         if (rc_ok && c16 == 0 && co0 == 0) {
                             float o0 = v[0] + hb0, o1 = v[1] + hb1;
                             if (p.planar_mode == 1) {
@@ -554,7 +558,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const __grid_cons
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
-    if (p.a_out != nullptr) {
+    if ((FEAT & TC_APPLY) && p.a_out != nullptr) {
         // ---- fused InstanceNorm + ReLU (+ skip); see conv3_tc_kdn.cu ---------------------------------------------------
         __threadfence();
         __syncthreads();
@@ -596,13 +600,16 @@ int nc_for(int gout) { return nc_for_dev(gout); }
 long long* g_tc_dbg = nullptr;   // vs_debug_set_tc_phase_buffer: device buffer of >= 16 clock64 slots (tools/tc_phase_probe.py)
 int g_conv3_ksplit = 1;          // A/B switch (vs_debug_set_conv3_ksplit): K split over the issuer warps that share a plane
 
-template <int NC, bool CIN8, int NSTAGE, bool H8 = false>
-int launch_tc(const CUtensorMap& map, const TcParams& p, cudaStream_t st) {
+template <int NC, bool CIN8, int NSTAGE, bool H8, int FEAT>
+int launch_tc_feat(const CUtensorMap& map, const TcParams& p, cudaStream_t st) {
     constexpr int A_BYTES = CIN8 ? (PLANE_BYTES + PLANE_PAD) : 2 * PLANE_BYTES;
     constexpr int B_BYTES = (CIN8 ? 14 : 27) * NC * 32;
-    constexpr int SMEM = NSTAGE * (A_BYTES + B_BYTES) + 128 /*align*/ + 8 * (2 * NSTAGE + 4) + 16 + NC * 4 + NC * 16 + 64;
+    constexpr int SMEM_NEED = NSTAGE * (A_BYTES + B_BYTES) + 128 /*align*/ + 8 * (2 * NSTAGE + 4) + 16 + NC * 4 + NC * 16 + 64;
+    // one CTA per SM whatever the register count (see conv3_tc_kdn.cu: a second resident CTA that blocks in tcgen05.alloc
+    // can dead-lock the shift hand-off)
+    constexpr int SMEM = SMEM_NEED > 120 * 1024 ? SMEM_NEED : 120 * 1024;
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
-    auto kern = conv3_tc_kernel<NC, CIN8, NSTAGE, H8>;
+    auto kern = conv3_tc_kernel<NC, CIN8, NSTAGE, H8, FEAT>;
     static bool configured = false;
     if (!configured) {
         VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM), "conv3_tc smem attribute");
@@ -615,6 +622,18 @@ int launch_tc(const CUtensorMap& map, const TcParams& p, cudaStream_t st) {
         VS_CUDA(vs_launch(kern, dim3((unsigned)grid), dim3(NTHREADS), SMEM, st, map, p), "conv3_tc_kernel launch");
     VS_CHECK_LAUNCH("conv3_tc_kernel");
     return VS_OK;
+}
+
+// picks the instantiation for the features this launch needs (see TC_* above)
+template <int NC, bool CIN8, int NSTAGE, bool H8 = false>
+int launch_tc(const CUtensorMap& map, const TcParams& p, cudaStream_t st) {
+    if (p.a_out != nullptr) return launch_tc_feat<NC, CIN8, NSTAGE, H8, TC_APPLY>(map, p, st);
+    if (p.planar_mode != 0) {
+        if constexpr (H8) return launch_tc_feat<NC, CIN8, NSTAGE, H8, TC_PLANAR>(map, p, st);      // planar output: Cout padded to 8
+        else VS_FAIL(VS_ERR_UNSUPPORTED, "conv3_tc: planar output needs Cout padded to 8");
+    }
+    if (p.psums != nullptr) return launch_tc_feat<NC, CIN8, NSTAGE, H8, TC_REDUCE>(map, p, st);
+    return launch_tc_feat<NC, CIN8, NSTAGE, H8, 0>(map, p, st);
 }
 
 }  // namespace

@@ -122,7 +122,12 @@ __device__ __forceinline__ void decode_item(unsigned item, const KdnParams& p, i
     d0 = r * TD;
 }
 
-template <bool CIN8, int NCO, int NSTAGE>
+// FEAT: compile-time feature set -- the rarely used paths live in their OWN instantiations so that the default kernel
+// (FEAT = 0: bf16 NDHWC store, concurrent issue) stays as small as it was before they existed: with the planar epilogue,
+// the ordered issue and the fused InstanceNorm pass compiled into one body the 2 x 96^3 8->8 launch went from 31 to 41 us
+// under ncu (registers 79 -> 128, the warp-specialised roles no longer fit the instruction cache together).
+constexpr int KDN_PLANAR = 1, KDN_APPLY = 2, KDN_ORDERED = 4, KDN_REDUCE = 8;
+template <bool CIN8, int NCO, int NSTAGE, int FEAT>
 __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kdn_kernel(const __grid_constant__ CUtensorMap xmap, KdnParams p) {
     constexpr int N = 4 * NCO;                                // kd' blocks 0..2 + one zero block
     constexpr int NMP = CIN8 ? 5 : 9;                         // MMAs per input plane per 16-channel slice
@@ -235,14 +240,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kdn_kernel(const __grid_
                 bd_rel[k] = make_desc(b_base + m * (N * 32), N * 16, 128u);
                 dcol_rel[k] = (uint32_t)((5 - q) * NCO);                                  // slots (5-q) .. (5-q)+3
                 if (i < HD * NMP && q < p.bd) valid |= 1u << k;                          // q >= bd: plane not staged (never with D >= 4)
-                if (p.ordered && lane == 0 && i < HD * NMP) { tab_a[i] = ad_rel[k]; tab_b[i] = bd_rel[k]; tab_d[i] = dcol_rel[k]; }
+                if ((FEAT & KDN_ORDERED) && lane == 0 && i < HD * NMP) { tab_a[i] = ad_rel[k]; tab_b[i] = bd_rel[k]; tab_d[i] = dcol_rel[k]; }
             }
         }
         // Ordered mode: accumulating MMAs issued by different warps into the same TMEM columns add in ISSUE order, which
         // varies from run to run (fp32 rounding of y moves, a few bf16 roundings flip).  Here warp j = 0 alone issues the
         // whole list, in list order, from the descriptor table the four warps just filled; the other three only keep the
         // barrier protocol going (their commits track no MMAs and arrive at once).
-        if (p.ordered) asm volatile("bar.sync 8, 128;" ::: "memory");
+        if (FEAT & KDN_ORDERED) asm volatile("bar.sync 8, 128;" ::: "memory");
         uint32_t stage = 0, phase = 0, buf = 0, bphase = 0;
         for (int item = blockIdx.x; item < p.work_items; item += gridDim.x) {
             const bool dbg_tile = j == 0 && lane == 0 && item == (int)blockIdx.x + KDN_DBG_TILE * (int)gridDim.x;
@@ -258,7 +263,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kdn_kernel(const __grid_
                 tc_fence_after();
                 if (dbg_tile && ks == 0) KDN_DBG(4);
                 const uint64_t soff = (uint64_t)((stage * (uint32_t)STAGE_BYTES) >> 4);   // start-address field, 16-byte units
-                if (p.ordered) {
+                if (FEAT & KDN_ORDERED) {
                     if (j == 0) {
 #pragma unroll 6
                         for (int i = 0; i < HD * NMP; ++i)
@@ -300,7 +305,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kdn_kernel(const __grid_
         float rs[16], rq[16], shr[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) { rs[k] = 0.f; rq[k] = 0.f; shr[k] = 0.f; }
-        const bool fused = p.psums != nullptr;
+        const bool fused = (FEAT & KDN_REDUCE) && p.psums != nullptr;     // compile-time false outside the dgrad-with-reduction instantiation
         double* const sout = fused ? p.psums : p.stats;
         auto flush_stats = [&]() {
             if (sout != nullptr && stat_n >= 0) {
@@ -322,7 +327,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kdn_kernel(const __grid_
         const bool has_stats = p.stats != nullptr;
         const uint32_t sshift_addr = smem_u32(my_shift);
         float hb0 = 0.f, hb1 = 0.f;
-        if (p.planar_mode == 1 && p.bias != nullptr) { hb0 = p.bias[0]; hb1 = p.bias[1]; }
+        if ((FEAT & KDN_PLANAR) && p.planar_mode == 1 && p.bias != nullptr) { hb0 = p.bias[0]; hb1 = p.bias[1]; }
         const long long vol = (long long)p.d * p.h * p.w;
         const uint32_t smean_addr = smem_u32(smean + 16 * e), srstd_addr = smem_u32(srstd + 16 * e);
         const int ref_row = rh * TW + rw;
@@ -436,7 +441,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kdn_kernel(const __grid_
                         for (int k = 0; k < 8; ++k) v[NCO == 16 ? 8 + k : k] = __uint_as_float(r8[k]) - shr[8 + k];
                     }
                 }
-                if (p.planar_mode != 0) {
+                if ((FEAT & KDN_PLANAR) && p.planar_mode != 0) {
                     if (rc_ok) {
                         float o0 = v[0] + hb0, o1 = v[1] + hb1;
                         if (p.planar_mode == 1) {
@@ -509,7 +514,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kdn_kernel(const __grid_
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
-    if (p.a_out != nullptr) {
+    if ((FEAT & KDN_APPLY) && p.a_out != nullptr) {
         // ---- fused InstanceNorm + ReLU (+ skip) ----------------------------------------------------------------------
         // The statistics are complete once every CTA has flushed: grid barrier (the launch is cooperative: all CTAs are
         // co-resident), then ALL warps of the CTA -- the pipeline roles are over, the stage buffers are free -- turn the
@@ -543,13 +548,19 @@ __global__ void pack_kdn_kernel(const float* __restrict__ w, bf16* __restrict__ 
         out[i] = __float2bfloat16_rn(pack_kdn_elem(w, i, cin, cout, dgrad, cin_real, cout_real));
 }
 
-template <bool CIN8, int NCO, int NSTAGE>
-int launch_kdn(const CUtensorMap& map, const KdnParams& p, cudaStream_t st) {
+template <bool CIN8, int NCO, int NSTAGE, int FEAT>
+int launch_kdn_feat(const CUtensorMap& map, const KdnParams& p, cudaStream_t st) {
     constexpr int A_BYTES = CIN8 ? (PLANE_BYTES + PLANE_PAD) : 2 * PLANE_BYTES;
     constexpr int B_BYTES = (CIN8 ? 5 : 9) * 4 * NCO * 32;
-    constexpr int SMEM = NSTAGE * (A_BYTES + B_BYTES) + 128 + 8 * (2 * NSTAGE + 8) + 16 + 3 * 32 * 4 + 64 + HD * 9 * 20 + 16;
+    constexpr int SMEM_NEED = NSTAGE * (A_BYTES + B_BYTES) + 128 + 8 * (2 * NSTAGE + 8) + 16 + 3 * 32 * 4 + 64 + HD * 9 * 20 + 16;
+    // ONE CTA per SM, enforced through the shared-memory request: a CTA allocates all 512 TMEM columns, so a second
+    // resident CTA (possible by registers and by the 92 KB the Cin = 8 variant really needs) would block in tcgen05.alloc
+    // while holding its slot -- and when the CTA it blocks behind is spinning on a shift that the blocked CTA has to
+    // publish, that is a dead-lock (observed as the spin's trap under the three-branch graph once the default
+    // instantiation dropped below 114 registers)
+    constexpr int SMEM = SMEM_NEED > 120 * 1024 ? SMEM_NEED : 120 * 1024;
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
-    auto kern = conv3_tc_kdn_kernel<CIN8, NCO, NSTAGE>;
+    auto kern = conv3_tc_kdn_kernel<CIN8, NCO, NSTAGE, FEAT>;
     static bool configured = false;
     if (!configured) {
         VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM), "conv3_tc_kdn smem attribute");
@@ -562,6 +573,29 @@ int launch_kdn(const CUtensorMap& map, const KdnParams& p, cudaStream_t st) {
         VS_CUDA(vs_launch(kern, dim3((unsigned)grid), dim3(NTHREADS), SMEM, st, map, p), "conv3_tc_kdn_kernel launch");
     VS_CHECK_LAUNCH("conv3_tc_kdn_kernel");
     return VS_OK;
+}
+
+// picks the instantiation for the features this launch needs (see KDN_* above)
+template <bool CIN8, int NCO, int NSTAGE>
+int launch_kdn(const CUtensorMap& map, const KdnParams& p, cudaStream_t st) {
+    if (p.a_out != nullptr) {
+        if (p.ordered) return launch_kdn_feat<CIN8, NCO, NSTAGE, KDN_APPLY | KDN_ORDERED>(map, p, st);
+        return launch_kdn_feat<CIN8, NCO, NSTAGE, KDN_APPLY>(map, p, st);
+    }
+    if (p.planar_mode != 0) {
+        if constexpr (NCO == 8) {
+            if (p.ordered) return launch_kdn_feat<CIN8, NCO, NSTAGE, KDN_PLANAR | KDN_ORDERED>(map, p, st);
+            return launch_kdn_feat<CIN8, NCO, NSTAGE, KDN_PLANAR>(map, p, st);
+        } else {
+            VS_FAIL(VS_ERR_UNSUPPORTED, "conv3_tc_kdn: planar output needs 8 GEMM output channels");
+        }
+    }
+    if (p.psums != nullptr) {
+        if (p.ordered) return launch_kdn_feat<CIN8, NCO, NSTAGE, KDN_REDUCE | KDN_ORDERED>(map, p, st);
+        return launch_kdn_feat<CIN8, NCO, NSTAGE, KDN_REDUCE>(map, p, st);
+    }
+    if (p.ordered) return launch_kdn_feat<CIN8, NCO, NSTAGE, KDN_ORDERED>(map, p, st);
+    return launch_kdn_feat<CIN8, NCO, NSTAGE, 0>(map, p, st);
 }
 
 }  // namespace
