@@ -1,5 +1,6 @@
 """CPU-side checks of the drop-in module surface: state_dict layout, initialisation stream,
 layer programs (no kernels run here)."""
+import pytest
 import torch
 
 from oracle import ref_torch as R
@@ -104,3 +105,55 @@ def test_batchnorm_variant_state_dict_matches_reference():
                     (k.rsplit(".", 2)[-2] in ("1", "4", "7") and "conv" in k):
                 assert torch.equal(a[k], b[k]), k                                  # BatchNorm init: ones / zeros / 0
         ours.load_state_dict(b, strict=True)
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_batchnorm_host_tables_reproduce_torch_batch_norm(training):
+    """engine._bn_forward_tables / _bn_backward_tables (the host-side part of the norm_type=2 path: pooling of the
+    per-(n,c) convolution statistics, running-statistics update, folding of gamma / beta / shift into the coefficient
+    tables of csrc/affine_act.cu) against torch's batch_norm + ReLU with autograd.  The three affine kernels are
+    restated in torch here (they are elementwise); everything else is the product code, run on CPU tensors."""
+    import torch.nn.functional as F
+    from vae_segmentation_b200 import engine
+    from vae_segmentation_b200.joint_model import _BatchNormParams
+    torch.manual_seed(17 + int(training))
+    n, c, S = 3, 8, 5 * 6 * 7
+    bias = torch.randn(c, dtype=torch.float64)                       # conv bias: y_true = y_nobias + bias
+    y_nobias = (torch.randn(n, c, S, dtype=torch.float64) * 2.0 + 0.7)
+    shift = y_nobias[:, :, 1].clone()                                # stored output = y_nobias - shift[n,c]
+    y_s = y_nobias - shift[..., None]
+    stats = torch.stack([y_s.sum(-1), (y_s ** 2).sum(-1)], -1)      # what the convolution kernels emit
+    bn = _BatchNormParams(c).double()
+    with torch.no_grad():
+        bn.weight.copy_(0.5 + torch.rand(c)); bn.weight[0] = -0.7
+        bn.bias.copy_(0.3 * torch.randn(c))
+        bn.running_mean.copy_(0.2 * torch.randn(c)); bn.running_var.copy_(0.5 + torch.rand(c))
+    bn.train(training)
+    rm0, rv0 = bn.running_mean.clone(), bn.running_var.clone()
+    L = engine.Layer(engine.C3IN, "t", c, c, 0, 1, bn=bn, gi=2, bti=3)
+    tensors = [None, bias, bn.weight, bn.bias]
+
+    # reference: torch batch_norm on the TRUE conv output (with bias), ReLU, upstream gradient g
+    x = (y_nobias + bias[None, :, None]).clone().requires_grad_(True)
+    gam, bet = bn.weight.detach().clone().requires_grad_(True), bn.bias.detach().clone().requires_grad_(True)
+    rm, rv = rm0.clone(), rv0.clone()
+    out_ref = F.relu(F.batch_norm(x, rm, rv, gam, bet, training=training, momentum=0.1, eps=1e-5))
+    g = torch.randn_like(out_ref)
+    out_ref.backward(g)
+
+    kb, k2b2, aux = engine._bn_forward_tables(L, tensors, stats, shift.float(), float(S))
+    kb, k2b2 = kb.double(), k2b2.double()
+    pre = kb[..., 0, None] * y_s + kb[..., 1, None]                  # vs_affine_relu_apply
+    assert torch.allclose(pre.clamp_min(0), out_ref.detach(), rtol=1e-5, atol=1e-5)
+    assert torch.allclose(bn.running_mean, rm, rtol=1e-6, atol=1e-6) and torch.allclose(bn.running_var, rv, rtol=1e-6, atol=1e-6)
+    assert int(bn.num_batches_tracked) == (1 if training else 0)
+    gm = g * (pre > 0)                                               # vs_affine_relu_bwd_reduce
+    xhat = k2b2[..., 0, None] * y_s + k2b2[..., 1, None]
+    sums = torch.stack([gm.sum(-1), (gm * xhat).sum(-1)], -1)
+    coef, dgamma, dbeta, dbias = engine._bn_backward_tables(L, sums, kb.float(), k2b2.float(), aux, float(S), training)
+    coef = coef.double()
+    dy = coef[..., 0, None] * gm + coef[..., 1, None] + coef[..., 2, None] * y_s      # vs_affine_relu_bwd_apply
+    assert torch.allclose(dy, x.grad, rtol=1e-4, atol=1e-6)
+    assert torch.allclose(dgamma.double(), gam.grad, rtol=1e-5, atol=1e-6) and torch.allclose(dbeta.double(), bet.grad, rtol=1e-5, atol=1e-6)
+    # conv bias: x = y_nobias + bias, so dbias = sum over (n, voxels) of dx -- exactly zero under batch statistics
+    assert torch.allclose(dbias.double(), x.grad.sum((0, 2)), rtol=1e-4, atol=1e-5)
