@@ -80,3 +80,25 @@ def test_source_unwired_method_and_missing_gpu_are_errors():
     if not torch.cuda.is_available():
         with pytest.raises(SystemExit, match="no CUDA device"):
             src.main(shlex.split(SEG_NIH) + ["--synthetic", "2"])
+
+
+# ---- bench.py accounting ------------------------------------------------------------------------------------------------
+def test_bench_kernel_cost_covers_the_hot_entry_points():
+    """bench.py's roofline object is built from kernel_cost(entry point, integer-argument key): every entry point that can
+    be the dominant kernel of a mode must have an algorithmic (flops, bytes) model -- a zero here would silently report
+    frac = 0.  Keys as the C-ABI calls produce them (integer arguments in call order)."""
+    import bench
+    vox = 2 * 96 ** 3
+    fl, by = bench.kernel_cost("vs_conv3x3x3_tc_kdn_ex", (1, 2, 96, 96, 96, 8, 8))
+    assert fl == 2.0 * 27 * 8 * 8 * vox and by == vox * 16 * 2
+    fl, by = bench.kernel_cost("vs_conv3x3x3_tc_kdn_planar", (1, 2, 96, 96, 96, 8))
+    assert fl == 2.0 * 27 * 8 * 8 * vox and by == vox * (16 + 8)
+    fl, by = bench.kernel_cost("vs_conv3x3x3_fprop", (1, 1, 0, 0, 1, 2, 24, 24, 24, 32, 32))
+    assert fl == 2.0 * 27 * 32 * 32 * 2 * 24 ** 3 and by == 2 * 24 ** 3 * 64 * 2
+    fl, by = bench.kernel_cost("vs_conv3x3x3_wgrad", (1, 0, 0, 1, 2, 48, 48, 48, 16, 16))
+    assert fl > 0 and by == 2 * 48 ** 3 * 32 * 2
+    for name in ("vs_k2s2_gather_tc", "vs_k2s2_scatter_tc"):
+        fl, by = bench.kernel_cost(name, (2, 48, 48, 48, 16, 16))
+        assert fl == 2.0 * 8 * 16 * 16 * 2 * 48 ** 3 and by == 2 * 48 ** 3 * (16 + 128) * 2
+    assert bench.kernel_cost("vs_inorm_relu_apply", (1, 2, 884736, 8))[1] == 2.0 * 2 * 884736 * 8 * 2
+    assert set(bench.MODES) == {"joint", "seg", "vae", "joint_ttt"}
