@@ -305,11 +305,11 @@ class JointTrainer(object):
         # (VAESEG_SAMPLE_PARALLEL=1); parity-tested (tests/test_models_gpu.py runs the joint step both ways).
         self.sample_parallel = os.environ.get("VAESEG_SAMPLE_PARALLEL", "0") == "1"
         self._chain_streams = {}
-        # data parallel.  Default: ONE all-reduce of the 9.1 MB gradient arena after backward.  VAESEG_DDP_OVERLAP=1 (or
-        # trainer.ddp_overlap = True before the first step) selects the bucketed all-reduce overlapped with backward
-        # (BucketedAllReduce; captured inside the CUDA graph of the step).  MEASURED on 2 x B200, 2 x 96^3 per GPU:
-        # 657.6 / 648.6 vol/s plain (two runs) vs 648.7 vol/s overlapped -- inside the run-to-run noise: the payload
-        # costs ~40 us on NVLink (< 1 % of the step), so the simpler plain path stays the default.
+        # data parallel.  The 9.1 MB gradient arena is all-reduced in `ddp_buckets` buckets, each issued as soon as its
+        # parameters' gradients are complete and overlapped with the rest of backward (BucketedAllReduce; captured
+        # inside the CUDA graph of the step).  VAESEG_DDP_OVERLAP=0 (or trainer.ddp_overlap = False before the first
+        # step) selects ONE all-reduce after backward.  Round 1, 2 x B200: no difference outside the noise (657.6 / 648.6
+        # plain vs 648.7 overlapped: the payload costs ~40 us on NVLink, < 1 % of the step).
         # NOTE for callers: destroy the captured graph (trainer.release_graph()) before tearing the process group down --
         # destroy_process_group() does not return while a live CUDA graph still holds NCCL kernels (observed, B200 x2).
         self.ddp_buckets = int(os.environ.get("VAESEG_DDP_BUCKETS", "3"))
