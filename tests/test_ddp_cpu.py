@@ -123,3 +123,39 @@ def test_bucketed_allreduce_covers_every_element_once():
     assert len(bounds) >= 2
     # the last bucket went out before the first parameters were ready (overlap), everything by the end
     assert outs[0]["launched"][0] <= outs[0]["launched"][-1] and outs[0]["launched"][-2] >= 1
+
+
+def _validate_worker(rank, world, port, outdir):
+    """JointTrainer.validate's host logic (sharding cases[rank::world], ONE all-reduce of the two sums and the count at
+    the end, nothing per case) with the per-case GPU work stubbed out: an odd number of cases over two ranks."""
+    import types
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        tr = object.__new__(ts.JointTrainer)                       # no CUDA modules: only validate() itself is under test
+        tr.arena = types.SimpleNamespace(data=torch.zeros(1))
+        tr._val_graphs = {}
+        calls = []
+
+        def fake_case_scores(finetune, img, label, val_finetune, lr_finetune):
+            calls.append(float(img))
+            return torch.stack([img * 0.5, img * 0.25])             # (finetuned, student) "scores" of case `img`
+        tr._case_scores = fake_case_scores
+        cases = [(torch.tensor(float(i + 1)), torch.zeros(())) for i in range(3)]
+        out = tr.validate(cases, finetune=None, val_finetune=1, graphed=False)
+        torch.save({"out": out, "calls": calls}, os.path.join(outdir, "val%d.pt" % rank))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_validation_shards_an_odd_case_count_without_hanging():
+    world = 2
+    with tempfile.TemporaryDirectory() as outdir:
+        mp.spawn(_validate_worker, args=(world, _free_port(), outdir), nprocs=world, join=True)
+        outs = [torch.load(os.path.join(outdir, "val%d.pt" % r)) for r in range(world)]
+    assert outs[0]["calls"] == [1.0, 3.0] and outs[1]["calls"] == [2.0]          # cases[rank::world]
+    for o in outs:                                                               # both ranks report the GLOBAL means
+        assert abs(o["out"]["dsc"] - 0.5 * (1 + 2 + 3) / 3) < 1e-6
+        assert abs(o["out"]["dsc_noft"] - 0.25 * (1 + 2 + 3) / 3) < 1e-6
+    assert [round(x, 6) for x in outs[0]["out"]["scores"]] == [0.5, 1.5] and [round(x, 6) for x in outs[1]["out"]["scores"]] == [1.0]
